@@ -1,0 +1,437 @@
+// capi.cu — extern "C" entry points of libedvr_b200.so (see include/edvr_b200.h).
+// Host side only validates arguments, fills parameter blocks and launches; no allocation,
+// no synchronisation, no global mutable state (the error text is thread-local).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/edvr_b200.h"
+#include "common.cuh"
+#include "conv_igemm.cuh"
+#include "dcn_backward.cuh"
+#include "dcn_fused.cuh"
+#include "elementwise.cuh"
+#include "epilogue.cuh"
+#include "selftest.cuh"
+
+using namespace eb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(EB_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+    return EB_OK;
+}
+
+int num_sms() {
+    static int n = 0;   // benign race: every thread computes the same value
+    if (n == 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n = v > 0 ? v : 148;
+    }
+    return n;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int grid_1d(long long work_items, int block) {
+    long long b = (work_items + block - 1) / block;
+    long long cap = static_cast<long long>(num_sms()) * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+int fill_epi(const eb_epilogue_t* e, int H, int W, int cout_packed, EpiParams* o) {
+    if (e == nullptr) return fail(EB_ERR_NULLPTR, "epilogue is NULL");
+    o->bias = e->bias;
+    o->act = e->act;
+    o->H = H;
+    o->W = W;
+    o->res16 = static_cast<const __half*>(e->res16);
+    o->res32 = e->res32;
+    o->res_pix_stride = e->res_pix_stride;
+    o->res_ch_off = e->res_ch_off;
+    o->out16 = static_cast<__half*>(e->out16);
+    o->out16_pix_stride = e->out16_pix_stride;
+    o->out16_ch_off = e->out16_ch_off;
+    o->out32 = e->out32;
+    o->out32_pix_stride = e->out32_pix_stride;
+    o->out32_ch_off = e->out32_ch_off;
+    o->out_nchw = e->out_nchw;
+    o->nchw_C = e->nchw_C;
+    o->out_mode = e->out_mode;
+    o->absmean_acc = e->absmean_acc;
+    if (e->act < EB_ACT_NONE || e->act > EB_ACT_SIGMOID) return fail(EB_ERR_UNSUPPORTED, "act %d", e->act);
+    if (e->out_mode < EB_OUT_SAME || e->out_mode > EB_OUT_STRIDE2)
+        return fail(EB_ERR_UNSUPPORTED, "out_mode %d", e->out_mode);
+    if (!e->out16 && !e->out32 && !e->out_nchw) return fail(EB_ERR_NULLPTR, "no output pointer");
+    if (e->out_mode != EB_OUT_SAME && (!e->out16 || e->out32 || e->out_nchw || e->res16 || e->res32))
+        return fail(EB_ERR_UNSUPPORTED, "pixel-shuffle / stride-2 stores support a single fp16 output, no residual");
+    if (e->out16 && (!al16(e->out16) || e->out16_pix_stride % 8 || e->out16_ch_off % 8))
+        return fail(EB_ERR_ALIGNMENT, "out16 view must be 16-byte aligned");
+    if (e->out32 && (!al16(e->out32) || e->out32_pix_stride % 4 || e->out32_ch_off % 4))
+        return fail(EB_ERR_ALIGNMENT, "out32 view must be 16-byte aligned");
+    if ((e->res16 && (!al16(e->res16) || e->res_pix_stride % 8 || e->res_ch_off % 8)) ||
+        (e->res32 && (!al16(e->res32) || e->res_pix_stride % 4 || e->res_ch_off % 4)))
+        return fail(EB_ERR_ALIGNMENT, "residual view must be 16-byte aligned");
+    if (e->res16 && e->res32) return fail(EB_ERR_UNSUPPORTED, "one residual at most");
+    if (e->out_mode == EB_OUT_PIXSHUF2 && cout_packed % 32) return fail(EB_ERR_INVALID_SHAPE, "pixel shuffle needs Cout %% 32 == 0");
+    return EB_OK;
+}
+
+template <typename KernelT>
+int set_smem(KernelT k, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return fail(EB_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e));
+    return EB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eb_version(void) { return 100; }
+const char* eb_last_error(void) { return g_err; }
+
+int eb_selftest_umma(const void* A, const void* B, float* D, int N, int K, int variant, void* stream) {
+    if (!A || !B || !D) return fail(EB_ERR_NULLPTR, "selftest: null pointer");
+    if (N < 32 || N > 256 || N % 32 || K < 16 || K % 16) return fail(EB_ERR_INVALID_SHAPE, "selftest: N=%d K=%d", N, K);
+    const int smem = (K / 8) * (128 + N) * 16;
+    if (smem > 200 * 1024) return fail(EB_ERR_INVALID_SHAPE, "selftest: K too large");
+    if (int rc = set_smem(selftest_umma_kernel, smem)) return rc;
+    selftest_umma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(A), static_cast<const __half*>(B), D, N, K, variant);
+    return check_launch("selftest_umma");
+}
+
+size_t eb_packed_weight_bytes(int cin, int ktaps, int BN, int n_tiles_n) {
+    return static_cast<size_t>(n_tiles_n) * BN * cin * ktaps * 2;
+}
+
+int eb_pack_weight(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN,
+                   int n_tiles_n, int tap_major, void* wpack, void* stream) {
+    if (!w || !wpack) return fail(EB_ERR_NULLPTR, "pack_weight: null pointer");
+    if (cin % 64 || BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || ktaps < 1 || cout < 1)
+        return fail(EB_ERR_INVALID_SHAPE, "pack_weight: cin=%d BN=%d tiles=%d taps=%d", cin, BN, n_tiles_n, ktaps);
+    if (!row_map && cout > BN * n_tiles_n) return fail(EB_ERR_INVALID_SHAPE, "pack_weight: cout exceeds packed rows");
+    const long long groups = static_cast<long long>(n_tiles_n) * (cin / 64) * ktaps * 8 * BN;
+    pack_weight_kernel<<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, cout, cin, ktaps, row_map, BN, n_tiles_n, tap_major, static_cast<__half*>(wpack));
+    return check_launch("pack_weight");
+}
+
+int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack, int BN,
+              int n_tiles_n, const eb_epilogue_t* epi, void* stream) {
+    if (!srcs || !wpack) return fail(EB_ERR_NULLPTR, "conv2d: null pointer");
+    if (nsrc < 1 || nsrc > 2) return fail(EB_ERR_UNSUPPORTED, "conv2d: nsrc=%d", nsrc);
+    if (ksize != 1 && ksize != 3) return fail(EB_ERR_UNSUPPORTED, "conv2d: ksize=%d", ksize);
+    if (N < 0 || H < 1 || W < 1) return fail(EB_ERR_INVALID_SHAPE, "conv2d: N=%d H=%d W=%d", N, H, W);
+    if (BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || BN * n_tiles_n > CV_MAX_COUT)
+        return fail(EB_ERR_INVALID_SHAPE, "conv2d: BN=%d n_tiles_n=%d", BN, n_tiles_n);
+    if (!al16(wpack)) return fail(EB_ERR_ALIGNMENT, "conv2d: wpack must be 16-byte aligned");
+    ConvParams P;
+    memset(&P, 0, sizeof(P));
+    for (int i = 0; i < nsrc; ++i) {
+        const eb_src_t& s = srcs[i];
+        if (!s.ptr) return fail(EB_ERR_NULLPTR, "conv2d: src %d null", i);
+        if (s.C < 64 || s.C % 64) return fail(EB_ERR_INVALID_SHAPE, "conv2d: src %d C=%d (multiple of 64)", i, s.C);
+        if (!al16(s.ptr) || s.pix_stride % 8 || s.ch_off % 8 || s.pix_stride < s.C + s.ch_off)
+            return fail(EB_ERR_ALIGNMENT, "conv2d: src %d view (stride %d, off %d)", i, s.pix_stride, s.ch_off);
+        if (s.div < 1) return fail(EB_ERR_INVALID_SHAPE, "conv2d: src %d div=%d", i, s.div);
+        P.src[i].ptr = static_cast<const __half*>(s.ptr);
+        P.src[i].C = s.C; P.src[i].pix_stride = s.pix_stride; P.src[i].ch_off = s.ch_off;
+        P.src[i].div = s.div; P.src[i].mul = s.mul; P.src[i].keep = s.keep; P.src[i].add = s.add;
+    }
+    P.nsrc = nsrc; P.N = N; P.H = H; P.W = W; P.taps = ksize * ksize; P.BN = BN; P.n_tiles_n = n_tiles_n;
+    P.wpack = static_cast<const __half*>(wpack);
+    if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
+    if (N == 0) return EB_OK;
+    const long long tiles = static_cast<long long>(N) * ((H + 15) / 16) * ((W + 15) / 16) * n_tiles_n;
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ksize == 3) {
+        if (int rc = set_smem(conv_igemm_kernel<1>, CV_SMEM_BYTES)) return rc;
+        conv_igemm_kernel<1><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    } else {
+        if (int rc = set_smem(conv_igemm_kernel<0>, CV_SMEM_BYTES)) return rc;
+        conv_igemm_kernel<0><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    }
+    return check_launch("conv_igemm");
+}
+
+static int launch_dcn(DcnParams& P, cudaStream_t st) {
+    const long long tiles = static_cast<long long>(P.N) * ((P.Ho + DC_TILE_H - 1) / DC_TILE_H) *
+                            ((P.Wo + DC_TILE_W - 1) / DC_TILE_W) * P.n_tiles_n;
+    if (tiles == 0) return EB_OK;
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    if (P.off_mode == OFF_NCHW_F32) {
+        if (int rc = set_smem(dcn_fused_kernel<OFF_NCHW_F32>, DC_SMEM_BYTES)) return rc;
+        dcn_fused_kernel<OFF_NCHW_F32><<<grid, DC_THREADS, DC_SMEM_BYTES, st>>>(P);
+    } else {
+        if (int rc = set_smem(dcn_fused_kernel<OFF_PACK_F16>, DC_SMEM_BYTES)) return rc;
+        dcn_fused_kernel<OFF_PACK_F16><<<grid, DC_THREADS, DC_SMEM_BYTES, st>>>(P);
+    }
+    return check_launch("dcn_fused");
+}
+
+int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
+                const void* offpack, int offpack_pix_stride, const void* wpack, int BN, int n_tiles_n,
+                const eb_epilogue_t* epi, void* stream) {
+    if (!x || !offpack || !wpack) return fail(EB_ERR_NULLPTR, "dcn_nhwc: null pointer");
+    if (N < 0 || H < 1 || W < 1 || C < 64 || C % 64 || dg < 1 || C % dg || (C / dg) % 8)
+        return fail(EB_ERR_INVALID_SHAPE, "dcn_nhwc: N=%d H=%d W=%d C=%d dg=%d", N, H, W, C, dg);
+    if (BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || BN * n_tiles_n > DC_MAX_COUT)
+        return fail(EB_ERR_INVALID_SHAPE, "dcn_nhwc: BN=%d n_tiles_n=%d", BN, n_tiles_n);
+    if (!al16(x) || !al16(offpack) || !al16(wpack) || x_pix_stride % 8 || x_ch_off % 8 ||
+        offpack_pix_stride % 8 || offpack_pix_stride < dg * 32)
+        return fail(EB_ERR_ALIGNMENT, "dcn_nhwc: views must be 16-byte aligned");
+    DcnParams P;
+    memset(&P, 0, sizeof(P));
+    P.x = static_cast<const __half*>(x); P.x_pix_stride = x_pix_stride; P.x_ch_off = x_ch_off;
+    P.N = N; P.H = H; P.W = W; P.C = C; P.Ho = H; P.Wo = W;
+    P.kh = 3; P.kw = 3; P.stride = 1; P.pad = 1; P.dil = 1; P.dg = dg; P.cpg = C / dg;
+    P.off_mode = OFF_PACK_F16;
+    P.offpack = static_cast<const __half*>(offpack); P.offpack_pix_stride = offpack_pix_stride;
+    P.wpack = static_cast<const __half*>(wpack); P.BN = BN; P.n_tiles_n = n_tiles_n;
+    if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
+    if (P.epi.out_mode != OUT_SAME) return fail(EB_ERR_UNSUPPORTED, "dcn_nhwc: out_mode");
+    return launch_dcn(P, static_cast<cudaStream_t>(stream));
+}
+
+// ---- reference-layout operator -----------------------------------------------------------
+static inline size_t up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+static inline int cout_tiles(int Cout, int* BN) {
+    int bn = Cout >= 128 ? 128 : ((Cout + 31) / 32) * 32;
+    *BN = bn;
+    return (Cout + bn - 1) / bn;
+}
+
+size_t eb_mdcn_forward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw) {
+    int BN;
+    const int nt = cout_tiles(Cout, &BN);
+    return up256(static_cast<size_t>(N) * H * W * C * 2) + up256(eb_packed_weight_bytes(C, kh * kw, BN, nt)) +
+           up256(static_cast<size_t>(BN) * nt * 4);
+}
+
+int eb_mdcn_forward(const float* x, const float* offset, const float* mask, const float* weight,
+                    const float* bias, float* out, int N, int C, int H, int W, int Cout, int kh, int kw,
+                    int stride, int pad, int dil, int groups, int dg, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    if (!x || !offset || !mask || !weight || !out) return fail(EB_ERR_NULLPTR, "mdcn_forward: null pointer");
+    if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || stride < 1 || pad < 0 || dil < 1 ||
+        groups < 1 || dg < 1 || C % dg || C % groups || Cout % groups)
+        return fail(EB_ERR_INVALID_SHAPE, "mdcn_forward: invalid shape");
+    if (groups != 1) return fail(EB_ERR_UNSUPPORTED, "mdcn_forward: groups=%d (only 1; EDVR uses 1)", groups);
+    if (C % 64 || (C / dg) % 8) return fail(EB_ERR_UNSUPPORTED, "mdcn_forward: C=%d dg=%d (C %% 64 == 0, (C/dg) %% 8 == 0)", C, dg);
+    if (Cout > DC_MAX_COUT) return fail(EB_ERR_UNSUPPORTED, "mdcn_forward: Cout=%d > %d", Cout, DC_MAX_COUT);
+    const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
+    const int Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
+    if (Ho < 1 || Wo < 1) return fail(EB_ERR_INVALID_SHAPE, "mdcn_forward: empty output");
+    if (workspace_bytes < eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw) || (!workspace && N > 0))
+        return fail(EB_ERR_WORKSPACE, "mdcn_forward: workspace %zu < %zu", workspace_bytes,
+                    eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw));
+    if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "mdcn_forward: workspace must be 16-byte aligned");
+    if (N == 0) return EB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int BN;
+    const int nt = cout_tiles(Cout, &BN);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    __half* x16 = reinterpret_cast<__half*>(ws);
+    ws += up256(static_cast<size_t>(N) * H * W * C * 2);
+    __half* wpack = reinterpret_cast<__half*>(ws);
+    ws += up256(eb_packed_weight_bytes(C, kh * kw, BN, nt));
+    float* bpack = reinterpret_cast<float*>(ws);
+
+    {
+        dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+        nchw_f32_to_nhwc_f16_kernel<<<grid, block, 0, st>>>(x, x16, C, H * W, C, 0);
+        if (int rc = check_launch("nchw_to_nhwc")) return rc;
+    }
+    if (int rc = eb_pack_weight(weight, Cout, C, kh * kw, nullptr, BN, nt, 1, wpack, stream)) return rc;
+    pack_bias_kernel<<<(BN * nt + 127) / 128, 128, 0, st>>>(bias, Cout, nullptr, BN * nt, bpack);
+    if (int rc = check_launch("pack_bias")) return rc;
+
+    DcnParams P;
+    memset(&P, 0, sizeof(P));
+    P.x = x16; P.x_pix_stride = C; P.x_ch_off = 0;
+    P.N = N; P.H = H; P.W = W; P.C = C; P.Ho = Ho; P.Wo = Wo;
+    P.kh = kh; P.kw = kw; P.stride = stride; P.pad = pad; P.dil = dil; P.dg = dg; P.cpg = C / dg;
+    P.off_mode = OFF_NCHW_F32; P.offset = offset; P.mask = mask;
+    P.wpack = wpack; P.BN = BN; P.n_tiles_n = nt;
+    P.epi.bias = bpack; P.epi.act = ACT_NONE; P.epi.H = Ho; P.epi.W = Wo;
+    P.epi.out_nchw = out; P.epi.nchw_C = Cout; P.epi.out_mode = OUT_SAME;
+    return launch_dcn(P, st);
+}
+
+size_t eb_mdcn_backward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int stride,
+                                  int pad, int dil) {
+    (void)N; (void)Cout; (void)stride; (void)pad; (void)dil;
+    // one sample's gcol [C*K][Ho*Wo] fp32 (upper bound: Ho*Wo <= (H+2p)*(W+2p))
+    const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
+    const int Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
+    return up256(static_cast<size_t>(C) * kh * kw * (Ho > 0 ? Ho : 0) * (Wo > 0 ? Wo : 0) * 4);
+}
+
+int eb_mdcn_backward(const float* x, const float* offset, const float* mask, const float* weight,
+                     const float* grad_out, float* grad_x, float* grad_offset, float* grad_mask,
+                     float* grad_weight, float* grad_bias, int N, int C, int H, int W, int Cout, int kh,
+                     int kw, int stride, int pad, int dil, int groups, int dg, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (!x || !offset || !mask || !weight || !grad_out || !grad_x || !grad_offset || !grad_mask || !grad_weight)
+        return fail(EB_ERR_NULLPTR, "mdcn_backward: null pointer");
+    if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || stride < 1 || pad < 0 || dil < 1 ||
+        groups < 1 || dg < 1 || C % dg || C % groups || Cout % groups)
+        return fail(EB_ERR_INVALID_SHAPE, "mdcn_backward: invalid shape");
+    if (groups != 1) return fail(EB_ERR_UNSUPPORTED, "mdcn_backward: groups=%d (only 1; EDVR uses 1)", groups);
+    const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
+    const int Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
+    if (Ho < 1 || Wo < 1) return fail(EB_ERR_INVALID_SHAPE, "mdcn_backward: empty output");
+    if (workspace_bytes < eb_mdcn_backward_workspace(N, C, H, W, Cout, kh, kw, stride, pad, dil) || (!workspace && N > 0))
+        return fail(EB_ERR_WORKSPACE, "mdcn_backward: workspace too small");
+    if (N == 0) return EB_OK;
+    DcnBwdParams P;
+    P.x = x; P.offset = offset; P.mask = mask; P.weight = weight; P.grad_out = grad_out;
+    P.grad_x = grad_x; P.grad_offset = grad_offset; P.grad_mask = grad_mask; P.grad_weight = grad_weight;
+    P.grad_bias = grad_bias; P.gcol = static_cast<float*>(workspace);
+    P.N = N; P.C = C; P.H = H; P.W = W; P.Cout = Cout; P.kh = kh; P.kw = kw; P.stride = stride; P.pad = pad;
+    P.dil = dil; P.dg = dg; P.Ho = Ho; P.Wo = Wo;
+    return dcn_backward_launch(P, static_cast<cudaStream_t>(stream), num_sms());
+}
+
+// ---- layout / elementwise ---------------------------------------------------------------------
+int eb_nchw_f32_to_nhwc_f16(const float* src, void* dst, int N, int C, int H, int W, int dst_pix_stride,
+                            int dst_ch_off, void* stream) {
+    if (!src || !dst) return fail(EB_ERR_NULLPTR, "nchw_to_nhwc: null pointer");
+    if (N < 0 || C < 1 || H < 1 || W < 1 || dst_pix_stride < C + dst_ch_off) return fail(EB_ERR_INVALID_SHAPE, "nchw_to_nhwc");
+    if (N == 0) return EB_OK;
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+    nchw_f32_to_nhwc_f16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, static_cast<__half*>(dst), C, H * W, dst_pix_stride, dst_ch_off);
+    return check_launch("nchw_to_nhwc");
+}
+
+int eb_nhwc_f16_to_nchw_f32(const void* src, int src_pix_stride, int src_ch_off, float* dst, int N, int C,
+                            int H, int W, void* stream) {
+    if (!src || !dst) return fail(EB_ERR_NULLPTR, "nhwc_to_nchw: null pointer");
+    if (N < 0 || C < 1 || H < 1 || W < 1 || src_pix_stride < C + src_ch_off) return fail(EB_ERR_INVALID_SHAPE, "nhwc_to_nchw");
+    if (N == 0) return EB_OK;
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+    nhwc_f16_to_nchw_f32_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(src), dst, C, H * W, src_pix_stride, src_ch_off);
+    return check_launch("nhwc_to_nchw");
+}
+
+int eb_conv_first(const float* x, const float* w, const float* bias, void* out, int N, int H, int W, int Cout,
+                  int out_pix_stride, int act, void* stream) {
+    if (!x || !w || !out) return fail(EB_ERR_NULLPTR, "conv_first: null pointer");
+    if (N < 0 || H < 1 || W < 1 || Cout < 8 || Cout % 8 || Cout > 512 || out_pix_stride % 8 || out_pix_stride < Cout || !al16(out))
+        return fail(EB_ERR_INVALID_SHAPE, "conv_first: shape");
+    if (N == 0) return EB_OK;
+    const int smem = Cout * 28 * 4;
+    if (int rc = set_smem(conv_first_kernel, smem)) return rc;
+    const long long items = static_cast<long long>(N) * H * W * (Cout / 8);
+    conv_first_kernel<<<grid_1d(items, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, w, bias, static_cast<__half*>(out), N, H, W, Cout, out_pix_stride, act);
+    return check_launch("conv_first");
+}
+
+int eb_conv_last(const void* x, int x_pix_stride, const float* w, const float* bias, const float* base,
+                 long long base_img_stride, int scale, float* out, int N, int H, int W, int Cin, void* stream) {
+    if (!x || !w || !base || !out) return fail(EB_ERR_NULLPTR, "conv_last: null pointer");
+    if (N < 0 || H < 1 || W < 1 || Cin < 8 || Cin % 8 || Cin > 512 || x_pix_stride % 8 || x_pix_stride < Cin || !al16(x) ||
+        (scale != 1 && scale != 4) || H % scale || W % scale)
+        return fail(EB_ERR_INVALID_SHAPE, "conv_last: shape");
+    if (N == 0) return EB_OK;
+    const int smem = 27 * Cin * 4;
+    if (int rc = set_smem(conv_last_kernel, smem)) return rc;
+    const long long items = static_cast<long long>(N) * H * W;
+    conv_last_kernel<<<grid_1d(items, 128), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), x_pix_stride, w, bias, base, base_img_stride, scale, out, N, H, W, Cin);
+    return check_launch("conv_last");
+}
+
+static bool view_ok(const void* p, int ps, int co, int C) {
+    return p && al16(p) && ps % 8 == 0 && co % 8 == 0 && C % 8 == 0 && ps >= co + C;
+}
+
+int eb_upsample2x(const void* src, int sps, int sco, void* dst, int dps, int dco, int N, int H, int W, int C,
+                  float mul, const void* add, int aps, int aco, void* stream) {
+    if (!view_ok(src, sps, sco, C) || !view_ok(dst, dps, dco, C) || (add && !view_ok(add, aps, aco, C)))
+        return fail(EB_ERR_ALIGNMENT, "upsample2x: bad view");
+    if (N < 0 || H < 1 || W < 1) return fail(EB_ERR_INVALID_SHAPE, "upsample2x: shape");
+    if (N == 0) return EB_OK;
+    const long long items = static_cast<long long>(N) * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<grid_1d(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(src), sps, sco, static_cast<__half*>(dst), dps, dco, N, H, W, C, mul,
+        static_cast<const __half*>(add), aps, aco);
+    return check_launch("upsample2x");
+}
+
+int eb_pool_max_avg(const void* src, int sps, int sco, void* dst, int dps, int dco, int N, int H, int W, int C,
+                    void* stream) {
+    if (!view_ok(src, sps, sco, C) || !view_ok(dst, dps, dco, 2 * C)) return fail(EB_ERR_ALIGNMENT, "pool: bad view");
+    if (N < 0 || H < 1 || W < 1) return fail(EB_ERR_INVALID_SHAPE, "pool: shape");
+    if (N == 0) return EB_OK;
+    const long long items = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    pool_max_avg_kernel<<<grid_1d(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(src), sps, sco, static_cast<__half*>(dst), dps, dco, N, H, W, C);
+    return check_launch("pool_max_avg");
+}
+
+int eb_tsa_temporal(const void* emb, const void* emb_ref, const void* aligned, void* dst, int B, int T, int H,
+                    int W, int C, void* stream) {
+    if (!emb || !emb_ref || !aligned || !dst) return fail(EB_ERR_NULLPTR, "tsa_temporal: null pointer");
+    const int lpp = C / 8;
+    if (B < 0 || T < 1 || H < 1 || W < 1 || C % 8 || lpp < 1 || lpp > 32 || (lpp & (lpp - 1)))
+        return fail(EB_ERR_INVALID_SHAPE, "tsa_temporal: C=%d must be 8*2^k <= 256", C);
+    if (!al16(emb) || !al16(emb_ref) || !al16(aligned) || !al16(dst)) return fail(EB_ERR_ALIGNMENT, "tsa_temporal");
+    if (B == 0) return EB_OK;
+    const long long items = static_cast<long long>(B) * H * W * lpp;
+    tsa_temporal_kernel<<<grid_1d(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(emb), static_cast<const __half*>(emb_ref), static_cast<const __half*>(aligned),
+        static_cast<__half*>(dst), B, T, H * W, C);
+    return check_launch("tsa_temporal");
+}
+
+int eb_tsa_modulate(const void* feat, int fps, int fco, const void* attn, const void* attn_add, void* out16,
+                    float* out32, int npix, int C, void* stream) {
+    if (!view_ok(feat, fps, fco, C) || !attn || !attn_add || (!out16 && !out32) || !al16(attn) || !al16(attn_add) ||
+        (out16 && !al16(out16)) || (out32 && !al16(out32)))
+        return fail(EB_ERR_ALIGNMENT, "tsa_modulate: bad view");
+    if (npix < 0) return fail(EB_ERR_INVALID_SHAPE, "tsa_modulate: npix");
+    if (npix == 0) return EB_OK;
+    const long long items = static_cast<long long>(npix) * (C / 8);
+    tsa_modulate_kernel<<<grid_1d(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(feat), fps, fco, static_cast<const __half*>(attn),
+        static_cast<const __half*>(attn_add), static_cast<__half*>(out16), out32, npix, C);
+    return check_launch("tsa_modulate");
+}
+
+int eb_add(const void* a, int aps, int aco, const void* b, int bps, int bco, void* dst, int dps, int dco, int npix,
+           int C, void* stream) {
+    if (!view_ok(a, aps, aco, C) || !view_ok(b, bps, bco, C) || !view_ok(dst, dps, dco, C))
+        return fail(EB_ERR_ALIGNMENT, "add: bad view");
+    if (npix < 0) return fail(EB_ERR_INVALID_SHAPE, "add: npix");
+    if (npix == 0) return EB_OK;
+    const long long items = static_cast<long long>(npix) * (C / 8);
+    add_kernel<<<grid_1d(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(a), aps, aco, static_cast<const __half*>(b), bps, bco, static_cast<__half*>(dst),
+        dps, dco, npix, C);
+    return check_launch("add");
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+// dcn_fused.cuh — DCNv2 (modulated deformable convolution) forward, one fused kernel.
+//
+// Replaces modulated_deform_conv_cuda_forward + modulated_deformable_im2col_gpu_kernel + the
+// per-sample addmm_ + the bias pass
+// (/root/reference/basicsr/models/ops/dcn/src/deform_conv_cuda.cpp:490-569,
+//  deform_conv_cuda_kernel.cu:467-497,570-633): the im2col "columns" matrix never exists in
+// HBM.  For each tile of 16x8 output pixels, eight gather warps bilinear-sample the NHWC fp16
+// input (16 B = 8 channels per corner load), apply the modulation mask and write the result
+// straight into the shared-memory A operand (no-swizzle K-major planes, common.cuh); one
+// thread issues tcgen05.mma against the pre-packed weights (B operand, bulk async copies);
+// the fp32 accumulator lives in TMEM and is drained by four epilogue warps (bias, activation,
+// NHWC fp16 and/or NCHW fp32 stores).  K is walked tap-major: stage = (tap, 64-channel chunk).
+//
+// Sampling semantics (bit-for-bit the reference's decisions, fp32 coordinate math):
+//   h_im = ho*stride - pad + i*dil + dh;  sample iff h_im > -1 && w_im > -1 && h_im < H && w_im < W
+//   corners outside [0,H-1]x[0,W-1] contribute 0; floor() picks the low corner.
+#pragma once
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace eb {
+
+constexpr int DC_STAGES = 6;
+constexpr int DC_A_BYTES = 128 * 128;    // 8 planes x 128 rows x 16 B
+constexpr int DC_B_BYTES = 128 * 128;    // BN(<=128) rows x 64 ch x 2 B
+constexpr int DC_THREADS = 448;          // 14 warps
+constexpr int DC_GATHER_THREADS = 256;
+constexpr int DC_MAX_COUT = 512;
+constexpr int DC_SMEM_BYTES = DC_STAGES * (DC_A_BYTES + DC_B_BYTES) + DC_MAX_COUT * 4 + 256;
+constexpr int DC_TILE_H = 16, DC_TILE_W = 8;
+
+enum : int { OFF_NCHW_F32 = 0, OFF_PACK_F16 = 1 };
+
+struct DcnParams {
+    const __half* x;          // NHWC fp16 [N][H][W][C] view
+    int x_pix_stride, x_ch_off;
+    int N, H, W, C;
+    int Ho, Wo;
+    int kh, kw, stride, pad, dil;
+    int dg, cpg;              // deformable groups, channels per group (multiple of 8)
+    int off_mode;
+    const float* offset;      // OFF_NCHW_F32: [N][dg*2*K][Ho][Wo]   (reference layout)
+    const float* mask;        //               [N][dg*K][Ho][Wo]
+    const __half* offpack;    // OFF_PACK_F16: [N][Ho][Wo][dg*32]: per group 18 offsets, 9 masks, 5 pad
+    int offpack_pix_stride;
+    const __half* wpack;      // [n_tile][tap][chunk][kc=8][BN][8] fp16
+    int BN, n_tiles_n;
+    EpiParams epi;            // epi.H/W == Ho/Wo
+};
+
+struct DcnCorner {
+    float w[4];
+    const __half* base;   // address of (h_low, w_low), channel 0 of the view
+    int dW;               // element offsets of the 4 corners: 0, dx, dy, dy+dx
+    int dH;
+    unsigned valid;       // bit c set if corner c contributes
+};
+
+template <int OFFMODE>
+__device__ __forceinline__ DcnCorner dcn_corner(const DcnParams& P, int img, int ho, int wo,
+                                                bool pix_valid, int g, int tap) {
+    DcnCorner c;
+    c.valid = 0;
+    c.base = P.x;
+    c.dW = P.x_pix_stride;
+    c.dH = P.W * P.x_pix_stride;
+    c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0.f;
+    if (!pix_valid) return c;
+    const int K = P.kh * P.kw;
+    float dh, dw, mk;
+    if (OFFMODE == OFF_NCHW_F32) {
+        const size_t plane = static_cast<size_t>(P.Ho) * P.Wo;
+        const size_t pix = static_cast<size_t>(ho) * P.Wo + wo;
+        const float* ob = P.offset + (static_cast<size_t>(img) * P.dg + g) * 2 * K * plane + pix;
+        dh = __ldg(ob + static_cast<size_t>(2 * tap) * plane);
+        dw = __ldg(ob + static_cast<size_t>(2 * tap + 1) * plane);
+        mk = __ldg(P.mask + ((static_cast<size_t>(img) * P.dg + g) * K + tap) * plane + pix);
+    } else {
+        const __half* rec = P.offpack +
+                            ((static_cast<size_t>(img) * P.Ho + ho) * P.Wo + wo) * P.offpack_pix_stride +
+                            g * 32;
+        const __half2 o = *reinterpret_cast<const __half2*>(rec + 2 * tap);
+        dh = __low2float(o);
+        dw = __high2float(o);
+        mk = __half2float(rec[18 + tap]);
+    }
+    const int ki = tap / P.kw, kj = tap - ki * P.kw;
+    const float h_im = static_cast<float>(ho * P.stride - P.pad + ki * P.dil) + dh;
+    const float w_im = static_cast<float>(wo * P.stride - P.pad + kj * P.dil) + dw;
+    if (!(h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(P.H) && w_im < static_cast<float>(P.W)))
+        return c;
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    const int hl = static_cast<int>(hf), wl = static_cast<int>(wf);
+    const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+    c.w[0] = hh * hw * mk; c.w[1] = hh * lw * mk; c.w[2] = lh * hw * mk; c.w[3] = lh * lw * mk;
+    const bool t = hl >= 0, b = hl + 1 <= P.H - 1, l = wl >= 0, r = wl + 1 <= P.W - 1;
+    c.valid = (t && l ? 1u : 0u) | (t && r ? 2u : 0u) | (b && l ? 4u : 0u) | (b && r ? 8u : 0u);
+    c.base = P.x + P.x_ch_off +
+             ((static_cast<long long>(img) * P.H + hl) * P.W + wl) * static_cast<long long>(P.x_pix_stride);
+    return c;
+}
+
+__device__ __forceinline__ void dcn_blend8(float (&acc)[8], uint4 u, float w) {
+    const float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
+    acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
+    acc[2] = fmaf(w, b.x, acc[2]); acc[3] = fmaf(w, b.y, acc[3]);
+    acc[4] = fmaf(w, c.x, acc[4]); acc[5] = fmaf(w, c.y, acc[5]);
+    acc[6] = fmaf(w, d.x, acc[6]); acc[7] = fmaf(w, d.y, acc[7]);
+}
+
+template <int OFFMODE>
+__global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* a_smem = smem;
+    uint8_t* b_smem = smem + DC_STAGES * DC_A_BYTES;
+    float* bias_s = reinterpret_cast<float*>(b_smem + DC_STAGES * DC_B_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + DC_MAX_COUT);
+    uint64_t* full = bars;                       // [S]  256 gather arrivals + 1 expect_tx
+    uint64_t* empty = bars + DC_STAGES;          // [S]
+    uint64_t* acc_full = bars + 2 * DC_STAGES;   // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (P.Wo + DC_TILE_W - 1) / DC_TILE_W;
+    const int tiles_y = (P.Ho + DC_TILE_H - 1) / DC_TILE_H;
+    const int total_tiles = P.N * tiles_y * tiles_x * P.n_tiles_n;
+    const int nchunks = P.C / 64;
+    const int K = P.kh * P.kw;
+    const int nstages = K * nchunks;
+    const uint32_t b_bytes = static_cast<uint32_t>(P.BN) * 128u;
+
+    const int cout_packed = P.BN * P.n_tiles_n;
+    for (int i = threadIdx.x; i < cout_packed; i += blockDim.x)
+        bias_s[i] = P.epi.bias ? P.epi.bias[i] : 0.f;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < DC_STAGES; ++i) { mbar_init(&full[i], DC_GATHER_THREADS + 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= B producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % P.n_tiles_n;
+                const uint8_t* w = reinterpret_cast<const uint8_t*>(P.wpack) +
+                                   static_cast<size_t>(nt) * nstages * b_bytes;
+                for (int st = 0; st < nstages; ++st, ++it) {
+                    const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full[s], b_bytes);
+                    bulk_g2s(b_smem + s * DC_B_BYTES, w + static_cast<size_t>(st) * b_bytes, b_bytes, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, P.BN);
+            const uint32_t lbo_b = static_cast<uint32_t>(P.BN) * 16u;
+            uint32_t it = 0, acc_it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+                const uint32_t ab = acc_it & 1u;
+                mbar_wait(&acc_empty[ab], ((acc_it >> 1) & 1u) ^ 1u);
+                tc_fence_after_sync();
+                const uint32_t d = tmem_base + ab * 128u;
+                for (int st = 0; st < nstages; ++st, ++it) {
+                    const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_base = smem_u32(a_smem + s * DC_A_BYTES);
+                    const uint32_t b_base = smem_u32(b_smem + s * DC_B_BYTES);
+#pragma unroll
+                    for (int k16 = 0; k16 < 4; ++k16) {
+                        const uint64_t ad = umma_desc_nosw(a_base + k16 * 2 * 2048, 2048, 128);
+                        const uint64_t bd = umma_desc_nosw(b_base + k16 * 2 * lbo_b, lbo_b, 128);
+                        umma_f16(d, ad, bd, idesc, (st | k16) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[ab]);
+            }
+        }
+    } else if (warp < 6) {
+        // ================= epilogue: warps 2..5 -> TMEM lane quarters 2,3,0,1
+        const int q = warp & 3;
+        uint32_t acc_it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+            const int nt = tile % P.n_tiles_n, pt = tile / P.n_tiles_n;
+            const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
+            const uint32_t ab = acc_it & 1u;
+            mbar_wait(&acc_full[ab], (acc_it >> 1) & 1u);
+            tc_fence_after_sync();
+            const int y = ty * DC_TILE_H + 4 * q + (lane >> 3);
+            const int x = tx * DC_TILE_W + (lane & 7);
+            const bool valid = (y < P.Ho) && (x < P.Wo);
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 128u;
+#pragma unroll 1
+            for (int cc = 0; cc < P.BN; cc += 32) {
+                float v[32];
+                tmem_ld32(t0 + cc, v);
+                epi_store32(P.epi, bias_s, v, img, y, x, nt * P.BN + cc, valid);
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&acc_empty[ab]);
+        }
+    } else {
+        // ================= gather warps (256 threads): build the A operand of each stage
+        const int tid = threadIdx.x - 192;
+        const int m = tid & 127;          // row of the tile == output pixel
+        const int kc0 = (tid >> 7) * 4;   // this thread fills planes kc0..kc0+3
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int pt = tile / P.n_tiles_n;
+            const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
+            const int ho = ty * DC_TILE_H + (m >> 3), wo = tx * DC_TILE_W + (m & 7);
+            const bool pix_valid = (ho < P.Ho) && (wo < P.Wo);
+            for (int st = 0; st < nstages; ++st, ++it) {
+                const int tap = st / nchunks, chunk = st - tap * nchunks;
+                const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + m * 16;
+                int g_prev = -1;
+                DcnCorner cn;
+#pragma unroll
+                for (int qk = 0; qk < 4; ++qk) {
+                    const int kc = kc0 + qk;
+                    const int ch = chunk * 64 + kc * 8;
+                    const int g = ch / P.cpg;
+                    if (g != g_prev) { cn = dcn_corner<OFFMODE>(P, img, ho, wo, pix_valid, g, tap); g_prev = g; }
+                    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    const __half* b = cn.base + ch;
+                    uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0, u2 = u0, u3 = u0;
+                    if (cn.valid & 1u) u0 = ldg_nc_v4(b);
+                    if (cn.valid & 2u) u1 = ldg_nc_v4(b + cn.dW);
+                    if (cn.valid & 4u) u2 = ldg_nc_v4(b + cn.dH);
+                    if (cn.valid & 8u) u3 = ldg_nc_v4(b + cn.dH + cn.dW);
+                    dcn_blend8(acc, u0, cn.w[0]);
+                    dcn_blend8(acc, u1, cn.w[1]);
+                    dcn_blend8(acc, u2, cn.w[2]);
+                    dcn_blend8(acc, u3, cn.w[3]);
+                    sts_v4(dst + kc * 2048,
+                           make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]),
+                                      pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7])));
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&full[s]);
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace eb

@@ -1,0 +1,331 @@
+// elementwise.cuh — the HBM-bound stages of the EDVR graph on NHWC fp16 tensors, plus the
+// layout converters at the NCHW-fp32 boundary and the weight packer.  Each thread moves
+// 16-byte vectors (8 halfs); fp32 math inside.
+#pragma once
+#include "common.cuh"
+
+namespace eb {
+
+struct H8 { float v[8]; };
+__device__ __forceinline__ H8 h8_load(const __half* p) {
+    uint4 u = ldg_nc_v4(p);
+    H8 r;
+    float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+    return r;
+}
+__device__ __forceinline__ void h8_store(__half* p, const H8& r) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_h2(r.v[0], r.v[1]), pack_h2(r.v[2], r.v[3]),
+                                              pack_h2(r.v[4], r.v[5]), pack_h2(r.v[6], r.v[7]));
+}
+
+// ------------------------------------------------------------------ NCHW fp32 <-> NHWC fp16
+// grid: (ceil(HW/32), ceil(C/32), N), block (32, 8)
+__global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst,
+                                            int C, int HW, int dst_pix_stride, int dst_ch_off) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? src[(static_cast<size_t>(n) * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C)
+            dst[(static_cast<size_t>(n) * HW + p) * dst_pix_stride + dst_ch_off + c] =
+                __float2half_rn(tile[threadIdx.x][i]);
+    }
+}
+__global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst,
+                                            int C, int HW, int src_pix_stride, int src_ch_off) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (p < HW && c < C)
+            ? __half2float(src[(static_cast<size_t>(n) * HW + p) * src_pix_stride + src_ch_off + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < HW) dst[(static_cast<size_t>(n) * C + c) * HW + p] = tile[threadIdx.x][i];
+    }
+}
+
+// ------------------------------------------------------------------ weight packer
+// out element group (16 B): [nt][s1][s2][kc][n][0..7]; one thread per group.
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int ktaps,
+                                   const int* __restrict__ row_map, int BN, int n_tiles_n,
+                                   int tap_major, __half* __restrict__ out) {
+    const int nchunks = cin / 64;
+    const long long total = static_cast<long long>(n_tiles_n) * nchunks * ktaps * 8 * BN;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int n = r % BN; r /= BN;
+        const int kc = r % 8; r /= 8;
+        int tap, chunk;
+        if (tap_major) { chunk = r % nchunks; r /= nchunks; tap = r % ktaps; r /= ktaps; }
+        else           { tap = r % ktaps; r /= ktaps; chunk = r % nchunks; r /= nchunks; }
+        const int nt = static_cast<int>(r);
+        const int prow = nt * BN + n;
+        int srow = row_map ? row_map[prow] : prow;
+        if (srow >= cout) srow = -1;
+        H8 v;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ci = chunk * 64 + kc * 8 + e;
+            v.v[e] = srow >= 0 ? w[(static_cast<size_t>(srow) * cin + ci) * ktaps + tap] : 0.f;
+        }
+        h8_store(out + i * 8, v);
+    }
+}
+__global__ void pack_bias_kernel(const float* __restrict__ b, int cout, const int* __restrict__ row_map,
+                                 int n_packed, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_packed) return;
+    int s = row_map ? row_map[i] : i;
+    if (s >= cout) s = -1;
+    out[i] = (b != nullptr && s >= 0) ? b[s] : 0.f;
+}
+
+// ------------------------------------------------------------------ conv_first (Cin = 3)
+// thread = (pixel, 8 output channels); weights [Cout][3][3][3] staged in smem.
+__global__ void conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                  const float* __restrict__ bias, __half* __restrict__ out, int N,
+                                  int H, int W, int Cout, int out_pix_stride, int act) {
+    extern __shared__ float ws[];   // [Cout*27] + [Cout]
+    float* bs = ws + Cout * 27;
+    for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) ws[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int groups = Cout / 8;
+    const long long total = static_cast<long long>(N) * H * W * groups;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = i % groups;
+        const long long pix = i / groups;
+        const int xw = pix % W, yh = (pix / W) % H, n = pix / (static_cast<long long>(W) * H);
+        float in[27];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int yy = yh + dy - 1, xx = xw + dx - 1;
+                    in[c * 9 + dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                        ? __ldg(x + ((static_cast<size_t>(n) * 3 + c) * H + yy) * W + xx) : 0.f;
+                }
+        H8 r;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float* wr = ws + (g * 8 + e) * 27;
+            float a = bs[g * 8 + e];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) a = fmaf(wr[k], in[k], a);
+            r.v[e] = apply_act(a, act);
+        }
+        h8_store(out + pix * out_pix_stride + g * 8, r);
+    }
+}
+
+// ------------------------------------------------------------------ conv_last (Cin -> 3) + base
+// thread = one HR pixel; w [3][Cin][3][3] in smem as [tap][c][3].
+__device__ __forceinline__ float bilinear_up_sample(const float* __restrict__ im, int h, int w,
+                                                    int oy, int ox, int scale) {
+    // PyTorch upsample_bilinear2d, align_corners=False (edvr_arch.py:417-418)
+    const float rs = 1.0f / static_cast<float>(scale);
+    float sy = rs * (oy + 0.5f) - 0.5f, sx = rs * (ox + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    return hy * (hx * im[y0 * w + x0] + lx * im[y0 * w + x1]) +
+           ly * (hx * im[y1 * w + x0] + lx * im[y1 * w + x1]);
+}
+__global__ void conv_last_kernel(const __half* __restrict__ x, int x_pix_stride,
+                                 const float* __restrict__ w, const float* __restrict__ bias,
+                                 const float* __restrict__ base, long long base_img_stride, int scale,
+                                 float* __restrict__ out, int N, int H, int W, int Cin) {
+    extern __shared__ float ws[];   // [9][Cin][3]
+    for (int i = threadIdx.x; i < 27 * Cin; i += blockDim.x) {
+        const int co = i / (Cin * 9), rem = i % (Cin * 9), c = rem / 9, tap = rem % 9;
+        ws[(tap * Cin + c) * 3 + co] = w[i];
+    }
+    __syncthreads();
+    const long long total = static_cast<long long>(N) * H * W;
+    for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < total;
+         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int xw = pix % W, yh = (pix / W) % H, n = pix / (static_cast<long long>(W) * H);
+        float a0 = bias ? bias[0] : 0.f, a1 = bias ? bias[1] : 0.f, a2 = bias ? bias[2] : 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const __half* px = x + ((static_cast<size_t>(n) * H + yy) * W + xx) * x_pix_stride;
+            const float* wt = ws + tap * Cin * 3;
+            for (int c = 0; c < Cin; c += 8) {
+                const H8 v = h8_load(px + c);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    a0 = fmaf(v.v[e], wt[(c + e) * 3 + 0], a0);
+                    a1 = fmaf(v.v[e], wt[(c + e) * 3 + 1], a1);
+                    a2 = fmaf(v.v[e], wt[(c + e) * 3 + 2], a2);
+                }
+            }
+        }
+        const size_t plane = static_cast<size_t>(H) * W;
+        float* o = out + static_cast<size_t>(n) * 3 * plane + static_cast<size_t>(yh) * W + xw;
+        const int bh = H / scale, bw = W / scale;
+        const float* b = base + static_cast<size_t>(n) * base_img_stride;
+        float acc[3] = {a0, a1, a2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* bc = b + static_cast<size_t>(c) * bh * bw;
+            const float bv = scale == 1 ? bc[yh * bw + xw] : bilinear_up_sample(bc, bh, bw, yh, xw, scale);
+            o[c * plane] = acc[c] + bv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ bilinear x2 (align_corners=False)
+// out[2k] = .25 in[k-1] + .75 in[k]; out[2k+1] = .75 in[k] + .25 in[k+1]; edges replicate.
+__global__ void upsample2x_kernel(const __half* __restrict__ src, int sps, int sco,
+                                  __half* __restrict__ dst, int dps, int dco, int N, int H, int W, int C,
+                                  float mul, const __half* __restrict__ add, int aps, int aco) {
+    const int groups = C / 8, H2 = 2 * H, W2 = 2 * W;
+    const long long total = static_cast<long long>(N) * H2 * W2 * groups;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = i % groups;
+        const long long opix = i / groups;
+        const int ox = opix % W2, oy = (opix / W2) % H2, n = opix / (static_cast<long long>(W2) * H2);
+        const int y0 = max((oy - 1) >> 1, 0), y1 = min((oy + 1) >> 1, H - 1);
+        const int x0 = max((ox - 1) >> 1, 0), x1 = min((ox + 1) >> 1, W - 1);
+        // weight of the "far" neighbour is .25, of the near one .75; at the clamped edges both coincide
+        const float wy1 = (oy & 1) ? 0.25f : 0.75f, wx1 = (ox & 1) ? 0.25f : 0.75f;
+        const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+        const __half* s = src + static_cast<size_t>(n) * H * W * sps + sco + g * 8;
+        const H8 v00 = h8_load(s + (static_cast<size_t>(y0) * W + x0) * sps);
+        const H8 v01 = h8_load(s + (static_cast<size_t>(y0) * W + x1) * sps);
+        const H8 v10 = h8_load(s + (static_cast<size_t>(y1) * W + x0) * sps);
+        const H8 v11 = h8_load(s + (static_cast<size_t>(y1) * W + x1) * sps);
+        H8 r;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            r.v[e] = (wy0 * (wx0 * v00.v[e] + wx1 * v01.v[e]) + wy1 * (wx0 * v10.v[e] + wx1 * v11.v[e])) * mul;
+        if (add != nullptr) {
+            const H8 a = h8_load(add + opix * aps + aco + g * 8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r.v[e] += a.v[e];
+        }
+        h8_store(dst + opix * dps + dco + g * 8, r);
+    }
+}
+
+// ------------------------------------------------------------------ max + avg pool 3x3 s2 p1
+__global__ void pool_max_avg_kernel(const __half* __restrict__ src, int sps, int sco,
+                                    __half* __restrict__ dst, int dps, int dco, int N, int H, int W, int C) {
+    const int groups = C / 8, Ho = (H + 1) / 2, Wo = (W + 1) / 2;   // floor((H+2-3)/2)+1
+    const long long total = static_cast<long long>(N) * Ho * Wo * groups;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = i % groups;
+        const long long opix = i / groups;
+        const int ox = opix % Wo, oy = (opix / Wo) % Ho, n = opix / (static_cast<long long>(Wo) * Ho);
+        H8 mx, sm;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { mx.v[e] = -INFINITY; sm.v[e] = 0.f; }
+        for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) {
+                const int yy = 2 * oy + dy - 1, xx = 2 * ox + dx - 1;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const H8 v = h8_load(src + ((static_cast<size_t>(n) * H + yy) * W + xx) * sps + sco + g * 8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { mx.v[e] = fmaxf(mx.v[e], v.v[e]); sm.v[e] += v.v[e]; }
+            }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sm.v[e] *= (1.0f / 9.0f);     // count_include_pad=True
+        h8_store(dst + opix * dps + dco + g * 8, mx);
+        h8_store(dst + opix * dps + dco + C + g * 8, sm);
+    }
+}
+
+// ------------------------------------------------------------------ TSA temporal attention
+// LPP = C/8 lanes cooperate on one pixel.
+__global__ void tsa_temporal_kernel(const __half* __restrict__ emb, const __half* __restrict__ emb_ref,
+                                    const __half* __restrict__ aligned, __half* __restrict__ dst,
+                                    int B, int T, int HW, int C) {
+    const int lpp = C / 8;
+    const int sub = threadIdx.x % lpp;
+    const long long npix = static_cast<long long>(B) * HW;
+    const long long gstride = static_cast<long long>(gridDim.x) * blockDim.x / lpp;
+    // all lanes of a warp iterate the same number of times (shuffles need full participation)
+    const long long first = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) / lpp;
+    const long long iters = (npix + gstride - 1) / gstride;
+    for (long long it = 0; it < iters; ++it) {
+        const long long pix = first + it * gstride;
+        const bool ok = pix < npix;
+        const long long b = ok ? pix / HW : 0, hw = ok ? pix % HW : 0;
+        H8 r8 = h8_load(emb_ref + (b * HW + hw) * C + sub * 8);
+        for (int t = 0; t < T; ++t) {
+            const size_t fp = ((b * T + t) * static_cast<size_t>(HW) + hw) * C + sub * 8;
+            const H8 e8 = h8_load(emb + fp);
+            float d = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d = fmaf(e8.v[e], r8.v[e], d);
+            for (int o = lpp >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            const float prob = 1.0f / (1.0f + __expf(-d));
+            H8 a8 = h8_load(aligned + fp);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a8.v[e] *= prob;
+            if (ok) h8_store(dst + (b * HW + hw) * (static_cast<size_t>(T) * C) + t * C + sub * 8, a8);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ TSA output modulation
+__global__ void tsa_modulate_kernel(const __half* __restrict__ feat, int fps, int fco,
+                                    const __half* __restrict__ attn, const __half* __restrict__ attn_add,
+                                    __half* __restrict__ out16, float* __restrict__ out32,
+                                    long long npix, int C) {
+    const int groups = C / 8;
+    const long long total = npix * groups;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = i % groups;
+        const long long pix = i / groups;
+        const H8 f = h8_load(feat + pix * fps + fco + g * 8);
+        const H8 a = h8_load(attn + pix * C + g * 8);
+        const H8 d = h8_load(attn_add + pix * C + g * 8);
+        H8 r;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r.v[e] = f.v[e] * (1.0f / (1.0f + __expf(-a.v[e]))) * 2.f + d.v[e];
+        if (out16) h8_store(out16 + pix * C + g * 8, r);
+        if (out32) {
+            float4* o = reinterpret_cast<float4*>(out32 + pix * C + g * 8);
+            o[0] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+            o[1] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+        }
+    }
+}
+
+__global__ void add_kernel(const __half* __restrict__ a, int aps, int aco, const __half* __restrict__ b,
+                           int bps, int bco, __half* __restrict__ dst, int dps, int dco, long long npix, int C) {
+    const int groups = C / 8;
+    const long long total = npix * groups;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = i % groups;
+        const long long pix = i / groups;
+        H8 x = h8_load(a + pix * aps + aco + g * 8);
+        const H8 y = h8_load(b + pix * bps + bco + g * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x.v[e] += y.v[e];
+        h8_store(dst + pix * dps + dco + g * 8, x);
+    }
+}
+
+}  // namespace eb

@@ -1,0 +1,128 @@
+// epilogue.cuh — shared accumulator epilogue: TMEM row (one output pixel, 32 channels at a
+// time) -> bias -> activation -> residual -> NHWC fp16 / NHWC fp32 / NCHW fp32 stores,
+// optionally through the PixelShuffle(2) index map or a stride-2 subsample.
+#pragma once
+#include "common.cuh"
+
+namespace eb {
+
+enum : int { OUT_SAME = 0, OUT_PIXSHUF2 = 1, OUT_STRIDE2 = 2 };
+
+struct EpiParams {
+    const float* bias;        // [cout_packed] or nullptr
+    int act;                  // ACT_*
+    int H, W;                 // spatial dims of the accumulator grid
+    // residual, added AFTER the activation (ResidualBlockNoBN: act = none)
+    const __half* res16;
+    const float* res32;
+    int res_pix_stride, res_ch_off;
+    // outputs (any subset)
+    __half* out16;
+    int out16_pix_stride, out16_ch_off;
+    float* out32;
+    int out32_pix_stride, out32_ch_off;
+    float* out_nchw;          // [N][nchw_C][H][W] fp32 (reference op layout)
+    int nchw_C;
+    int out_mode;             // OUT_*
+    float* absmean_acc;       // ACT_DCN_PACK: sum |offset| accumulator (optional)
+};
+
+// v: 32 consecutive accumulator channels [c0, c0+32) of output pixel (img, y, x).
+// Every lane of the warp must call this (shuffles inside); `valid` masks the memory traffic.
+__device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __restrict__ bias_s,
+                                            float (&v)[32], int img, int y, int x, int c0,
+                                            bool valid) {
+    if (bias_s != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += bias_s[c0 + j];
+    }
+    if (p.act == ACT_DCN_PACK) {
+        // channel j of each 32-group: [0,18) offsets (dh,dw per tap), [18,27) mask logits, rest pad
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 18; ++j) s += fabsf(v[j]);
+#pragma unroll
+        for (int j = 18; j < 27; ++j) v[j] = sigmoidf_fast(v[j]);
+        if (p.absmean_acc != nullptr) {
+            s = valid ? s : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane_id() == 0) atomicAdd(p.absmean_acc, s);
+        }
+    } else if (p.act != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+    }
+    if (!valid) return;
+
+    const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+    if (p.res16 != nullptr) {
+        const __half* r = p.res16 + pix * p.res_pix_stride + p.res_ch_off + c0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 u = ldg_nc_v4(r + q * 8);
+            float2 f0 = unpack_h2(u.x), f1 = unpack_h2(u.y), f2 = unpack_h2(u.z), f3 = unpack_h2(u.w);
+            v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
+            v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
+        }
+    }
+    if (p.res32 != nullptr) {
+        const float4* r = reinterpret_cast<const float4*>(p.res32 + pix * p.res_pix_stride +
+                                                          p.res_ch_off + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float4 f = __ldg(r + q);
+            v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+        }
+    }
+
+    if (p.out_mode == OUT_SAME) {
+        if (p.out16 != nullptr) {
+            uint4* o = reinterpret_cast<uint4*>(p.out16 + pix * p.out16_pix_stride + p.out16_ch_off + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                o[q] = make_uint4(pack_h2(v[q * 8 + 0], v[q * 8 + 1]), pack_h2(v[q * 8 + 2], v[q * 8 + 3]),
+                                  pack_h2(v[q * 8 + 4], v[q * 8 + 5]), pack_h2(v[q * 8 + 6], v[q * 8 + 7]));
+        }
+        if (p.out32 != nullptr) {
+            float4* o = reinterpret_cast<float4*>(p.out32 + pix * p.out32_pix_stride + p.out32_ch_off + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                o[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        }
+        if (p.out_nchw != nullptr) {
+            const size_t plane = static_cast<size_t>(p.H) * p.W;
+            float* o = p.out_nchw + (static_cast<size_t>(img) * p.nchw_C + c0) * plane +
+                       static_cast<size_t>(y) * p.W + x;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < p.nchw_C) o[j * plane] = v[j];
+        }
+    } else if (p.out_mode == OUT_PIXSHUF2) {
+        // nn.PixelShuffle(2): out[b, c, 2y+i, 2x+j] = in[b, 4c + 2i + j, y, x]
+        // (/root/reference/basicsr/models/archs/edvr_arch.py:351,410-411)
+        const int H2 = 2 * p.H, W2 = 2 * p.W;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const size_t opix = (static_cast<size_t>(img) * H2 + 2 * y + i) * W2 + 2 * x + j;
+                uint4* o = reinterpret_cast<uint4*>(p.out16 + opix * p.out16_pix_stride +
+                                                    p.out16_ch_off + (c0 >> 2));
+                const int s = 2 * i + j;
+                *o = make_uint4(pack_h2(v[s], v[4 + s]), pack_h2(v[8 + s], v[12 + s]),
+                                pack_h2(v[16 + s], v[20 + s]), pack_h2(v[24 + s], v[28 + s]));
+            }
+    } else {  // OUT_STRIDE2: stride-2 / pad-1 / k=3 conv == stride-1 result sampled at even pixels
+        if ((y | x) & 1) return;
+        const int Ho = (p.H + 1) >> 1, Wo = (p.W + 1) >> 1;
+        const size_t opix = (static_cast<size_t>(img) * Ho + (y >> 1)) * Wo + (x >> 1);
+        uint4* o = reinterpret_cast<uint4*>(p.out16 + opix * p.out16_pix_stride + p.out16_ch_off + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            o[q] = make_uint4(pack_h2(v[q * 8 + 0], v[q * 8 + 1]), pack_h2(v[q * 8 + 2], v[q * 8 + 3]),
+                              pack_h2(v[q * 8 + 4], v[q * 8 + 5]), pack_h2(v[q * 8 + 6], v[q * 8 + 7]));
+    }
+}
+
+}  // namespace eb

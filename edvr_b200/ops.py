@@ -1,0 +1,214 @@
+"""Thin Python front-end over the C ABI: NHWC fp16 views, weight packing, one function per kernel.
+
+PyTorch is used only for device memory and the current CUDA stream; every compute call goes
+through libedvr_b200.so (edvr_b200/_lib.py) with raw pointers.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_DCN_PACK, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, OUT_PIXSHUF2,  # noqa: F401
+                   OUT_SAME, OUT_STRIDE2)
+
+
+class View:
+    """Channel slice [ch_off, ch_off+C) of an NHWC fp16 tensor t[N, H, W, Ctot]."""
+
+    __slots__ = ("t", "ch_off", "C")
+
+    def __init__(self, t, ch_off=0, C=None):
+        assert t.dtype == torch.float16 and t.dim() == 4 and t.is_contiguous() and t.is_cuda
+        self.t, self.ch_off = t, ch_off
+        self.C = t.shape[3] - ch_off if C is None else C
+        assert 0 <= ch_off and ch_off + self.C <= t.shape[3]
+
+    N = property(lambda s: s.t.shape[0])
+    H = property(lambda s: s.t.shape[1])
+    W = property(lambda s: s.t.shape[2])
+    pix_stride = property(lambda s: s.t.shape[3])
+
+    def slice(self, off, C):
+        return View(self.t, self.ch_off + off, C)
+
+    def dense(self):
+        """Materialise as a dense torch tensor [N,H,W,C] (tests / debugging)."""
+        return self.t[..., self.ch_off:self.ch_off + self.C]
+
+
+def new_act(N, H, W, C, device="cuda"):
+    return View(torch.empty(N, H, W, C, dtype=torch.float16, device=device))
+
+
+class PackedConv:
+    """MMA-ready fp16 weights + fp32 bias of one convolution (see eb_pack_weight)."""
+
+    __slots__ = ("w", "b", "BN", "n_tiles", "cin", "ksize", "cout")
+
+
+def _choose_bn(cout_packed):
+    if cout_packed % 128 == 0:
+        return 128
+    for bn in (96, 64, 32):
+        if cout_packed % bn == 0:
+            return bn
+    raise ValueError(f"packed Cout {cout_packed} must be a multiple of 32")
+
+
+def pack_conv(weight, bias=None, row_map=None, tap_major=False, cout_packed=None):
+    """weight: fp32 [Cout, Cin, k, k] (CUDA). row_map: optional LongTensor packed-row -> source row (-1 = 0)."""
+    assert weight.is_cuda and weight.dtype == torch.float32
+    weight = weight.contiguous()
+    cout, cin, k, _ = weight.shape
+    if row_map is not None:
+        cout_packed = int(row_map.numel())
+        rm = row_map.to(device=weight.device, dtype=torch.int32).contiguous()
+    else:
+        cout_packed = cout_packed or ((cout + 31) // 32) * 32
+        rm = None
+    p = PackedConv()
+    p.BN = _choose_bn(cout_packed)
+    p.n_tiles = cout_packed // p.BN
+    p.cin, p.ksize, p.cout = cin, k, cout
+    nbytes = L.lib().eb_packed_weight_bytes(cin, k * k, p.BN, p.n_tiles)
+    p.w = torch.empty(nbytes // 2, dtype=torch.float16, device=weight.device)
+    L.check(L.lib().eb_pack_weight(L.ptr(weight), cout, cin, k * k, L.ptr(rm), p.BN, p.n_tiles,
+                                   1 if tap_major else 0, L.ptr(p.w), L.stream_ptr()), "eb_pack_weight")
+    b = torch.zeros(cout_packed, dtype=torch.float32, device=weight.device)
+    if bias is not None:
+        if rm is None:
+            b[:cout] = bias.float()
+        else:
+            sel = rm >= 0
+            b[sel] = bias.float()[rm[sel].long()]
+    p.b = b
+    return p
+
+
+def dcn_offset_row_map(dg, k2=9):
+    """conv_offset rows -> packed [g][32] layout: (dh,dw) x k2, then k2 mask logits, then pad.
+
+    Source rows follow the reference: offsets g*2*k2 + j, masks dg*2*k2 + g*k2 + k
+    (arch_util.py:244-247, deform_conv_cuda_kernel.cu:600-613).
+    """
+    assert k2 == 9
+    rm = torch.full((dg * 32,), -1, dtype=torch.int32)
+    for g in range(dg):
+        for j in range(18):
+            rm[g * 32 + j] = g * 18 + j
+        for k in range(9):
+            rm[g * 32 + 18 + k] = dg * 18 + g * 9 + k
+    return rm
+
+
+def _src(v, div=1, mul=1, keep=0, add=0):
+    return L.Src(v.t.data_ptr(), v.C, v.pix_stride, v.ch_off, div, mul, keep, add)
+
+
+def _epi(pc_bias, act, out16=None, out32=None, res16=None, res32=None, out_nchw=None, nchw_C=0,
+         out_mode=OUT_SAME, absmean=None):
+    e = L.Epilogue()
+    e.bias = None if pc_bias is None else pc_bias.data_ptr()
+    e.act = act
+    if res16 is not None:
+        e.res16, e.res_pix_stride, e.res_ch_off = res16.t.data_ptr(), res16.pix_stride, res16.ch_off
+    if res32 is not None:
+        e.res32, e.res_pix_stride, e.res_ch_off = res32.data_ptr(), res32.shape[3], 0
+    if out16 is not None:
+        e.out16, e.out16_pix_stride, e.out16_ch_off = out16.t.data_ptr(), out16.pix_stride, out16.ch_off
+    if out32 is not None:
+        e.out32, e.out32_pix_stride, e.out32_ch_off = out32.data_ptr(), out32.shape[3], 0
+    if out_nchw is not None:
+        e.out_nchw, e.nchw_C = out_nchw.data_ptr(), nchw_C
+    e.out_mode = out_mode
+    e.absmean_acc = None if absmean is None else absmean.data_ptr()
+    return e
+
+
+def conv2d(pc, srcs, out16=None, act=ACT_NONE, res16=None, res32=None, out32=None, out_mode=OUT_SAME,
+           absmean=None, src_maps=None, N=None):
+    """srcs: list of 1-2 Views (channel-concatenated input). src_maps: per-source (div, mul, keep, add)."""
+    v0 = srcs[0]
+    N = v0.N if N is None else N
+    arr = (L.Src * len(srcs))()
+    for i, v in enumerate(srcs):
+        m = (1, 1, 0, 0) if src_maps is None or src_maps[i] is None else src_maps[i]
+        arr[i] = _src(v, *m)
+    assert sum(v.C for v in srcs) == pc.cin, (sum(v.C for v in srcs), pc.cin)
+    e = _epi(pc.b, act, out16, out32, res16, res32, out_mode=out_mode, absmean=absmean)
+    L.check(L.lib().eb_conv2d(arr, len(srcs), N, v0.H, v0.W, pc.ksize, L.ptr(pc.w), pc.BN, pc.n_tiles,
+                              ctypes.byref(e), L.stream_ptr()), "eb_conv2d")
+
+
+def dcn_nhwc(pc, x, offpack, dg, out16=None, act=ACT_NONE, out_nchw=None, nchw_C=0):
+    e = _epi(pc.b, act, out16, out_nchw=out_nchw, nchw_C=nchw_C)
+    L.check(L.lib().eb_dcn_nhwc(L.ptr(x.t), x.pix_stride, x.ch_off, x.N, x.H, x.W, x.C, dg, L.ptr(offpack.t),
+                                offpack.pix_stride, L.ptr(pc.w), pc.BN, pc.n_tiles, ctypes.byref(e),
+                                L.stream_ptr()), "eb_dcn_nhwc")
+
+
+def nchw_to_nhwc(x, out=None):
+    """fp32 [N,C,H,W] -> View fp16 [N,H,W,C]."""
+    N, C, H, W = x.shape
+    out = out or new_act(N, H, W, C, x.device)
+    L.check(L.lib().eb_nchw_f32_to_nhwc_f16(L.ptr(x.contiguous()), L.ptr(out.t), N, C, H, W, out.pix_stride,
+                                            out.ch_off, L.stream_ptr()), "eb_nchw_f32_to_nhwc_f16")
+    return out
+
+
+def nhwc_to_nchw(v):
+    out = torch.empty(v.N, v.C, v.H, v.W, dtype=torch.float32, device=v.t.device)
+    L.check(L.lib().eb_nhwc_f16_to_nchw_f32(L.ptr(v.t), v.pix_stride, v.ch_off, L.ptr(out), v.N, v.C, v.H, v.W,
+                                            L.stream_ptr()), "eb_nhwc_f16_to_nchw_f32")
+    return out
+
+
+def conv_first(x_nchw, w, b, out, act=ACT_LRELU):
+    N, _, H, W = x_nchw.shape
+    L.check(L.lib().eb_conv_first(L.ptr(x_nchw), L.ptr(w), L.ptr(b), L.ptr(out.t), N, H, W, w.shape[0],
+                                  out.pix_stride, act, L.stream_ptr()), "eb_conv_first")
+
+
+def conv_last(x, w, b, base, base_img_stride, scale, out_nchw):
+    L.check(L.lib().eb_conv_last(L.ptr(x.t), x.pix_stride, L.ptr(w), L.ptr(b), L.ptr(base), base_img_stride, scale,
+                                 L.ptr(out_nchw), x.N, x.H, x.W, x.C, L.stream_ptr()), "eb_conv_last")
+
+
+def upsample2x(src, dst, mul=1.0, add=None):
+    a = (None, 0, 0) if add is None else (add.t, add.pix_stride, add.ch_off)
+    L.check(L.lib().eb_upsample2x(L.ptr(src.t), src.pix_stride, src.ch_off, L.ptr(dst.t), dst.pix_stride, dst.ch_off,
+                                  src.N, src.H, src.W, src.C, mul, L.ptr(a[0]), a[1], a[2], L.stream_ptr()),
+            "eb_upsample2x")
+
+
+def pool_max_avg(src, dst):
+    L.check(L.lib().eb_pool_max_avg(L.ptr(src.t), src.pix_stride, src.ch_off, L.ptr(dst.t), dst.pix_stride,
+                                    dst.ch_off, src.N, src.H, src.W, src.C, L.stream_ptr()), "eb_pool_max_avg")
+
+
+def tsa_temporal(emb, emb_ref, aligned, dst, B, T):
+    L.check(L.lib().eb_tsa_temporal(L.ptr(emb.t), L.ptr(emb_ref.t), L.ptr(aligned.t), L.ptr(dst.t), B, T, emb.H,
+                                    emb.W, emb.C, L.stream_ptr()), "eb_tsa_temporal")
+
+
+def tsa_modulate(feat, attn, attn_add, out16=None, out32=None):
+    npix = attn.N * attn.H * attn.W
+    L.check(L.lib().eb_tsa_modulate(L.ptr(feat.t), feat.pix_stride, feat.ch_off, L.ptr(attn.t), L.ptr(attn_add.t),
+                                    L.ptr(None if out16 is None else out16.t), L.ptr(out32), npix, attn.C,
+                                    L.stream_ptr()), "eb_tsa_modulate")
+
+
+def mdcn_forward(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, workspace=None):
+    """Reference-layout operator (fp32 NCHW) through eb_mdcn_forward."""
+    N, C, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    Ho = (H + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1
+    Wo = (W + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1
+    out = torch.empty(N, Cout, Ho, Wo, dtype=torch.float32, device=x.device)
+    need = L.lib().eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=x.device)
+    L.check(L.lib().eb_mdcn_forward(L.ptr(x), L.ptr(offset), L.ptr(mask), L.ptr(weight), L.ptr(bias), L.ptr(out),
+                                    N, C, H, W, Cout, kh, kw, stride, padding, dilation, groups, dg,
+                                    L.ptr(workspace), workspace.numel(), L.stream_ptr()), "eb_mdcn_forward")
+    return out

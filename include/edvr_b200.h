@@ -1,0 +1,144 @@
+/*
+ * edvr_b200.h — C ABI of libedvr_b200.so: the B200-native EDVR hot path.
+ *
+ * Every entry point takes raw DEVICE pointers, explicit sizes and a cudaStream_t (passed as
+ * void*), allocates nothing, never synchronises, and returns an int status:
+ *   0 ok, -1 invalid shape, -2 unsupported configuration, -3 launch failure,
+ *   -4 workspace too small, -5 null pointer, -6 misaligned pointer / stride.
+ * (The reference only printf()s launch errors and continues,
+ *  /root/reference/basicsr/models/ops/dcn/src/deform_conv_cuda_kernel.cu:794-798.)
+ * Calls on different streams may run concurrently; there is no global mutable state.
+ *
+ * Interface replaced (all paths relative to /root/reference/basicsr/models/):
+ *   eb_mdcn_forward / eb_mdcn_backward
+ *       == deform_conv_ext.modulated_deform_conv_forward / _backward
+ *          (ops/dcn/src/deform_conv_ext.cpp:106-146, bound at ops/dcn/deform_conv.py:141-145,
+ *           159-164; implementation ops/dcn/src/deform_conv_cuda.cpp:490-685).
+ *          Same tensor layouts (NCHW fp32, offset [N,dg*2*K,Ho,Wo], mask [N,dg*K,Ho,Wo]),
+ *          same ownership (caller allocates outputs; grad_weight / grad_bias are accumulated
+ *          into, the other grads overwritten), `ones` / `columns` scratch handles dropped in
+ *          favour of one caller-owned workspace.
+ *   eb_conv2d / eb_dcn_nhwc / eb_* elementwise
+ *       == the cuDNN / ATen dispatches behind nn.Conv2d, nn.LeakyReLU, nn.Upsample, nn.*Pool2d,
+ *          nn.PixelShuffle, torch.cat in archs/edvr_arch.py:76-117,161-214,250-269,358-420 and
+ *          archs/arch_util.py:92-95,243-257, on NHWC fp16 tensors (fp32 accumulation).
+ */
+#ifndef EDVR_B200_H
+#define EDVR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* activation codes */
+#define EB_ACT_NONE 0
+#define EB_ACT_RELU 1
+#define EB_ACT_LRELU 2      /* negative slope 0.1 (edvr_arch.py:70) */
+#define EB_ACT_DCN_PACK 3   /* conv_offset epilogue: per 32-ch group, ch 18..26 -> sigmoid */
+#define EB_ACT_SIGMOID 4
+/* output index maps */
+#define EB_OUT_SAME 0
+#define EB_OUT_PIXSHUF2 1   /* nn.PixelShuffle(2) fused into the store */
+#define EB_OUT_STRIDE2 2    /* k3/s2/p1 conv: even-pixel subsample of the stride-1 result */
+
+/* One NHWC fp16 input view of a convolution (channel slice of a wider buffer allowed).
+ * Image index used for accumulator image n: (n / div) * mul + (n % div) * keep + add. */
+typedef struct {
+    const void* ptr;
+    int C;            /* channels consumed (multiple of 64) */
+    int pix_stride;   /* elements between consecutive pixels (multiple of 8) */
+    int ch_off;       /* first channel (multiple of 8) */
+    int div, mul, keep, add;
+} eb_src_t;
+
+typedef struct {
+    const float* bias;        /* [packed Cout] fp32 or NULL */
+    int act;
+    const void* res16;        /* optional residual, NHWC fp16, added after the activation */
+    const float* res32;       /* optional residual, NHWC fp32 */
+    int res_pix_stride, res_ch_off;
+    void* out16;              /* optional NHWC fp16 output */
+    int out16_pix_stride, out16_ch_off;
+    float* out32;             /* optional NHWC fp32 output */
+    int out32_pix_stride, out32_ch_off;
+    float* out_nchw;          /* optional NCHW fp32 output [N][nchw_C][H][W] */
+    int nchw_C;
+    int out_mode;
+    float* absmean_acc;       /* optional: sum |offset| (EB_ACT_DCN_PACK), for the >50 warning */
+} eb_epilogue_t;
+
+/* ---- library info ------------------------------------------------------------------- */
+int eb_version(void);                 /* 100 * major + minor */
+const char* eb_last_error(void);      /* thread-local text of the last non-zero status */
+
+/* ---- hardware self-test: D[128,N] = A[128,K] * B[N,K]^T through tcgen05 (fp16 in, fp32 out).
+ * variant 0 is the production descriptor convention; other values probe alternatives. */
+int eb_selftest_umma(const void* A, const void* B, float* D, int N, int K, int variant, void* stream);
+
+/* ---- weight packing (device side; fp32 OIHW -> fp16 MMA-ready stages) ------------------
+ * layout [n_tile][s1][s2][kc=8][BN][8]; tap_major=1: s1=tap,s2=chunk (DCN); 0: s1=chunk,s2=tap.
+ * row_map (device int32[BN*n_tiles_n], or NULL=identity) maps packed row -> source row (-1 = zero). */
+size_t eb_packed_weight_bytes(int cin, int ktaps, int BN, int n_tiles_n);
+int eb_pack_weight(const float* w_oihw, int cout, int cin, int ktaps, const int* row_map, int BN,
+                   int n_tiles_n, int tap_major, void* wpack, void* stream);
+
+/* ---- dense convolution, NHWC fp16, 3x3 (pad 1) or 1x1, stride 1 (stride 2 via out_mode) ---- */
+int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack,
+              int BN, int n_tiles_n, const eb_epilogue_t* epi, void* stream);
+
+/* ---- DCNv2 forward on NHWC fp16 input with packed fp16 offsets/mask (fused pipeline) ---- */
+int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
+                const void* offpack, int offpack_pix_stride, const void* wpack, int BN, int n_tiles_n,
+                const eb_epilogue_t* epi, void* stream);
+
+/* ---- DCNv2 reference-layout operator (fp32 NCHW in / out) ------------------------------ */
+size_t eb_mdcn_forward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw);
+int eb_mdcn_forward(const float* x, const float* offset, const float* mask, const float* weight,
+                    const float* bias /* NULL = no bias */, float* out, int N, int C, int H, int W,
+                    int Cout, int kh, int kw, int stride, int pad, int dil, int groups, int dg,
+                    void* workspace, size_t workspace_bytes, void* stream);
+size_t eb_mdcn_backward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int stride,
+                                  int pad, int dil);
+int eb_mdcn_backward(const float* x, const float* offset, const float* mask, const float* weight,
+                     const float* grad_out, float* grad_x, float* grad_offset, float* grad_mask,
+                     float* grad_weight, float* grad_bias /* NULL = no bias */, int N, int C, int H,
+                     int W, int Cout, int kh, int kw, int stride, int pad, int dil, int groups, int dg,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- layout / elementwise stages of the EDVR graph (all NHWC fp16 unless noted) --------- */
+int eb_nchw_f32_to_nhwc_f16(const float* src, void* dst, int N, int C, int H, int W,
+                            int dst_pix_stride, int dst_ch_off, void* stream);
+int eb_nhwc_f16_to_nchw_f32(const void* src, int src_pix_stride, int src_ch_off, float* dst, int N,
+                            int C, int H, int W, void* stream);
+/* conv_first: 3x3 pad 1, Cin = 3 (NCHW fp32 frames) -> NHWC fp16, + bias + lrelu */
+int eb_conv_first(const float* x_nchw, const float* w_oihw, const float* bias, void* out, int N,
+                  int H, int W, int Cout, int out_pix_stride, int act, void* stream);
+/* conv_last: 3x3 pad 1, 64 -> 3, + bilinear x4 of the centre LR frame (or + centre frame itself
+ * when scale == 1), NCHW fp32 output (edvr_arch.py:413-419) */
+int eb_conv_last(const void* x, int x_pix_stride, const float* w_oihw, const float* bias,
+                 const float* base_nchw, long long base_img_stride, int scale, float* out_nchw, int N,
+                 int H, int W, int Cin, void* stream);
+/* bilinear x2, align_corners=False, times `mul` (edvr_arch.py:68-69,109-110), channel-slice I/O */
+int eb_upsample2x(const void* src, int src_pix_stride, int src_ch_off, void* dst, int dst_pix_stride,
+                  int dst_ch_off, int N, int H, int W, int C, float mul, const void* add,
+                  int add_pix_stride, int add_ch_off, void* stream);
+/* MaxPool2d(3,2,1) -> dst[.., 0:C) and AvgPool2d(3,2,1, count_include_pad) -> dst[.., C:2C) */
+int eb_pool_max_avg(const void* src, int src_pix_stride, int src_ch_off, void* dst,
+                    int dst_pix_stride, int dst_ch_off, int N, int H, int W, int C, void* stream);
+/* TSA temporal attention (edvr_arch.py:176-184): prob = sigmoid(sum_c emb[b,t]*emb_ref[b]);
+ * dst[b,h,w,t*C+c] = aligned[b*T+t,h,w,c] * prob */
+int eb_tsa_temporal(const void* emb, const void* emb_ref, const void* aligned, void* dst, int B, int T,
+                    int H, int W, int C, void* stream);
+/* TSA output (edvr_arch.py:210-213): out = feat * sigmoid(attn) * 2 + attn_add; fp16 + fp32 copies */
+int eb_tsa_modulate(const void* feat, int feat_pix_stride, int feat_ch_off, const void* attn,
+                    const void* attn_add, void* out16, float* out32, int npix, int C, void* stream);
+/* dst = a + b (NHWC fp16 views) */
+int eb_add(const void* a, int a_pix_stride, int a_ch_off, const void* b, int b_pix_stride,
+           int b_ch_off, void* dst, int dst_pix_stride, int dst_ch_off, int npix, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDVR_B200_H */

@@ -134,13 +134,27 @@ int eb_pack_weight(const float* w, int cout, int cin, int ktaps, const int* row_
     return check_launch("pack_weight");
 }
 
+static int launch_conv(const ConvParams& P, cudaStream_t st) {
+    if (P.N == 0) return EB_OK;
+    const long long tiles = static_cast<long long>(P.N) * ((P.H + 15) / 16) * ((P.W + 15) / 16) * P.n_tiles_n;
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    if (P.taps == 9) {
+        if (int rc = set_smem(conv_igemm_kernel<1>, CV_SMEM_BYTES)) return rc;
+        conv_igemm_kernel<1><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    } else {
+        if (int rc = set_smem(conv_igemm_kernel<0>, CV_SMEM_BYTES)) return rc;
+        conv_igemm_kernel<0><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    }
+    return check_launch("conv_igemm");
+}
+
 int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack, int BN,
               int n_tiles_n, const eb_epilogue_t* epi, void* stream) {
     if (!srcs || !wpack) return fail(EB_ERR_NULLPTR, "conv2d: null pointer");
     if (nsrc < 1 || nsrc > 2) return fail(EB_ERR_UNSUPPORTED, "conv2d: nsrc=%d", nsrc);
     if (ksize != 1 && ksize != 3) return fail(EB_ERR_UNSUPPORTED, "conv2d: ksize=%d", ksize);
     if (N < 0 || H < 1 || W < 1) return fail(EB_ERR_INVALID_SHAPE, "conv2d: N=%d H=%d W=%d", N, H, W);
-    if (BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || BN * n_tiles_n > CV_MAX_COUT)
+    if (BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || (epi && epi->bias && BN * n_tiles_n > CV_MAX_COUT))
         return fail(EB_ERR_INVALID_SHAPE, "conv2d: BN=%d n_tiles_n=%d", BN, n_tiles_n);
     if (!al16(wpack)) return fail(EB_ERR_ALIGNMENT, "conv2d: wpack must be 16-byte aligned");
     ConvParams P;
@@ -159,18 +173,7 @@ int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, co
     P.nsrc = nsrc; P.N = N; P.H = H; P.W = W; P.taps = ksize * ksize; P.BN = BN; P.n_tiles_n = n_tiles_n;
     P.wpack = static_cast<const __half*>(wpack);
     if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
-    if (N == 0) return EB_OK;
-    const long long tiles = static_cast<long long>(N) * ((H + 15) / 16) * ((W + 15) / 16) * n_tiles_n;
-    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (ksize == 3) {
-        if (int rc = set_smem(conv_igemm_kernel<1>, CV_SMEM_BYTES)) return rc;
-        conv_igemm_kernel<1><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
-    } else {
-        if (int rc = set_smem(conv_igemm_kernel<0>, CV_SMEM_BYTES)) return rc;
-        conv_igemm_kernel<0><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
-    }
-    return check_launch("conv_igemm");
+    return launch_conv(P, static_cast<cudaStream_t>(stream));
 }
 
 static int launch_dcn(DcnParams& P, cudaStream_t st) {
@@ -277,13 +280,38 @@ int eb_mdcn_forward(const float* x, const float* offset, const float* mask, cons
     return launch_dcn(P, st);
 }
 
+namespace {
+struct BwdWs {
+    size_t x16, go16, wT, gcol16, gx32, colT, goT, total;
+    int Cout64, BN, mt;
+    long long P, Ppad;
+};
+BwdWs bwd_ws(int N, int C, int H, int W, int Cout, int K, int Ho, int Wo) {
+    BwdWs w;
+    w.Cout64 = ((Cout + 63) / 64) * 64;
+    w.BN = (C % 128 == 0) ? 128 : 64;
+    w.mt = (Cout + 127) / 128;
+    w.P = static_cast<long long>(N) * Ho * Wo;
+    w.Ppad = ((w.P + 63) / 64) * 64;
+    size_t o = 0;
+    w.x16 = o;    o += up256(static_cast<size_t>(N) * H * W * C * 2);
+    w.go16 = o;   o += up256(static_cast<size_t>(w.P) * w.Cout64 * 2);
+    w.wT = o;     o += up256(static_cast<size_t>(K) * C * w.Cout64 * 2);
+    w.gcol16 = o; o += up256(static_cast<size_t>(w.P) * K * C * 2);
+    w.gx32 = o;   o += up256(static_cast<size_t>(N) * H * W * C * 4);
+    w.colT = o;   o += up256(static_cast<size_t>(K) * C * w.Ppad * 2);
+    w.goT = o;    o += up256(static_cast<size_t>(w.mt) * 128 * w.Ppad * 2);
+    w.total = o;
+    return w;
+}
+}  // namespace
+
 size_t eb_mdcn_backward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int stride,
                                   int pad, int dil) {
-    (void)N; (void)Cout; (void)stride; (void)pad; (void)dil;
-    // one sample's gcol [C*K][Ho*Wo] fp32 (upper bound: Ho*Wo <= (H+2p)*(W+2p))
     const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
     const int Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
-    return up256(static_cast<size_t>(C) * kh * kw * (Ho > 0 ? Ho : 0) * (Wo > 0 ? Wo : 0) * 4);
+    if (Ho < 1 || Wo < 1 || N < 1) return 256;
+    return bwd_ws(N, C, H, W, Cout, kh * kw, Ho, Wo).total;
 }
 
 int eb_mdcn_backward(const float* x, const float* offset, const float* mask, const float* weight,
@@ -297,19 +325,77 @@ int eb_mdcn_backward(const float* x, const float* offset, const float* mask, con
         groups < 1 || dg < 1 || C % dg || C % groups || Cout % groups)
         return fail(EB_ERR_INVALID_SHAPE, "mdcn_backward: invalid shape");
     if (groups != 1) return fail(EB_ERR_UNSUPPORTED, "mdcn_backward: groups=%d (only 1; EDVR uses 1)", groups);
+    if (C % 64 || (C / dg) % 8) return fail(EB_ERR_UNSUPPORTED, "mdcn_backward: C=%d dg=%d (C %% 64 == 0, (C/dg) %% 8 == 0)", C, dg);
     const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
     const int Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
     if (Ho < 1 || Wo < 1) return fail(EB_ERR_INVALID_SHAPE, "mdcn_backward: empty output");
-    if (workspace_bytes < eb_mdcn_backward_workspace(N, C, H, W, Cout, kh, kw, stride, pad, dil) || (!workspace && N > 0))
-        return fail(EB_ERR_WORKSPACE, "mdcn_backward: workspace too small");
     if (N == 0) return EB_OK;
-    DcnBwdParams P;
-    P.x = x; P.offset = offset; P.mask = mask; P.weight = weight; P.grad_out = grad_out;
-    P.grad_x = grad_x; P.grad_offset = grad_offset; P.grad_mask = grad_mask; P.grad_weight = grad_weight;
-    P.grad_bias = grad_bias; P.gcol = static_cast<float*>(workspace);
-    P.N = N; P.C = C; P.H = H; P.W = W; P.Cout = Cout; P.kh = kh; P.kw = kw; P.stride = stride; P.pad = pad;
-    P.dil = dil; P.dg = dg; P.Ho = Ho; P.Wo = Wo;
-    return dcn_backward_launch(P, static_cast<cudaStream_t>(stream), num_sms());
+    const int K = kh * kw;
+    const BwdWs ws = bwd_ws(N, C, H, W, Cout, K, Ho, Wo);
+    if (!workspace || workspace_bytes < ws.total)
+        return fail(EB_ERR_WORKSPACE, "mdcn_backward: workspace %zu < %zu", workspace_bytes, ws.total);
+    if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "mdcn_backward: workspace must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    __half* x16 = reinterpret_cast<__half*>(base + ws.x16);
+    __half* go16 = reinterpret_cast<__half*>(base + ws.go16);
+    __half* wT = reinterpret_cast<__half*>(base + ws.wT);
+    __half* gcol16 = reinterpret_cast<__half*>(base + ws.gcol16);
+    float* gx32 = reinterpret_cast<float*>(base + ws.gx32);
+    __half* colT = reinterpret_cast<__half*>(base + ws.colT);
+    __half* goT = reinterpret_cast<__half*>(base + ws.goT);
+    const DcnBwdGeom G{N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, Ho, Wo};
+    const int HWo = Ho * Wo;
+
+    // layouts
+    {
+        dim3 block(32, 8);
+        nchw_f32_to_nhwc_f16_kernel<<<dim3((H * W + 31) / 32, (C + 31) / 32, N), block, 0, st>>>(x, x16, C, H * W, C, 0);
+        if (ws.Cout64 != Cout) cudaMemsetAsync(go16, 0, static_cast<size_t>(ws.P) * ws.Cout64 * 2, st);
+        nchw_f32_to_nhwc_f16_kernel<<<dim3((HWo + 31) / 32, (Cout + 31) / 32, N), block, 0, st>>>(grad_out, go16, Cout, HWo, ws.Cout64, 0);
+        if (int rc = check_launch("bwd layouts")) return rc;
+    }
+    // stage 1: gcol = W^T . gO as a 1x1 conv with K*C output channels
+    {
+        const long long groups16 = static_cast<long long>(K) * C * (ws.Cout64 / 8);
+        pack_wT_kernel<<<grid_1d(groups16, 256), 256, 0, st>>>(weight, Cout, C, K, ws.Cout64, ws.BN, wT);
+        ConvParams P;
+        memset(&P, 0, sizeof(P));
+        P.src[0].ptr = go16; P.src[0].C = ws.Cout64; P.src[0].pix_stride = ws.Cout64; P.src[0].ch_off = 0;
+        P.src[0].div = 1; P.src[0].mul = 1; P.src[0].keep = 0; P.src[0].add = 0;
+        P.nsrc = 1; P.N = N; P.H = Ho; P.W = Wo; P.taps = 1; P.BN = ws.BN; P.n_tiles_n = K * C / ws.BN;
+        P.wpack = wT;
+        P.epi.act = ACT_NONE; P.epi.H = Ho; P.epi.W = Wo; P.epi.out16 = gcol16; P.epi.out16_pix_stride = K * C;
+        P.epi.out_mode = OUT_SAME;
+        if (int rc = launch_conv(P, st)) return rc;
+    }
+    // stage 2: grad_offset, grad_mask, grad_input
+    {
+        cudaMemsetAsync(gx32, 0, static_cast<size_t>(N) * H * W * C * 4, st);
+        const long long items = static_cast<long long>(N) * dg * K * HWo;
+        dcn_bwd_coord_scatter_kernel<<<grid_1d(items, 256), 256, 0, st>>>(G, x16, offset, mask, gcol16, gx32, grad_offset, grad_mask);
+        nhwc_f32_to_nchw_f32_kernel<<<dim3((H * W + 31) / 32, (C + 31) / 32, N), dim3(32, 8), 0, st>>>(gx32, grad_x, C, H * W);
+        if (int rc = check_launch("bwd coord/scatter")) return rc;
+    }
+    // stage 3: grad_weight (+= over the batch), grad_bias
+    {
+        cudaMemsetAsync(goT, 0, static_cast<size_t>(ws.mt) * 128 * ws.Ppad * 2, st);
+        if (ws.Ppad != ws.P) cudaMemsetAsync(colT, 0, static_cast<size_t>(K) * C * ws.Ppad * 2, st);
+        dcn_bwd_goT_kernel<<<grid_1d(static_cast<long long>(N) * Cout * HWo, 256), 256, 0, st>>>(grad_out, goT, N, Cout, HWo, ws.Ppad);
+        dcn_bwd_colT_kernel<<<grid_1d(static_cast<long long>(N) * (C / 8) * K * HWo, 256), 256, 0, st>>>(G, x16, offset, mask, colT, ws.Ppad);
+        const int ntn = K * C / ws.BN;
+        const long long steps = ws.Ppad / 64;
+        long long want = (2LL * num_sms() + ntn * ws.mt - 1) / (ntn * ws.mt);   // ~2 waves of CTAs
+        if (want < 1) want = 1;
+        if (want > steps) want = steps;
+        const int sps = static_cast<int>((steps + want - 1) / want);
+        const int splits = static_cast<int>((steps + sps - 1) / sps);
+        if (int rc = set_smem(dcn_bwd_wgrad_kernel, WG_SMEM_BYTES)) return rc;
+        dcn_bwd_wgrad_kernel<<<dim3(ntn, ws.mt, splits), 128, WG_SMEM_BYTES, st>>>(goT, colT, grad_weight, Cout, C, K, ws.Ppad, ws.BN, sps);
+        if (grad_bias) dcn_bwd_bias_kernel<<<Cout, 256, 0, st>>>(grad_out, grad_bias, N, Cout, HWo);
+        if (int rc = check_launch("bwd wgrad")) return rc;
+    }
+    return EB_OK;
 }
 
 // ---- layout / elementwise ---------------------------------------------------------------------

@@ -115,8 +115,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
 
     // ---- one-time setup
     const int cout_packed = P.BN * P.n_tiles_n;
-    for (int i = threadIdx.x; i < cout_packed; i += blockDim.x)
-        bias_s[i] = P.epi.bias ? P.epi.bias[i] : 0.f;
+    const bool has_bias = P.epi.bias != nullptr;   // host guarantees cout_packed <= CV_MAX_COUT then
+    if (has_bias)
+        for (int i = threadIdx.x; i < cout_packed; i += blockDim.x) bias_s[i] = P.epi.bias[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < CV_A_BUFS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < CV_B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
                 for (int cc = 0; cc < P.BN; cc += 32) {
                     float v[32];
                     tmem_ld32(t0 + cc, v);
-                    epi_store32(P.epi, bias_s, v, img, y, x, nt * P.BN + cc, valid);
+                    epi_store32(P.epi, has_bias ? bias_s : nullptr, v, img, y, x, nt * P.BN + cc, valid);
                 }
             }
             tc_fence_before_sync();

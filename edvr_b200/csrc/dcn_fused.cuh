@@ -131,8 +131,9 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
     const uint32_t b_bytes = static_cast<uint32_t>(P.BN) * 128u;
 
     const int cout_packed = P.BN * P.n_tiles_n;
-    for (int i = threadIdx.x; i < cout_packed; i += blockDim.x)
-        bias_s[i] = P.epi.bias ? P.epi.bias[i] : 0.f;
+    const bool has_bias = P.epi.bias != nullptr;
+    if (has_bias)
+        for (int i = threadIdx.x; i < cout_packed; i += blockDim.x) bias_s[i] = P.epi.bias[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < DC_STAGES; ++i) { mbar_init(&full[i], DC_GATHER_THREADS + 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             for (int cc = 0; cc < P.BN; cc += 32) {
                 float v[32];
                 tmem_ld32(t0 + cc, v);
-                epi_store32(P.epi, bias_s, v, img, y, x, nt * P.BN + cc, valid);
+                epi_store32(P.epi, has_bias ? bias_s : nullptr, v, img, y, x, nt * P.BN + cc, valid);
             }
             tc_fence_before_sync();
             mbar_arrive(&acc_empty[ab]);

@@ -1,0 +1,228 @@
+"""Drop-in for ``basicsr.models.ops.dcn`` (B2/B3 boundary of SURVEY §8b) on the B200 kernels.
+
+Same public names, argument meaning, parameter names/shapes/initialisation and error behaviour as
+/root/reference/basicsr/models/ops/dcn/deform_conv.py:
+  ModulatedDeformConvFunction / modulated_deform_conv ... :111-185
+  ModulatedDeformConv ................................. :295-342
+  ModulatedDeformConvPack ............................. :345-390
+and DCNv2Pack of /root/reference/basicsr/models/archs/arch_util.py:232-257.
+The v1 names (DeformConv, DeformConvPack, deform_conv) are exported for import compatibility and
+raise NotImplementedError when called: EDVR never reaches them.
+
+There is no CPU path and no fallback: CPU tensors raise NotImplementedError exactly like the
+reference (deform_conv.py:133-134), and a missing libedvr_b200.so raises RuntimeError.
+"""
+import logging
+import math
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair, _single
+
+from . import _lib as L
+from . import ops
+
+
+def _out_hw(H, W, kh, kw, stride, padding, dilation):
+    return ((H + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1,
+            (W + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1)
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class ModulatedDeformConvFunction(Function):
+
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                deformable_groups=1):
+        ctx.stride, ctx.padding, ctx.dilation = stride, padding, dilation
+        ctx.groups, ctx.deformable_groups = groups, deformable_groups
+        ctx.with_bias = bias is not None
+        if not input.is_cuda:
+            raise NotImplementedError
+        if weight.requires_grad or mask.requires_grad or offset.requires_grad or input.requires_grad:
+            ctx.save_for_backward(input, offset, mask, weight, bias if ctx.with_bias else input.new_empty(1))
+        out = ops.mdcn_forward(_f32c(input), _f32c(offset), _f32c(mask), _f32c(weight),
+                               _f32c(bias) if ctx.with_bias else None, stride, padding, dilation, groups,
+                               deformable_groups)
+        return out.to(input.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        input, offset, mask, weight, bias = ctx.saved_tensors
+        gx, goff, gmask, gw, gb = mdcn_backward(_f32c(input), _f32c(offset), _f32c(mask), _f32c(weight),
+                                                _f32c(grad_output), ctx.with_bias, ctx.stride, ctx.padding,
+                                                ctx.dilation, ctx.groups, ctx.deformable_groups)
+        return (gx.to(input.dtype), goff.to(offset.dtype), gmask.to(mask.dtype), gw.to(weight.dtype),
+                gb.to(bias.dtype) if ctx.with_bias else None, None, None, None, None, None)
+
+
+def mdcn_backward(x, offset, mask, weight, grad_out, with_bias, stride, padding, dilation, groups, dg):
+    """All five gradients through eb_mdcn_backward (fp32 NCHW, reference layouts)."""
+    N, C, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    gx = torch.empty_like(x)
+    goff = torch.empty_like(offset)
+    gmask = torch.empty_like(mask)
+    gw = torch.zeros_like(weight)
+    gb = torch.zeros(Cout, dtype=torch.float32, device=x.device) if with_bias else None
+    need = L.lib().eb_mdcn_backward_workspace(N, C, H, W, Cout, kh, kw, stride, padding, dilation)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=x.device)
+    L.check(L.lib().eb_mdcn_backward(L.ptr(x), L.ptr(offset), L.ptr(mask), L.ptr(weight), L.ptr(grad_out),
+                                     L.ptr(gx), L.ptr(goff), L.ptr(gmask), L.ptr(gw), L.ptr(gb), N, C, H, W, Cout,
+                                     kh, kw, stride, padding, dilation, groups, dg, L.ptr(ws), ws.numel(),
+                                     L.stream_ptr()), "eb_mdcn_backward")
+    return gx, goff, gmask, gw, gb
+
+
+modulated_deform_conv = ModulatedDeformConvFunction.apply
+
+
+def deform_conv(*args, **kwargs):
+    raise NotImplementedError("DCNv1 (deform_conv) is not on the EDVR hot path; see DESIGN.md (row f3)")
+
+
+class ModulatedDeformConv(nn.Module):
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=True):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride = stride
+        self.padding = padding
+        self.dilation = dilation
+        self.groups = groups
+        self.deformable_groups = deformable_groups
+        self.with_bias = bias
+        self.transposed = False
+        self.output_padding = _single(0)
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.init_weights()
+
+    def init_weights(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1.0 / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.zero_()
+
+    def forward(self, x, offset, mask):
+        return modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
+                                     self.dilation, self.groups, self.deformable_groups)
+
+
+class ModulatedDeformConvPack(ModulatedDeformConv):
+    """conv_offset (zero-initialised) + modulated deformable conv, like the reference's Pack."""
+
+    _version = 2
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.conv_offset = nn.Conv2d(self.in_channels,
+                                     self.deformable_groups * 3 * self.kernel_size[0] * self.kernel_size[1],
+                                     kernel_size=self.kernel_size, stride=_pair(self.stride),
+                                     padding=_pair(self.padding), dilation=_pair(self.dilation), bias=True)
+        self.init_weights()
+        self._packed = None
+
+    def init_weights(self):
+        super().init_weights()
+        if hasattr(self, "conv_offset"):
+            self.conv_offset.weight.data.zero_()
+            self.conv_offset.bias.data.zero_()
+
+    # -- fused inference path: conv_offset -> packed (offset, sigmoid(mask)) -> DCN, no host sync
+    def _fusable(self, x):
+        k = self.kernel_size
+        return (not torch.is_grad_enabled() and x.is_cuda and k == (3, 3) and self.stride == 1 and self.padding == 1
+                and self.dilation == 1 and self.groups == 1 and self.in_channels % 64 == 0
+                and (self.in_channels // self.deformable_groups) % 8 == 0)
+
+    def _packs(self):
+        key = tuple(int(p._version) for p in self.parameters()) + (self.weight.data_ptr(),)
+        if self._packed is None or self._packed[0] != key:
+            pw = ops.pack_conv(self.weight.detach().float(), None if self.bias is None else self.bias.detach().float(),
+                               tap_major=True)
+            po = ops.pack_conv(self.conv_offset.weight.detach().float(), self.conv_offset.bias.detach().float(),
+                               row_map=ops.dcn_offset_row_map(self.deformable_groups))
+            self._packed = (key, pw, po)
+        return self._packed[1], self._packed[2]
+
+    def _fused_forward(self, x, feat, warn=True):
+        pw, po = self._packs()
+        xv, fv = ops.nchw_to_nhwc(x.float()), ops.nchw_to_nhwc(feat.float())
+        offp = ops.new_act(fv.N, fv.H, fv.W, self.deformable_groups * 32, x.device)
+        acc = torch.zeros(1, dtype=torch.float32, device=x.device)
+        ops.conv2d(po, [fv], out16=offp, act=ops.ACT_DCN_PACK, absmean=acc)
+        out = torch.empty(xv.N, self.out_channels, xv.H, xv.W, dtype=torch.float32, device=x.device)
+        ops.dcn_nhwc(pw, xv, offp, self.deformable_groups, out_nchw=out, nchw_C=self.out_channels)
+        self.last_offset_abssum = (acc, fv.N * fv.H * fv.W * self.deformable_groups * 18)   # checked lazily
+        return out.to(x.dtype)
+
+    def forward(self, x):
+        if self._fusable(x):
+            return self._fused_forward(x, x)
+        out = self.conv_offset(x)
+        o1, o2, mask = torch.chunk(out, 3, dim=1)
+        offset = torch.cat((o1, o2), dim=1)
+        mask = torch.sigmoid(mask)
+        return modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
+                                     self.dilation, self.groups, self.deformable_groups)
+
+
+class DCNv2Pack(ModulatedDeformConvPack):
+    """Offsets and masks come from a second feature map (arch_util.py:232-257).
+
+    The reference's `offset_absmean > 50` warning forces a device->host sync on every call
+    (arch_util.py:249-253).  Here the sum is accumulated on the device; call
+    ``check_offset_absmean()`` whenever convenient to get the same warning without stalling the stream.
+    """
+
+    def forward(self, x, feat):
+        if self._fusable(x):
+            return self._fused_forward(x, feat)
+        out = self.conv_offset(feat)
+        o1, o2, mask = torch.chunk(out, 3, dim=1)
+        offset = torch.cat((o1, o2), dim=1)
+        mask = torch.sigmoid(mask)
+        self.last_offset_abssum = (offset.detach().abs().sum().reshape(1), offset.numel())
+        return modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
+                                     self.dilation, self.groups, self.deformable_groups)
+
+    def check_offset_absmean(self):
+        acc, n = getattr(self, "last_offset_abssum", (None, 0))
+        if acc is None:
+            return None
+        mean = float(acc.item()) / max(n, 1)
+        if mean > 50:
+            logging.getLogger("basicsr").warning(f"Offset abs mean is {mean}, larger than 50.")
+        return mean
+
+
+class DeformConv(nn.Module):
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        raise NotImplementedError("DCNv1 is not on the EDVR hot path; see DESIGN.md (row f3)")
+
+
+class DeformConvPack(DeformConv):
+    pass
+
+
+__all__ = ["DeformConv", "DeformConvPack", "ModulatedDeformConv", "ModulatedDeformConvPack", "deform_conv",
+           "modulated_deform_conv", "DCNv2Pack"]

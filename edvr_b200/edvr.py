@@ -1,0 +1,310 @@
+"""Drop-in module types for ``basicsr.models.archs.edvr_arch`` / ``arch_util`` (B3 boundary).
+
+Same class names, constructor signatures, parameter names, shapes and initialisation as the reference
+(/root/reference/basicsr/models/archs/edvr_arch.py:9-117 PCDAlignment, :120-214 TSAFusion, :217-269
+PredeblurModule, :272-420 EDVR; arch_util.py:51-64 make_layer, :67-95 ResidualBlockNoBN), so reference
+checkpoints load with ``strict=True``.  The modules only OWN parameters; ``forward`` hands them to the
+B200 executor (edvr_b200/engine.py).  Packed weights are cached and re-packed when a parameter changes.
+
+Inference (torch.no_grad) runs entirely on the sm_100a kernels.  With autograd enabled the graph is
+evaluated with differentiable PyTorch ops around the custom DCN autograd Function (edvr_b200/dcn.py) —
+the training configuration (BASELINE cfg 5) is a later row of the scope table.
+"""
+import torch
+from torch import nn
+from torch.nn import functional as F
+from torch.nn import init
+
+from . import ops
+from .dcn import DCNv2Pack
+from .engine import EDVREngine, _Arena, pack_pcd, pack_tsa, run_pcd, run_tsa
+
+
+@torch.no_grad()
+def default_init_weights(module_list, scale=1, bias_fill=0, **kwargs):
+    if not isinstance(module_list, list):
+        module_list = [module_list]
+    for module in module_list:
+        for m in module.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                init.kaiming_normal_(m.weight, **kwargs)
+                m.weight.data *= scale
+                if m.bias is not None:
+                    m.bias.data.fill_(bias_fill)
+
+
+def make_layer(basic_block, num_basic_block, **kwarg):
+    return nn.Sequential(*[basic_block(**kwarg) for _ in range(num_basic_block)])
+
+
+def _params_key(module):
+    return tuple((p.data_ptr(), int(p._version)) for p in module.parameters())
+
+
+def _sd(module, prefix=""):
+    return {prefix + k: v for k, v in module.state_dict().items()}
+
+
+class ResidualBlockNoBN(nn.Module):
+    """x + conv2(relu(conv1(x))) * res_scale  (arch_util.py:67-95)."""
+
+    def __init__(self, num_feat=64, res_scale=1, pytorch_init=False):
+        super().__init__()
+        self.res_scale = res_scale
+        self.conv1 = nn.Conv2d(num_feat, num_feat, 3, 1, 1, bias=True)
+        self.conv2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1, bias=True)
+        self.relu = nn.ReLU(inplace=True)
+        if not pytorch_init:
+            default_init_weights([self.conv1, self.conv2], 0.1)
+        self._cache = None
+
+    def forward(self, x):
+        C = self.conv1.in_channels
+        if torch.is_grad_enabled() or not x.is_cuda or C % 64 or self.res_scale != 1:
+            return x + self.conv2(F.relu(self.conv1(x))) * self.res_scale
+        key = _params_key(self)
+        if self._cache is None or self._cache[0] != key:
+            self._cache = (key, ops.pack_conv(self.conv1.weight.detach().float(), self.conv1.bias.detach().float()),
+                           ops.pack_conv(self.conv2.weight.detach().float(), self.conv2.bias.detach().float()))
+        xv = ops.nchw_to_nhwc(x.float())
+        t, o = ops.new_act(xv.N, xv.H, xv.W, C), ops.new_act(xv.N, xv.H, xv.W, C)
+        ops.conv2d(self._cache[1], [xv], out16=t, act=ops.ACT_RELU)
+        ops.conv2d(self._cache[2], [t], out16=o, act=ops.ACT_NONE, res16=xv)
+        return ops.nhwc_to_nchw(o).to(x.dtype)
+
+
+class PCDAlignment(nn.Module):
+    """Pyramid, cascading and deformable alignment (edvr_arch.py:9-117)."""
+
+    def __init__(self, num_feat=64, deformable_groups=8):
+        super().__init__()
+        self.offset_conv1 = nn.ModuleDict()
+        self.offset_conv2 = nn.ModuleDict()
+        self.offset_conv3 = nn.ModuleDict()
+        self.dcn_pack = nn.ModuleDict()
+        self.feat_conv = nn.ModuleDict()
+        for i in range(3, 0, -1):
+            level = f"l{i}"
+            self.offset_conv1[level] = nn.Conv2d(num_feat * 2, num_feat, 3, 1, 1)
+            self.offset_conv2[level] = nn.Conv2d(num_feat if i == 3 else num_feat * 2, num_feat, 3, 1, 1)
+            if i < 3:
+                self.offset_conv3[level] = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+                self.feat_conv[level] = nn.Conv2d(num_feat * 2, num_feat, 3, 1, 1)
+            self.dcn_pack[level] = DCNv2Pack(num_feat, num_feat, 3, padding=1, deformable_groups=deformable_groups)
+        self.cas_offset_conv1 = nn.Conv2d(num_feat * 2, num_feat, 3, 1, 1)
+        self.cas_offset_conv2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.cas_dcnpack = DCNv2Pack(num_feat, num_feat, 3, padding=1, deformable_groups=deformable_groups)
+        self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+        self.num_feat, self.deformable_groups = num_feat, deformable_groups
+        self._cache = None
+
+    def _autograd_forward(self, nbr, ref):
+        lrelu = lambda t: F.leaky_relu(t, 0.1)
+        up_off = up_feat = feat = None
+        for i in (3, 2, 1):
+            L = f"l{i}"
+            off = lrelu(self.offset_conv1[L](torch.cat([nbr[i - 1], ref[i - 1]], 1)))
+            if i == 3:
+                off = lrelu(self.offset_conv2[L](off))
+            else:
+                off = lrelu(self.offset_conv3[L](lrelu(self.offset_conv2[L](torch.cat([off, up_off], 1)))))
+            feat = self.dcn_pack[L](nbr[i - 1], off)
+            if i < 3:
+                feat = self.feat_conv[L](torch.cat([feat, up_feat], 1))
+            if i > 1:
+                feat = lrelu(feat)
+                up_off, up_feat = self.upsample(off) * 2, self.upsample(feat)
+        off = lrelu(self.cas_offset_conv2(lrelu(self.cas_offset_conv1(torch.cat([feat, ref[0]], 1)))))
+        return lrelu(self.cas_dcnpack(feat, off))
+
+    def forward(self, nbr_feat_l, ref_feat_l):
+        x0 = nbr_feat_l[0]
+        if torch.is_grad_enabled() or not x0.is_cuda or self.num_feat % 64:
+            return self._autograd_forward(nbr_feat_l, ref_feat_l)
+        key = _params_key(self)
+        if self._cache is None or self._cache[0] != key:
+            p = {}
+            pack_pcd(p, {k: v.detach().float() for k, v in _sd(self, "pcd.").items()}, "pcd.", self.deformable_groups)
+            self._cache = (key, p, _Arena(x0.device))
+        _, p, arena = self._cache
+        nbr = [ops.nchw_to_nhwc(t.float()) for t in nbr_feat_l]
+        ref = [ops.nchw_to_nhwc(t.float()) for t in ref_feat_l]
+        out = ops.new_act(nbr[0].N, nbr[0].H, nbr[0].W, self.num_feat)
+        run_pcd(arena, p, "pcd.", self.deformable_groups, None, nbr, ref, None, out)
+        return ops.nhwc_to_nchw(out).to(x0.dtype)
+
+
+class TSAFusion(nn.Module):
+    """Temporal-spatial attention fusion (edvr_arch.py:120-214)."""
+
+    def __init__(self, num_feat=64, num_frame=5, center_frame_idx=2):
+        super().__init__()
+        self.center_frame_idx = center_frame_idx
+        self.temporal_attn1 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.temporal_attn2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.feat_fusion = nn.Conv2d(num_frame * num_feat, num_feat, 1, 1)
+        self.max_pool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.avg_pool = nn.AvgPool2d(3, stride=2, padding=1)
+        self.spatial_attn1 = nn.Conv2d(num_frame * num_feat, num_feat, 1)
+        self.spatial_attn2 = nn.Conv2d(num_feat * 2, num_feat, 1)
+        self.spatial_attn3 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.spatial_attn4 = nn.Conv2d(num_feat, num_feat, 1)
+        self.spatial_attn5 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.spatial_attn_l1 = nn.Conv2d(num_feat, num_feat, 1)
+        self.spatial_attn_l2 = nn.Conv2d(num_feat * 2, num_feat, 3, 1, 1)
+        self.spatial_attn_l3 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.spatial_attn_add1 = nn.Conv2d(num_feat, num_feat, 1)
+        self.spatial_attn_add2 = nn.Conv2d(num_feat, num_feat, 1)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+        self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
+        self.num_feat = num_feat
+        self._cache = None
+
+    def _autograd_forward(self, aligned):
+        lrelu = lambda t: F.leaky_relu(t, 0.1)
+        b, t, c, h, w = aligned.shape
+        emb_ref = self.temporal_attn1(aligned[:, self.center_frame_idx])
+        emb = self.temporal_attn2(aligned.reshape(-1, c, h, w)).view(b, t, -1, h, w)
+        prob = torch.sigmoid((emb * emb_ref.unsqueeze(1)).sum(2, keepdim=True))
+        x = (aligned * prob).reshape(b, t * c, h, w)
+        feat = lrelu(self.feat_fusion(x))
+        attn = lrelu(self.spatial_attn1(x))
+        attn = lrelu(self.spatial_attn2(torch.cat([self.max_pool(attn), self.avg_pool(attn)], 1)))
+        lvl = lrelu(self.spatial_attn_l1(attn))
+        lvl = lrelu(self.spatial_attn_l2(torch.cat([self.max_pool(lvl), self.avg_pool(lvl)], 1)))
+        lvl = self.upsample(lrelu(self.spatial_attn_l3(lvl)))
+        attn = self.upsample(lrelu(self.spatial_attn4(lrelu(self.spatial_attn3(attn)) + lvl)))
+        attn = self.spatial_attn5(attn)
+        add = self.spatial_attn_add2(lrelu(self.spatial_attn_add1(attn)))
+        return feat * torch.sigmoid(attn) * 2 + add
+
+    def forward(self, aligned_feat):
+        b, t, c, h, w = aligned_feat.size()
+        if torch.is_grad_enabled() or not aligned_feat.is_cuda or self.num_feat % 64 or h % 4 or w % 4:
+            return self._autograd_forward(aligned_feat)
+        key = _params_key(self)
+        if self._cache is None or self._cache[0] != key:
+            p = {}
+            pack_tsa(p, {k: v.detach().float() for k, v in _sd(self, "tsa.").items()}, "tsa.")
+            self._cache = (key, p, _Arena(aligned_feat.device))
+        _, p, arena = self._cache
+        av = ops.nchw_to_nhwc(aligned_feat.reshape(b * t, c, h, w).float())
+        f16 = ops.new_act(b, h, w, c)
+        run_tsa(arena, p, "tsa.", av, b, t, self.center_frame_idx, f16, None)
+        return ops.nhwc_to_nchw(f16).to(aligned_feat.dtype)
+
+
+class PredeblurModule(nn.Module):
+    """Pre-deblur pyramid (edvr_arch.py:217-269)."""
+
+    def __init__(self, num_in_ch=3, num_feat=64, hr_in=False):
+        super().__init__()
+        self.hr_in = hr_in
+        self.conv_first = nn.Conv2d(num_in_ch, num_feat, 3, 1, 1)
+        if self.hr_in:
+            self.stride_conv_hr1 = nn.Conv2d(num_feat, num_feat, 3, 2, 1)
+            self.stride_conv_hr2 = nn.Conv2d(num_feat, num_feat, 3, 2, 1)
+        self.stride_conv_l2 = nn.Conv2d(num_feat, num_feat, 3, 2, 1)
+        self.stride_conv_l3 = nn.Conv2d(num_feat, num_feat, 3, 2, 1)
+        self.resblock_l3 = ResidualBlockNoBN(num_feat=num_feat)
+        self.resblock_l2_1 = ResidualBlockNoBN(num_feat=num_feat)
+        self.resblock_l2_2 = ResidualBlockNoBN(num_feat=num_feat)
+        self.resblock_l1 = nn.ModuleList([ResidualBlockNoBN(num_feat=num_feat) for _ in range(5)])
+        self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+
+    def forward(self, x):
+        lrelu = lambda t: F.leaky_relu(t, 0.1)
+        l1 = lrelu(self.conv_first(x))
+        if self.hr_in:
+            l1 = lrelu(self.stride_conv_hr2(lrelu(self.stride_conv_hr1(l1))))
+        l2 = lrelu(self.stride_conv_l2(l1))
+        l3 = lrelu(self.stride_conv_l3(l2))
+        l3 = self.upsample(self.resblock_l3(l3))
+        l2 = self.upsample(self.resblock_l2_2(self.resblock_l2_1(l2) + l3))
+        for i in range(2):
+            l1 = self.resblock_l1[i](l1)
+        l1 = l1 + l2
+        for i in range(2, 5):
+            l1 = self.resblock_l1[i](l1)
+        return l1
+
+
+class EDVR(nn.Module):
+    """EDVR network, x4 video SR / restoration (edvr_arch.py:272-420)."""
+
+    def __init__(self, num_in_ch=3, num_out_ch=3, num_feat=64, num_frame=5, deformable_groups=8,
+                 num_extract_block=5, num_reconstruct_block=10, center_frame_idx=2, hr_in=False,
+                 with_predeblur=False, with_tsa=True):
+        super().__init__()
+        self.center_frame_idx = num_frame // 2 if center_frame_idx is None else center_frame_idx
+        self.hr_in, self.with_predeblur, self.with_tsa = hr_in, with_predeblur, with_tsa
+        self.num_frame, self.num_feat = num_frame, num_feat
+        if self.with_predeblur:
+            self.predeblur = PredeblurModule(num_feat=num_feat, hr_in=self.hr_in)
+            self.conv_1x1 = nn.Conv2d(num_feat, num_feat, 1, 1)
+        else:
+            self.conv_first = nn.Conv2d(num_in_ch, num_feat, 3, 1, 1)
+        self.feature_extraction = make_layer(ResidualBlockNoBN, num_extract_block, num_feat=num_feat)
+        self.conv_l2_1 = nn.Conv2d(num_feat, num_feat, 3, 2, 1)
+        self.conv_l2_2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_l3_1 = nn.Conv2d(num_feat, num_feat, 3, 2, 1)
+        self.conv_l3_2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.pcd_align = PCDAlignment(num_feat=num_feat, deformable_groups=deformable_groups)
+        if self.with_tsa:
+            self.fusion = TSAFusion(num_feat=num_feat, num_frame=num_frame, center_frame_idx=self.center_frame_idx)
+        else:
+            self.fusion = nn.Conv2d(num_frame * num_feat, num_feat, 1, 1)
+        self.reconstruction = make_layer(ResidualBlockNoBN, num_reconstruct_block, num_feat=num_feat)
+        self.upconv1 = nn.Conv2d(num_feat, num_feat * 4, 3, 1, 1)
+        self.upconv2 = nn.Conv2d(num_feat, 64 * 4, 3, 1, 1)
+        self.pixel_shuffle = nn.PixelShuffle(2)
+        self.conv_hr = nn.Conv2d(64, 64, 3, 1, 1)
+        self.conv_last = nn.Conv2d(64, 3, 3, 1, 1)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+        self._engine = None
+
+    def engine(self):
+        """The B200 executor for the current parameters (re-packed when any parameter changed)."""
+        key = _params_key(self)
+        if self._engine is None or self._engine[0] != key:
+            dev = next(self.parameters()).device
+            self._engine = (key, EDVREngine(self.state_dict(), self.num_frame, self.center_frame_idx,
+                                            self.hr_in, device=dev))
+        return self._engine[1]
+
+    def _autograd_forward(self, x):
+        lrelu = lambda t: F.leaky_relu(t, 0.1)
+        b, t, c, h, w = x.size()
+        xc = x[:, self.center_frame_idx].contiguous()
+        if self.with_predeblur:
+            l1 = self.conv_1x1(self.predeblur(x.view(-1, c, h, w)))
+            if self.hr_in:
+                h, w = h // 4, w // 4
+        else:
+            l1 = lrelu(self.conv_first(x.view(-1, c, h, w)))
+        l1 = self.feature_extraction(l1)
+        l2 = lrelu(self.conv_l2_2(lrelu(self.conv_l2_1(l1))))
+        l3 = lrelu(self.conv_l3_2(lrelu(self.conv_l3_1(l2))))
+        l1, l2, l3 = l1.view(b, t, -1, h, w), l2.view(b, t, -1, h // 2, w // 2), l3.view(b, t, -1, h // 4, w // 4)
+        ci = self.center_frame_idx
+        ref = [l1[:, ci], l2[:, ci], l3[:, ci]]
+        aligned = torch.stack([self.pcd_align([l1[:, i], l2[:, i], l3[:, i]], ref) for i in range(t)], 1)
+        feat = self.fusion(aligned if self.with_tsa else aligned.view(b, -1, h, w))
+        out = self.reconstruction(feat)
+        out = lrelu(self.pixel_shuffle(self.upconv1(out)))
+        out = lrelu(self.pixel_shuffle(self.upconv2(out)))
+        out = self.conv_last(lrelu(self.conv_hr(out)))
+        base = xc if self.hr_in else F.interpolate(xc, scale_factor=4, mode="bilinear", align_corners=False)
+        return out + base
+
+    def forward(self, x):
+        b, t, c, h, w = x.size()
+        if self.hr_in:
+            assert h % 16 == 0 and w % 16 == 0, "The height and width must be multiple of 16."
+        else:
+            assert h % 4 == 0 and w % 4 == 0, "The height and width must be multiple of 4."
+        if torch.is_grad_enabled() or not x.is_cuda or self.num_feat % 64:
+            return self._autograd_forward(x)
+        return self.engine().forward(x.float()).to(x.dtype)

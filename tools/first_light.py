@@ -34,7 +34,7 @@ def sec_selftest():
         A = torch.randn(128, K, device="cuda").half()
         B = torch.randn(N, K, device="cuda").half()
         ref = A.float() @ B.float().t()
-        for variant in (0, 1, 2, 3):
+        for variant in (0,):   # other variants probe wrong conventions (they fault)
             D = torch.full((128, N), float("nan"), device="cuda")
             rc = L.lib().eb_selftest_umma(L.ptr(A), L.ptr(B), L.ptr(D), N, K, variant, L.stream_ptr())
             torch.cuda.synchronize()

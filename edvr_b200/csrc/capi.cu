@@ -234,6 +234,7 @@ int eb_mdcn_forward(const float* x, const float* offset, const float* mask, cons
                     const float* bias, float* out, int N, int C, int H, int W, int Cout, int kh, int kw,
                     int stride, int pad, int dil, int groups, int dg, void* workspace,
                     size_t workspace_bytes, void* stream) {
+    if (N == 0 && C > 0 && H > 0 && W > 0 && Cout > 0) return EB_OK;   // empty batch: nothing to do, pointers may be NULL
     if (!x || !offset || !mask || !weight || !out) return fail(EB_ERR_NULLPTR, "mdcn_forward: null pointer");
     if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || stride < 1 || pad < 0 || dil < 1 ||
         groups < 1 || dg < 1 || C % dg || C % groups || Cout % groups)
@@ -319,6 +320,7 @@ int eb_mdcn_backward(const float* x, const float* offset, const float* mask, con
                      float* grad_weight, float* grad_bias, int N, int C, int H, int W, int Cout, int kh,
                      int kw, int stride, int pad, int dil, int groups, int dg, void* workspace,
                      size_t workspace_bytes, void* stream) {
+    if (N == 0 && C > 0 && H > 0 && W > 0 && Cout > 0) return EB_OK;   // empty batch
     if (!x || !offset || !mask || !weight || !grad_out || !grad_x || !grad_offset || !grad_mask || !grad_weight)
         return fail(EB_ERR_NULLPTR, "mdcn_backward: null pointer");
     if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || stride < 1 || pad < 0 || dil < 1 ||

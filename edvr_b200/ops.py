@@ -12,6 +12,31 @@ from ._lib import (ACT_DCN_PACK, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, OUT
                    OUT_SAME, OUT_STRIDE2)
 
 
+LAUNCHES = [0]      # number of libedvr_b200 kernel launches issued through this module (bench.py: gpu_launches)
+PROFILE = None      # when a list: (kernel name, algorithmic FLOPs, start event, end event) per call (bench.py)
+
+
+class _Rec:
+    """Counts launches and, when PROFILE is a list, brackets the call with CUDA events on the current stream."""
+
+    def __init__(self, name, kernels=1, flops=0.0):
+        self.name, self.kernels, self.flops = name, kernels, flops
+
+    def __enter__(self):
+        LAUNCHES[0] += self.kernels
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.name, self.flops, self.e0, self.e1))
+        return False
+
+
 class View:
     """Channel slice [ch_off, ch_off+C) of an NHWC fp16 tensor t[N, H, W, Ctot]."""
 
@@ -72,8 +97,9 @@ def pack_conv(weight, bias=None, row_map=None, tap_major=False, cout_packed=None
     p.cin, p.ksize, p.cout = cin, k, cout
     nbytes = L.lib().eb_packed_weight_bytes(cin, k * k, p.BN, p.n_tiles)
     p.w = torch.empty(nbytes // 2, dtype=torch.float16, device=weight.device)
-    L.check(L.lib().eb_pack_weight(L.ptr(weight), cout, cin, k * k, L.ptr(rm), p.BN, p.n_tiles,
-                                   1 if tap_major else 0, L.ptr(p.w), L.stream_ptr()), "eb_pack_weight")
+    with _Rec("pack_weight", 1):
+        L.check(L.lib().eb_pack_weight(L.ptr(weight), cout, cin, k * k, L.ptr(rm), p.BN, p.n_tiles,
+                                       1 if tap_major else 0, L.ptr(p.w), L.stream_ptr()), "eb_pack_weight")
     b = torch.zeros(cout_packed, dtype=torch.float32, device=weight.device)
     if bias is not None:
         if rm is None:
@@ -136,66 +162,77 @@ def conv2d(pc, srcs, out16=None, act=ACT_NONE, res16=None, res32=None, out32=Non
         arr[i] = _src(v, *m)
     assert sum(v.C for v in srcs) == pc.cin, (sum(v.C for v in srcs), pc.cin)
     e = _epi(pc.b, act, out16, out32, res16, res32, out_mode=out_mode, absmean=absmean)
-    L.check(L.lib().eb_conv2d(arr, len(srcs), N, v0.H, v0.W, pc.ksize, L.ptr(pc.w), pc.BN, pc.n_tiles,
-                              ctypes.byref(e), L.stream_ptr()), "eb_conv2d")
+    opix = N * v0.H * v0.W if out_mode != OUT_STRIDE2 else N * ((v0.H + 1) // 2) * ((v0.W + 1) // 2)
+    with _Rec(f"conv_igemm_{pc.ksize}x{pc.ksize}", 1, 2.0 * opix * pc.cout * pc.cin * pc.ksize * pc.ksize):
+        L.check(L.lib().eb_conv2d(arr, len(srcs), N, v0.H, v0.W, pc.ksize, L.ptr(pc.w), pc.BN, pc.n_tiles,
+                                  ctypes.byref(e), L.stream_ptr()), "eb_conv2d")
 
 
 def dcn_nhwc(pc, x, offpack, dg, out16=None, act=ACT_NONE, out_nchw=None, nchw_C=0):
     e = _epi(pc.b, act, out16, out_nchw=out_nchw, nchw_C=nchw_C)
-    L.check(L.lib().eb_dcn_nhwc(L.ptr(x.t), x.pix_stride, x.ch_off, x.N, x.H, x.W, x.C, dg, L.ptr(offpack.t),
-                                offpack.pix_stride, L.ptr(pc.w), pc.BN, pc.n_tiles, ctypes.byref(e),
-                                L.stream_ptr()), "eb_dcn_nhwc")
+    with _Rec("dcn_fused", 1, 2.0 * x.N * x.H * x.W * pc.cout * pc.cin * 9):
+        L.check(L.lib().eb_dcn_nhwc(L.ptr(x.t), x.pix_stride, x.ch_off, x.N, x.H, x.W, x.C, dg, L.ptr(offpack.t),
+                                    offpack.pix_stride, L.ptr(pc.w), pc.BN, pc.n_tiles, ctypes.byref(e),
+                                    L.stream_ptr()), "eb_dcn_nhwc")
 
 
 def nchw_to_nhwc(x, out=None):
     """fp32 [N,C,H,W] -> View fp16 [N,H,W,C]."""
     N, C, H, W = x.shape
     out = out or new_act(N, H, W, C, x.device)
-    L.check(L.lib().eb_nchw_f32_to_nhwc_f16(L.ptr(x.contiguous()), L.ptr(out.t), N, C, H, W, out.pix_stride,
-                                            out.ch_off, L.stream_ptr()), "eb_nchw_f32_to_nhwc_f16")
+    with _Rec("layout", 1):
+        L.check(L.lib().eb_nchw_f32_to_nhwc_f16(L.ptr(x.contiguous()), L.ptr(out.t), N, C, H, W, out.pix_stride,
+                                                out.ch_off, L.stream_ptr()), "eb_nchw_f32_to_nhwc_f16")
     return out
 
 
 def nhwc_to_nchw(v):
     out = torch.empty(v.N, v.C, v.H, v.W, dtype=torch.float32, device=v.t.device)
-    L.check(L.lib().eb_nhwc_f16_to_nchw_f32(L.ptr(v.t), v.pix_stride, v.ch_off, L.ptr(out), v.N, v.C, v.H, v.W,
-                                            L.stream_ptr()), "eb_nhwc_f16_to_nchw_f32")
+    with _Rec("layout", 1):
+        L.check(L.lib().eb_nhwc_f16_to_nchw_f32(L.ptr(v.t), v.pix_stride, v.ch_off, L.ptr(out), v.N, v.C, v.H, v.W,
+                                                L.stream_ptr()), "eb_nhwc_f16_to_nchw_f32")
     return out
 
 
 def conv_first(x_nchw, w, b, out, act=ACT_LRELU):
     N, _, H, W = x_nchw.shape
-    L.check(L.lib().eb_conv_first(L.ptr(x_nchw), L.ptr(w), L.ptr(b), L.ptr(out.t), N, H, W, w.shape[0],
-                                  out.pix_stride, act, L.stream_ptr()), "eb_conv_first")
+    with _Rec("conv_first", 1):
+        L.check(L.lib().eb_conv_first(L.ptr(x_nchw), L.ptr(w), L.ptr(b), L.ptr(out.t), N, H, W, w.shape[0],
+                                      out.pix_stride, act, L.stream_ptr()), "eb_conv_first")
 
 
 def conv_last(x, w, b, base, base_img_stride, scale, out_nchw):
-    L.check(L.lib().eb_conv_last(L.ptr(x.t), x.pix_stride, L.ptr(w), L.ptr(b), L.ptr(base), base_img_stride, scale,
-                                 L.ptr(out_nchw), x.N, x.H, x.W, x.C, L.stream_ptr()), "eb_conv_last")
+    with _Rec("conv_last", 1):
+        L.check(L.lib().eb_conv_last(L.ptr(x.t), x.pix_stride, L.ptr(w), L.ptr(b), L.ptr(base), base_img_stride, scale,
+                                     L.ptr(out_nchw), x.N, x.H, x.W, x.C, L.stream_ptr()), "eb_conv_last")
 
 
 def upsample2x(src, dst, mul=1.0, add=None):
     a = (None, 0, 0) if add is None else (add.t, add.pix_stride, add.ch_off)
-    L.check(L.lib().eb_upsample2x(L.ptr(src.t), src.pix_stride, src.ch_off, L.ptr(dst.t), dst.pix_stride, dst.ch_off,
-                                  src.N, src.H, src.W, src.C, mul, L.ptr(a[0]), a[1], a[2], L.stream_ptr()),
-            "eb_upsample2x")
+    with _Rec("upsample2x", 1):
+        L.check(L.lib().eb_upsample2x(L.ptr(src.t), src.pix_stride, src.ch_off, L.ptr(dst.t), dst.pix_stride, dst.ch_off,
+                                      src.N, src.H, src.W, src.C, mul, L.ptr(a[0]), a[1], a[2], L.stream_ptr()),
+                "eb_upsample2x")
 
 
 def pool_max_avg(src, dst):
-    L.check(L.lib().eb_pool_max_avg(L.ptr(src.t), src.pix_stride, src.ch_off, L.ptr(dst.t), dst.pix_stride,
-                                    dst.ch_off, src.N, src.H, src.W, src.C, L.stream_ptr()), "eb_pool_max_avg")
+    with _Rec("pool", 1):
+        L.check(L.lib().eb_pool_max_avg(L.ptr(src.t), src.pix_stride, src.ch_off, L.ptr(dst.t), dst.pix_stride,
+                                        dst.ch_off, src.N, src.H, src.W, src.C, L.stream_ptr()), "eb_pool_max_avg")
 
 
 def tsa_temporal(emb, emb_ref, aligned, dst, B, T):
-    L.check(L.lib().eb_tsa_temporal(L.ptr(emb.t), L.ptr(emb_ref.t), L.ptr(aligned.t), L.ptr(dst.t), B, T, emb.H,
-                                    emb.W, emb.C, L.stream_ptr()), "eb_tsa_temporal")
+    with _Rec("tsa_temporal", 1):
+        L.check(L.lib().eb_tsa_temporal(L.ptr(emb.t), L.ptr(emb_ref.t), L.ptr(aligned.t), L.ptr(dst.t), B, T, emb.H,
+                                        emb.W, emb.C, L.stream_ptr()), "eb_tsa_temporal")
 
 
 def tsa_modulate(feat, attn, attn_add, out16=None, out32=None):
     npix = attn.N * attn.H * attn.W
-    L.check(L.lib().eb_tsa_modulate(L.ptr(feat.t), feat.pix_stride, feat.ch_off, L.ptr(attn.t), L.ptr(attn_add.t),
-                                    L.ptr(None if out16 is None else out16.t), L.ptr(out32), npix, attn.C,
-                                    L.stream_ptr()), "eb_tsa_modulate")
+    with _Rec("tsa_modulate", 1):
+        L.check(L.lib().eb_tsa_modulate(L.ptr(feat.t), feat.pix_stride, feat.ch_off, L.ptr(attn.t), L.ptr(attn_add.t),
+                                        L.ptr(None if out16 is None else out16.t), L.ptr(out32), npix, attn.C,
+                                        L.stream_ptr()), "eb_tsa_modulate")
 
 
 def mdcn_forward(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, workspace=None):
@@ -208,7 +245,8 @@ def mdcn_forward(x, offset, mask, weight, bias, stride, padding, dilation, group
     need = L.lib().eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=x.device)
-    L.check(L.lib().eb_mdcn_forward(L.ptr(x), L.ptr(offset), L.ptr(mask), L.ptr(weight), L.ptr(bias), L.ptr(out),
-                                    N, C, H, W, Cout, kh, kw, stride, padding, dilation, groups, dg,
-                                    L.ptr(workspace), workspace.numel(), L.stream_ptr()), "eb_mdcn_forward")
+    with _Rec("mdcn_forward_op", 4):
+        L.check(L.lib().eb_mdcn_forward(L.ptr(x), L.ptr(offset), L.ptr(mask), L.ptr(weight), L.ptr(bias), L.ptr(out),
+                                        N, C, H, W, Cout, kh, kw, stride, padding, dilation, groups, dg,
+                                        L.ptr(workspace), workspace.numel(), L.stream_ptr()), "eb_mdcn_forward")
     return out

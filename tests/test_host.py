@@ -1,0 +1,88 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol (no compute calls
+without a GPU), host-side packing maps, and the N>1 sharding logic on gloo with world_size 2."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_match_header():
+    from edvr_b200 import build, _lib
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "edvr_b200.h")).read()
+    declared = set(re.findall(r"\b(eb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    h = _lib.lib()
+    for name in declared:
+        assert hasattr(h, name), f"{name} declared in include/edvr_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert h.eb_version() >= 100
+
+
+def test_host_validation_without_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on a CPU-only box."""
+    from edvr_b200 import _lib as L
+    h = L.lib()
+    assert h.eb_mdcn_forward(None, None, None, None, None, None, 1, 64, 8, 8, 64, 3, 3, 1, 1, 1, 1, 8, None, 0, None) == -5
+    one = torch.zeros(4)
+    p = L.ptr(one)
+    assert h.eb_mdcn_forward(p, p, p, p, None, p, 1, 60, 8, 8, 64, 3, 3, 1, 1, 1, 1, 4, None, 0, None) == -2   # C % 64
+    assert h.eb_mdcn_forward(p, p, p, p, None, p, 1, 64, 8, 8, 64, 3, 3, 1, 1, 1, 2, 8, None, 0, None) == -2   # groups
+    assert h.eb_mdcn_forward(p, p, p, p, None, p, 1, 64, 8, 8, 64, 3, 3, 0, 1, 1, 1, 8, None, 0, None) == -1   # stride 0
+    assert h.eb_mdcn_forward(p, p, p, p, None, p, 1, 64, 8, 8, 64, 3, 3, 1, 1, 1, 1, 8, None, 0, None) == -4   # workspace
+    assert b"workspace" in h.eb_last_error()
+    assert h.eb_mdcn_forward_workspace(1, 64, 8, 8, 64, 3, 3) >= 8 * 8 * 64 * 2
+    assert h.eb_packed_weight_bytes(128, 9, 128, 1) == 128 * 128 * 9 * 2
+
+
+def test_dcn_offset_row_map():
+    from edvr_b200.ops import dcn_offset_row_map
+    rm = dcn_offset_row_map(8)
+    assert rm.numel() == 256
+    used = rm[rm >= 0]
+    assert sorted(used.tolist()) == list(range(216))          # every conv_offset row lands exactly once
+    assert rm[32 + 18].item() == 144 + 9 and rm[32].item() == 18 and rm[27].item() == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from edvr_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libedvr_b200.so")
+    with pytest.raises(RuntimeError, match="no fallback"):
+        _lib.lib()
+
+
+def test_cpu_tensors_raise_like_reference():
+    from edvr_b200.dcn import modulated_deform_conv
+    with pytest.raises(NotImplementedError):
+        modulated_deform_conv(torch.zeros(1, 64, 4, 4), torch.zeros(1, 144, 4, 4), torch.zeros(1, 72, 4, 4),
+                              torch.zeros(64, 64, 3, 3), None, 1, 1, 1, 1, 8)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from edvr_b200 import shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    mine = shard.clip_shard(7, rank, world)
+    mx = shard.reduce_max(10.0 + rank)
+    sm = shard.reduce_sum(len(mine))
+    q.put((rank, mine, mx, sm))
+    dist.destroy_process_group()
+
+
+def test_sharding_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
+    assert all(r[2] == 11.0 for r in res) and all(r[3] == 7.0 for r in res)   # max over ranks, every clip once

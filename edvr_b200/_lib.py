@@ -38,6 +38,8 @@ _SIGS = {
     "eb_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "eb_conv2d": (c_int, [ctypes.POINTER(Src), c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                           ctypes.POINTER(Epilogue), c_void_p]),
+    "eb_conv2d_stats": (c_int, [ctypes.POINTER(Src), c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                ctypes.POINTER(Epilogue), c_void_p, c_void_p]),
     "eb_dcn_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                             c_void_p, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
     "eb_mdcn_forward_workspace": (c_size_t, [c_int] * 7),

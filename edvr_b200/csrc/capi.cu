@@ -4,10 +4,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/edvr_b200.h"
 #include "common.cuh"
 #include "conv_igemm.cuh"
+#include "conv_igemm2.cuh"
 #include "dcn_backward.cuh"
 #include "dcn_fused.cuh"
 #include "elementwise.cuh"
@@ -134,8 +136,26 @@ int eb_pack_weight(const float* w, int cout, int cin, int ktaps, const int* row_
     return check_launch("pack_weight");
 }
 
+static bool conv_force_v1() {
+    const char* e = getenv("EDVR_B200_CONV_V1");     // A/B switch for profiling; read-only, no mutable state
+    return e != nullptr && e[0] == '1';
+}
+
 static int launch_conv(const ConvParams& P, cudaStream_t st) {
     if (P.N == 0) return EB_OK;
+    if (P.BN == 128 && P.epi.out_nchw == nullptr && !conv_force_v1()) {
+        // transposed kernel: M = 128 output channels, N = 256 pixels (32 x 8 tile)
+        const long long tiles2 = static_cast<long long>(P.N) * ((P.H + C2_TH - 1) / C2_TH) * ((P.W + C2_TW - 1) / C2_TW) * P.n_tiles_n;
+        const int grid2 = static_cast<int>(tiles2 < num_sms() ? tiles2 : num_sms());
+        if (P.taps == 9) {
+            if (int rc = set_smem(conv_igemm2_kernel<1>, C2_SMEM_BYTES)) return rc;
+            conv_igemm2_kernel<1><<<grid2, C2_THREADS, C2_SMEM_BYTES, st>>>(P);
+        } else {
+            if (int rc = set_smem(conv_igemm2_kernel<0>, C2_SMEM_BYTES)) return rc;
+            conv_igemm2_kernel<0><<<grid2, C2_THREADS, C2_SMEM_BYTES, st>>>(P);
+        }
+        return check_launch("conv_igemm2");
+    }
     const long long tiles = static_cast<long long>(P.N) * ((P.H + 15) / 16) * ((P.W + 15) / 16) * P.n_tiles_n;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     if (P.taps == 9) {
@@ -150,6 +170,11 @@ static int launch_conv(const ConvParams& P, cudaStream_t st) {
 
 int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack, int BN,
               int n_tiles_n, const eb_epilogue_t* epi, void* stream) {
+    return eb_conv2d_stats(srcs, nsrc, N, H, W, ksize, wpack, BN, n_tiles_n, epi, nullptr, stream);
+}
+
+int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack, int BN,
+                    int n_tiles_n, const eb_epilogue_t* epi, unsigned long long* stats, void* stream) {
     if (!srcs || !wpack) return fail(EB_ERR_NULLPTR, "conv2d: null pointer");
     if (nsrc < 1 || nsrc > 2) return fail(EB_ERR_UNSUPPORTED, "conv2d: nsrc=%d", nsrc);
     if (ksize != 1 && ksize != 3) return fail(EB_ERR_UNSUPPORTED, "conv2d: ksize=%d", ksize);
@@ -173,6 +198,7 @@ int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, co
     P.nsrc = nsrc; P.N = N; P.H = H; P.W = W; P.taps = ksize * ksize; P.BN = BN; P.n_tiles_n = n_tiles_n;
     P.wpack = static_cast<const __half*>(wpack);
     if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
+    P.stats = stats;
     return launch_conv(P, static_cast<cudaStream_t>(stream));
 }
 
@@ -265,7 +291,7 @@ int eb_mdcn_forward(const float* x, const float* offset, const float* mask, cons
         nchw_f32_to_nhwc_f16_kernel<<<grid, block, 0, st>>>(x, x16, C, H * W, C, 0);
         if (int rc = check_launch("nchw_to_nhwc")) return rc;
     }
-    if (int rc = eb_pack_weight(weight, Cout, C, kh * kw, nullptr, BN, nt, 1, wpack, stream)) return rc;
+    if (int rc = eb_pack_weight(weight, Cout, C, kh * kw, nullptr, BN, nt, 0, wpack, stream)) return rc;
     pack_bias_kernel<<<(BN * nt + 127) / 128, 128, 0, st>>>(bias, Cout, nullptr, BN * nt, bpack);
     if (int rc = check_launch("pack_bias")) return rc;
 
@@ -431,7 +457,7 @@ int eb_conv_first(const float* x, const float* w, const float* bias, void* out, 
     if (N == 0) return EB_OK;
     const int smem = Cout * 28 * 4;
     if (int rc = set_smem(conv_first_kernel, smem)) return rc;
-    const long long items = static_cast<long long>(N) * H * W * (Cout / 8);
+    const long long items = static_cast<long long>(N) * H * ((W + 3) / 4) * (Cout / 8);
     conv_first_kernel<<<grid_1d(items, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         x, w, bias, static_cast<__half*>(out), N, H, W, Cout, out_pix_stride, act);
     return check_launch("conv_first");
@@ -446,7 +472,7 @@ int eb_conv_last(const void* x, int x_pix_stride, const float* w, const float* b
     if (N == 0) return EB_OK;
     const int smem = 27 * Cin * 4;
     if (int rc = set_smem(conv_last_kernel, smem)) return rc;
-    const long long items = static_cast<long long>(N) * H * W;
+    const long long items = static_cast<long long>(N) * H * ((W + 3) / 4);
     conv_last_kernel<<<grid_1d(items, 128), 128, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(x), x_pix_stride, w, bias, base, base_img_stride, scale, out, N, H, W, Cin);
     return check_launch("conv_last");

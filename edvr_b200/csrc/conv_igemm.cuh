@@ -49,6 +49,7 @@ struct ConvParams {
     int n_tiles_n;    // number of n-tiles; packed Cout = BN * n_tiles_n
     const __half* wpack;
     EpiParams epi;
+    unsigned long long* stats;   // optional [gridDim.x][16] cycle counters (profiling builds of the call only)
 };
 
 template <int HALO>

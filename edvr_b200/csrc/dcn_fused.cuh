@@ -9,7 +9,11 @@
 // straight into the shared-memory A operand (no-swizzle K-major planes, common.cuh); one
 // thread issues tcgen05.mma against the pre-packed weights (B operand, bulk async copies);
 // the fp32 accumulator lives in TMEM and is drained by four epilogue warps (bias, activation,
-// NHWC fp16 and/or NCHW fp32 stores).  K is walked tap-major: stage = (tap, 64-channel chunk).
+// NHWC fp16 and/or NCHW fp32 stores).  K is walked chunk-major: stage = (64-channel chunk, tap), so the nine
+// taps of a chunk re-read the same ~23 KB slab of x and hit L1.
+// Gather mapping (the L1TEX wavefront rate is the limiter of this kernel, profiles/r01_*): the 8 lanes of a
+// quarter-warp read the 8 consecutive 16-byte channel atoms of ONE sampled pixel = one full 128-byte line per
+// corner, instead of 32 lanes touching 32 different lines.
 //
 // Sampling semantics (bit-for-bit the reference's decisions, fp32 coordinate math):
 //   h_im = ho*stride - pad + i*dil + dh;  sample iff h_im > -1 && w_im > -1 && h_im < H && w_im < W
@@ -20,8 +24,9 @@
 
 namespace eb {
 
-constexpr int DC_STAGES = 6;
-constexpr int DC_A_BYTES = 128 * 128;    // 8 planes x 128 rows x 16 B
+constexpr int DC_STAGES = 4;             // 4 x 32 KB: leaves ~90 KB of the SM's L1 for the gather
+constexpr int DC_A_LBO = 128 * 16 + 16;  // plane pitch (+16 B: the 8 kc-lanes of a pixel hit 8 different bank groups)
+constexpr int DC_A_BYTES = 8 * DC_A_LBO; // 8 planes x 128 rows x 16 B (+ pad)
 constexpr int DC_B_BYTES = 128 * 128;    // BN(<=128) rows x 64 ch x 2 B
 constexpr int DC_THREADS = 448;          // 14 warps
 constexpr int DC_GATHER_THREADS = 256;
@@ -43,7 +48,7 @@ struct DcnParams {
     const float* mask;        //               [N][dg*K][Ho][Wo]
     const __half* offpack;    // OFF_PACK_F16: [N][Ho][Wo][dg*32]: per group 18 offsets, 9 masks, 5 pad
     int offpack_pix_stride;
-    const __half* wpack;      // [n_tile][tap][chunk][kc=8][BN][8] fp16
+    const __half* wpack;      // [n_tile][chunk][tap][kc=8][BN][8] fp16
     int BN, n_tiles_n;
     EpiParams epi;            // epi.H/W == Ho/Wo
 };
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                     const uint32_t b_base = smem_u32(b_smem + s * DC_B_BYTES);
 #pragma unroll
                     for (int k16 = 0; k16 < 4; ++k16) {
-                        const uint64_t ad = umma_desc_nosw(a_base + k16 * 2 * 2048, 2048, 128);
+                        const uint64_t ad = umma_desc_nosw(a_base + k16 * 2 * DC_A_LBO, DC_A_LBO, 128);
                         const uint64_t bd = umma_desc_nosw(b_base + k16 * 2 * lbo_b, lbo_b, 128);
                         umma_f16(d, ad, bd, idesc, (st | k16) != 0 ? 1u : 0u);
                     }
@@ -213,43 +218,55 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             mbar_arrive(&acc_empty[ab]);
         }
     } else {
-        // ================= gather warps (256 threads): build the A operand of each stage
-        const int tid = threadIdx.x - 192;
-        const int m = tid & 127;          // row of the tile == output pixel
-        const int kc0 = (tid >> 7) * 4;   // this thread fills planes kc0..kc0+3
+        // ================= gather warps (256 threads): build the A operand of each stage.
+        // lane -> (pixel slot = lane/8, channel atom kc = lane%8); a thread owns 4 pixels x 1 atom per stage.
+        const int gw = warp - 6;                      // 0..7
+        const int kc = lane & 7;
+        int m[4], ho[4], wo[4];
+        bool pv[4];
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int pt = tile / P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
-            const int ho = ty * DC_TILE_H + (m >> 3), wo = tx * DC_TILE_W + (m & 7);
-            const bool pix_valid = (ho < P.Ho) && (wo < P.Wo);
-            for (int st = 0; st < nstages; ++st, ++it) {
-                const int tap = st / nchunks, chunk = st - tap * nchunks;
-                const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + m * 16;
-                int g_prev = -1;
-                DcnCorner cn;
 #pragma unroll
-                for (int qk = 0; qk < 4; ++qk) {
-                    const int kc = kc0 + qk;
-                    const int ch = chunk * 64 + kc * 8;
-                    const int g = ch / P.cpg;
-                    if (g != g_prev) { cn = dcn_corner<OFFMODE>(P, img, ho, wo, pix_valid, g, tap); g_prev = g; }
+            for (int i = 0; i < 4; ++i) {
+                m[i] = i * 32 + gw * 4 + (lane >> 3);
+                ho[i] = ty * DC_TILE_H + (m[i] >> 3);
+                wo[i] = tx * DC_TILE_W + (m[i] & 7);
+                pv[i] = (ho[i] < P.Ho) && (wo[i] < P.Wo);
+            }
+            for (int st = 0; st < nstages; ++st, ++it) {
+                const int chunk = st / K, tap = st - chunk * K;
+                const int ch = chunk * 64 + kc * 8;
+                const int g = ch / P.cpg;
+                const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
+                // 1) sampling geometry of the 4 pixels (same group g, same tap)
+                DcnCorner cn[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cn[i] = dcn_corner<OFFMODE>(P, img, ho[i], wo[i], pv[i], g, tap);
+                // 2) all 16 corner loads in flight before anything is consumed
+                uint4 u[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const __half* b = cn[i].base + ch;
+                    u[i][0] = u[i][1] = u[i][2] = u[i][3] = make_uint4(0, 0, 0, 0);
+                    if (cn[i].valid & 1u) u[i][0] = ldg_nc_v4(b);
+                    if (cn[i].valid & 2u) u[i][1] = ldg_nc_v4(b + cn[i].dW);
+                    if (cn[i].valid & 4u) u[i][2] = ldg_nc_v4(b + cn[i].dH);
+                    if (cn[i].valid & 8u) u[i][3] = ldg_nc_v4(b + cn[i].dH + cn[i].dW);
+                }
+                // 3) the smem slot is needed only now
+                mbar_wait(&empty[s], ph ^ 1u);
+                const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + kc * DC_A_LBO;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
                     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    const __half* b = cn.base + ch;
-                    uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0, u2 = u0, u3 = u0;
-                    if (cn.valid & 1u) u0 = ldg_nc_v4(b);
-                    if (cn.valid & 2u) u1 = ldg_nc_v4(b + cn.dW);
-                    if (cn.valid & 4u) u2 = ldg_nc_v4(b + cn.dH);
-                    if (cn.valid & 8u) u3 = ldg_nc_v4(b + cn.dH + cn.dW);
-                    dcn_blend8(acc, u0, cn.w[0]);
-                    dcn_blend8(acc, u1, cn.w[1]);
-                    dcn_blend8(acc, u2, cn.w[2]);
-                    dcn_blend8(acc, u3, cn.w[3]);
-                    sts_v4(dst + kc * 2048,
-                           make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]),
-                                      pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7])));
+                    dcn_blend8(acc, u[i][0], cn[i].w[0]);
+                    dcn_blend8(acc, u[i][1], cn[i].w[1]);
+                    dcn_blend8(acc, u[i][2], cn[i].w[2]);
+                    dcn_blend8(acc, u[i][3], cn[i].w[3]);
+                    sts_v4(dst + m[i] * 16, make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]),
+                                                       pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7])));
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&full[s]);

@@ -91,48 +91,65 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, int cout, const in
 }
 
 // ------------------------------------------------------------------ conv_first (Cin = 3)
-// thread = (pixel, 8 output channels); weights [Cout][3][3][3] staged in smem.
+// thread = (4 consecutive pixels of a row, 8 output channels): each weight read from smem feeds 4 FMAs.
+// weights staged as ws[k = c*9+dy*3+dx][Cout] so that the 8 channels of a thread are two LDS.128.
 __global__ void conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                   const float* __restrict__ bias, __half* __restrict__ out, int N,
                                   int H, int W, int Cout, int out_pix_stride, int act) {
-    extern __shared__ float ws[];   // [Cout*27] + [Cout]
+    extern __shared__ float ws[];   // [27][Cout] + [Cout]
     float* bs = ws + Cout * 27;
-    for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) ws[i] = w[i];
+    for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) ws[(i % 27) * Cout + i / 27] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    const int groups = Cout / 8;
-    const long long total = static_cast<long long>(N) * H * W * groups;
+    const int groups = Cout / 8, W4 = (W + 3) / 4;
+    const long long total = static_cast<long long>(N) * H * W4 * groups;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int g = i % groups;
-        const long long pix = i / groups;
-        const int xw = pix % W, yh = (pix / W) % H, n = pix / (static_cast<long long>(W) * H);
-        float in[27];
+        const long long q = i / groups;
+        const int x0 = (q % W4) * 4, yh = (q / W4) % H, n = q / (static_cast<long long>(W4) * H);
+        float in[3][3][6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 6; ++dx) {
+                    const int yy = yh + dy - 1, xx = x0 + dx - 1;
+                    in[c][dy][dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                        ? __ldg(x + ((static_cast<size_t>(n) * 3 + c) * H + yy) * W + xx) : 0.f;
+                }
+        float acc[4][8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[p][e] = bs[g * 8 + e];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                    const int yy = yh + dy - 1, xx = xw + dx - 1;
-                    in[c * 9 + dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
-                        ? __ldg(x + ((static_cast<size_t>(n) * 3 + c) * H + yy) * W + xx) : 0.f;
+                    const float4 wa = *reinterpret_cast<const float4*>(ws + (c * 9 + dy * 3 + dx) * Cout + g * 8);
+                    const float4 wb = *reinterpret_cast<const float4*>(ws + (c * 9 + dy * 3 + dx) * Cout + g * 8 + 4);
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(wv[e], in[c][dy][dx + p], acc[p][e]);
                 }
-        H8 r;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float* wr = ws + (g * 8 + e) * 27;
-            float a = bs[g * 8 + e];
+        for (int p = 0; p < 4; ++p) {
+            if (x0 + p >= W) break;
+            H8 r;
 #pragma unroll
-            for (int k = 0; k < 27; ++k) a = fmaf(wr[k], in[k], a);
-            r.v[e] = apply_act(a, act);
+            for (int e = 0; e < 8; ++e) r.v[e] = apply_act(acc[p][e], act);
+            h8_store(out + ((static_cast<size_t>(n) * H + yh) * W + x0 + p) * out_pix_stride + g * 8, r);
         }
-        h8_store(out + pix * out_pix_stride + g * 8, r);
     }
 }
 
 // ------------------------------------------------------------------ conv_last (Cin -> 3) + base
-// thread = one HR pixel; w [3][Cin][3][3] in smem as [tap][c][3].
 __device__ __forceinline__ float bilinear_up_sample(const float* __restrict__ im, int h, int w,
                                                     int oy, int ox, int scale) {
     // PyTorch upsample_bilinear2d, align_corners=False (edvr_arch.py:417-418)
@@ -146,46 +163,74 @@ __device__ __forceinline__ float bilinear_up_sample(const float* __restrict__ im
     return hy * (hx * im[y0 * w + x0] + lx * im[y0 * w + x1]) +
            ly * (hx * im[y1 * w + x0] + lx * im[y1 * w + x1]);
 }
+// thread = 4 consecutive HR pixels of a row x 3 outputs; smem weights ws[dy][c8][dx][e][co] (72 floats per
+// (dy, c8)), so each LDS.128 feeds 16 FMAs and each 16-byte input load 36.
 __global__ void conv_last_kernel(const __half* __restrict__ x, int x_pix_stride,
                                  const float* __restrict__ w, const float* __restrict__ bias,
                                  const float* __restrict__ base, long long base_img_stride, int scale,
                                  float* __restrict__ out, int N, int H, int W, int Cin) {
-    extern __shared__ float ws[];   // [9][Cin][3]
+    extern __shared__ float ws[];
+    const int C8 = Cin / 8;
     for (int i = threadIdx.x; i < 27 * Cin; i += blockDim.x) {
         const int co = i / (Cin * 9), rem = i % (Cin * 9), c = rem / 9, tap = rem % 9;
-        ws[(tap * Cin + c) * 3 + co] = w[i];
+        const int dy = tap / 3, dx = tap % 3;
+        ws[(((dy * C8 + c / 8) * 3 + dx) * 8 + (c & 7)) * 3 + co] = w[i];
     }
     __syncthreads();
-    const long long total = static_cast<long long>(N) * H * W;
-    for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < total;
-         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int xw = pix % W, yh = (pix / W) % H, n = pix / (static_cast<long long>(W) * H);
-        float a0 = bias ? bias[0] : 0.f, a1 = bias ? bias[1] : 0.f, a2 = bias ? bias[2] : 0.f;
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const __half* px = x + ((static_cast<size_t>(n) * H + yy) * W + xx) * x_pix_stride;
-            const float* wt = ws + tap * Cin * 3;
-            for (int c = 0; c < Cin; c += 8) {
-                const H8 v = h8_load(px + c);
+    const int W4 = (W + 3) / 4;
+    const long long total = static_cast<long long>(N) * H * W4;
+    for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int x0 = (q % W4) * 4, yh = (q / W4) % H, n = q / (static_cast<long long>(W4) * H);
+        float acc[4][3];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    a0 = fmaf(v.v[e], wt[(c + e) * 3 + 0], a0);
-                    a1 = fmaf(v.v[e], wt[(c + e) * 3 + 1], a1);
-                    a2 = fmaf(v.v[e], wt[(c + e) * 3 + 2], a2);
+        for (int p = 0; p < 4; ++p) { acc[p][0] = bias ? bias[0] : 0.f; acc[p][1] = bias ? bias[1] : 0.f; acc[p][2] = bias ? bias[2] : 0.f; }
+        for (int dy = 0; dy < 3; ++dy) {
+            const int yy = yh + dy - 1;
+            if (yy < 0 || yy >= H) continue;
+            const __half* row = x + (static_cast<size_t>(n) * H + yy) * W * x_pix_stride;
+            for (int c8 = 0; c8 < C8; ++c8) {
+                H8 v[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int xx = x0 + j - 1;
+                    if (xx >= 0 && xx < W) v[j] = h8_load(row + static_cast<size_t>(xx) * x_pix_stride + c8 * 8);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[j].v[e] = 0.f;
+                    }
                 }
+                const float4* wq = reinterpret_cast<const float4*>(ws + (dy * C8 + c8) * 72);
+                float wl[72];
+#pragma unroll
+                for (int t = 0; t < 18; ++t) { const float4 f = wq[t]; wl[4 * t] = f.x; wl[4 * t + 1] = f.y; wl[4 * t + 2] = f.z; wl[4 * t + 3] = f.w; }
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float iv = v[p + dx].v[e];
+                            acc[p][0] = fmaf(iv, wl[(dx * 8 + e) * 3 + 0], acc[p][0]);
+                            acc[p][1] = fmaf(iv, wl[(dx * 8 + e) * 3 + 1], acc[p][1]);
+                            acc[p][2] = fmaf(iv, wl[(dx * 8 + e) * 3 + 2], acc[p][2]);
+                        }
             }
         }
         const size_t plane = static_cast<size_t>(H) * W;
-        float* o = out + static_cast<size_t>(n) * 3 * plane + static_cast<size_t>(yh) * W + xw;
         const int bh = H / scale, bw = W / scale;
         const float* b = base + static_cast<size_t>(n) * base_img_stride;
-        float acc[3] = {a0, a1, a2};
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* bc = b + static_cast<size_t>(c) * bh * bw;
-            const float bv = scale == 1 ? bc[yh * bw + xw] : bilinear_up_sample(bc, bh, bw, yh, xw, scale);
-            o[c * plane] = acc[c] + bv;
+        for (int p = 0; p < 4; ++p) {
+            const int xw = x0 + p;
+            if (xw >= W) break;
+            float* o = out + static_cast<size_t>(n) * 3 * plane + static_cast<size_t>(yh) * W + xw;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* bc = b + static_cast<size_t>(c) * bh * bw;
+                const float bv = scale == 1 ? bc[yh * bw + xw] : bilinear_up_sample(bc, bh, bw, yh, xw, scale);
+                o[c * plane] = acc[p][c] + bv;
+            }
         }
     }
 }

@@ -156,8 +156,7 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
     def _packs(self):
         key = tuple(int(p._version) for p in self.parameters()) + (self.weight.data_ptr(),)
         if self._packed is None or self._packed[0] != key:
-            pw = ops.pack_conv(self.weight.detach().float(), None if self.bias is None else self.bias.detach().float(),
-                               tap_major=True)
+            pw = ops.pack_conv(self.weight.detach().float(), None if self.bias is None else self.bias.detach().float())
             po = ops.pack_conv(self.conv_offset.weight.detach().float(), self.conv_offset.bias.detach().float(),
                                row_map=ops.dcn_offset_row_map(self.deformable_groups))
             self._packed = (key, pw, po)

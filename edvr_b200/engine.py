@@ -46,7 +46,7 @@ class _Arena:
 
 
 def pack_dcn_site(p, sd, key, dg):
-    p[key] = ops.pack_conv(sd[key + ".weight"], sd.get(key + ".bias"), tap_major=True)
+    p[key] = ops.pack_conv(sd[key + ".weight"], sd.get(key + ".bias"))
     p[key + ".conv_offset"] = ops.pack_conv(sd[key + ".conv_offset.weight"], sd[key + ".conv_offset.bias"],
                                             row_map=ops.dcn_offset_row_map(dg))
 

@@ -87,6 +87,9 @@ int eb_pack_weight(const float* w_oihw, int cout, int cin, int ktaps, const int*
 /* ---- dense convolution, NHWC fp16, 3x3 (pad 1) or 1x1, stride 1 (stride 2 via out_mode) ---- */
 int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack,
               int BN, int n_tiles_n, const eb_epilogue_t* epi, void* stream);
+/* same, plus per-CTA cycle counters (device uint64 [148][16]; who waited on which pipeline barrier) */
+int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack,
+                    int BN, int n_tiles_n, const eb_epilogue_t* epi, unsigned long long* stats, void* stream);
 
 /* ---- DCNv2 forward on NHWC fp16 input with packed fp16 offsets/mask (fused pipeline) ---- */
 int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,

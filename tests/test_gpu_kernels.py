@@ -63,11 +63,22 @@ CONV_CASES = [
     ("1x1_c896_o256", 1, 20, 32, [896], 256, 1, "lrelu", False, "same", None),
     ("3x3_cout96", 1, 20, 20, [128], 96, 3, "none", False, "same", None),
     ("3x3_single_pixel_rows", 1, 1, 40, [64], 64, 3, "none", False, "same", None),
+    ("3x3_c128_tall_ragged", 1, 70, 19, [128], 128, 3, "relu", True, "same", None),
+    ("3x3_c128_o256_stride2", 1, 38, 26, [128], 256, 3, "lrelu", False, "stride2", None),
+    ("1x1_c128_o128_pixshuf", 2, 9, 11, [128], 128, 1, "none", False, "pixshuf", None),
 ]
 
 
+@pytest.fixture(params=["v2_transposed", "v1_pixel_major"])
+def conv_variant(request, monkeypatch):
+    """Cout tiles of 128 run conv_igemm2 (channel-major accumulator) by default; EDVR_B200_CONV_V1=1 forces the
+    pixel-major kernel, which also serves every other tile width.  Both must pass the same cases."""
+    monkeypatch.setenv("EDVR_B200_CONV_V1", "1" if request.param == "v1_pixel_major" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv2d_vs_torch_fp32(ops, case):
+def test_conv2d_vs_torch_fp32(ops, case, conv_variant):
     _, N, H, W, cins, cout, k, act, res, out_mode, maps = case
     g = torch.Generator(device="cuda").manual_seed(1)
     xs = [torch.randn(N if (maps is None or maps[i] is None) else maps[i][4], c, H, W, device="cuda", generator=g)
@@ -109,6 +120,21 @@ def test_conv2d_vs_torch_fp32(ops, case):
     assert not torch.isnan(got).any()
     e = rel_err(got.cpu(), y.cpu())
     assert e[0] < TOL and e[1] < TOL, e
+
+
+def test_conv_fp32_residual_stream_and_dual_output(ops, conv_variant):
+    """Trunk block epilogue: out32 = res32 + conv, out16 = half(out32), in place on the fp32 stream."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N, C, H, W = 2, 128, 37, 21
+    x = torch.randn(N, C, H, W, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, device="cuda", generator=g) / 34
+    b = torch.randn(C, device="cuda", generator=g) * 0.1
+    stream = torch.randn(N, H, W, C, device="cuda", generator=g)
+    want = stream.permute(0, 3, 1, 2) + F.conv2d(x.half().double(), w.half().double(), b.double(), 1, 1).float()
+    out16 = ops.new_act(N, H, W, C)
+    ops.conv2d(ops.pack_conv(w, b), [ops.nchw_to_nhwc(x)], out16=out16, out32=stream, res32=stream)
+    assert rel_err(stream.permute(0, 3, 1, 2).cpu(), want.cpu())[0] < 1e-5
+    assert rel_err(ops.nhwc_to_nchw(out16).cpu(), want.cpu())[0] < TOL
 
 
 def test_stride2_conv_matches_torch_stride2(ops):
@@ -252,7 +278,7 @@ def test_dcn_nhwc_packed_offsets_matches_oracle(ops):
     off, mask = raw[:, :dg * 18].contiguous(), torch.sigmoid(raw[:, dg * 18:]).contiguous()
     ref = dcn_oracle.forward(x.numpy(), off.numpy(), mask.numpy(), w.numpy(), b.numpy(), 1, 1, 1, 1, dg)
     po = ops.pack_conv(wo.cuda(), bo.cuda(), row_map=ops.dcn_offset_row_map(dg))
-    pw = ops.pack_conv(w.cuda(), b.cuda(), tap_major=True)
+    pw = ops.pack_conv(w.cuda(), b.cuda())
     offp = ops.new_act(N, H, W, dg * 32)
     acc = torch.zeros(1, device="cuda")
     ops.conv2d(po, [ops.nchw_to_nhwc(feat.cuda())], out16=offp, act=ops.ACT_DCN_PACK, absmean=acc)
@@ -322,3 +348,30 @@ def test_conv_first_and_last_vs_torch(ops):
     ops.conv_last(ops.nchw_to_nhwc(hr), wl, bl, x, 3 * 12 * 16, 4, got)
     want = F.conv2d(hr, wl, bl, padding=1) + F.interpolate(x, scale_factor=4, mode="bilinear", align_corners=False)
     assert rel_err(got.cpu(), want.cpu())[0] < 1e-4
+
+
+def test_b1_extension_shim_signature_and_inplace_semantics(ops, golden_dir):
+    """edvr_b200.deform_conv_ext mirrors deform_conv_ext.cpp:106-146: caller-allocated outputs written in place,
+    grad_weight / grad_bias accumulated into."""
+    from edvr_b200 import deform_conv_ext as ext
+    z = np.load(os.path.join(golden_dir, "dcn_ref_cuda_g_c64_dg8.npz"))
+    N, C, H, W, Cout, dg, stride, pad, dil, groups = (int(v) for v in z["meta"])
+    t = {k: torch.from_numpy(z[k]).cuda() for k in ("x", "offset", "mask", "weight", "bias", "grad_out")}
+    out = torch.empty(N, Cout, H, W, device="cuda")
+    e = torch.empty(0, device="cuda")
+    ext.modulated_deform_conv_forward(t["x"], t["weight"], t["bias"], e, t["offset"], t["mask"], out, e, 3, 3, stride,
+                                      stride, pad, pad, dil, dil, groups, dg, True)
+    assert rel_err(out.cpu(), z["out"])[0] < TOL
+    gx, goff, gm = torch.zeros_like(t["x"]), torch.zeros_like(t["offset"]), torch.zeros_like(t["mask"])
+    gw, gb = torch.ones_like(t["weight"]), torch.ones_like(t["bias"])          # pre-filled: must be accumulated into
+    ext.modulated_deform_conv_backward(t["x"], t["weight"], t["bias"], e, t["offset"], t["mask"], e, gx, gw, gb, goff,
+                                       gm, t["grad_out"], 3, 3, stride, stride, pad, pad, dil, dil, groups, dg, True)
+    assert rel_err(gx.cpu(), z["grad_x"])[0] < TOL
+    assert rel_err(goff.cpu(), z["grad_offset"])[0] < TOL
+    assert rel_err((gw - 1).cpu(), z["grad_weight"])[0] < TOL
+    assert rel_err((gb - 1).cpu(), z["grad_bias"])[0] < TOL
+    with pytest.raises(RuntimeError, match="not implemented on CPU"):
+        ext.modulated_deform_conv_forward(t["x"].cpu(), t["weight"].cpu(), t["bias"].cpu(), e, t["offset"].cpu(),
+                                          t["mask"].cpu(), out.cpu(), e, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, True)
+    with pytest.raises(NotImplementedError):
+        ext.deform_conv_forward()

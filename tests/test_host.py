@@ -86,3 +86,20 @@ def test_sharding_world2_gloo():
         p.join(60)
     assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
     assert all(r[2] == 11.0 for r in res) and all(r[3] == 7.0 for r in res)   # max over ranks, every clip once
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/basicsr"), reason="reference tree not mounted")
+def test_reference_tree_imports_unchanged_with_b1_shim():
+    """Registering edvr_b200.deform_conv_ext as the compiled module lets the read-only reference tree import and
+    construct EDVR with its own ModulatedDeformConvPack."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.dont_write_bytecode=True; sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r);"
+            "import edvr_b200.deform_conv_ext as ext; sys.modules['basicsr.models.ops.dcn.deform_conv_ext'] = ext;"
+            "from basicsr.models.archs import edvr_arch, arch_util;"
+            "from basicsr.models.ops.dcn.deform_conv import ModulatedDeformConvPack as P;"
+            "net = edvr_arch.EDVR(num_feat=64, num_frame=3, num_reconstruct_block=1, center_frame_idx=None);"
+            "assert arch_util.DCNv2Pack.__mro__[1] is P; print(len(net.state_dict()))") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert int(r.stdout.strip().splitlines()[-1]) > 50

@@ -87,14 +87,15 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(threads=None, crop=(48, 64), steps=1, warmup=0):
+def cpu_reference_rate(threads=None, crop=(96, 160), steps=1, warmup=1):
     """Reference graph on the host cores: oracle port of edvr_arch.py (bit-exact, tests/test_oracle.py) with
     the DCN via torchvision's CPU deform_conv2d.  Bounded sample: one EDVR-L clip cropped to
     `crop` LR pixels; conv work is linear in pixels, so clips/s = (crop / full pixels) / seconds."""
     import torch
     from oracle import edvr_ref
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    if threads:
+        torch.set_num_threads(threads)
+    threads = torch.get_num_threads()          # PyTorch's default = all the cores it will use
     sd = edvr_ref.make_state_dict(**CFG3, seed=0)
     h, w = crop
     x = torch.rand(1, 7, 3, h, w, generator=torch.Generator().manual_seed(0))
@@ -115,7 +116,7 @@ def run_reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    cb = cpu_reference_rate(crop=(48, 64), steps=max(args.steps, 1), warmup=max(args.warmup, 0))
+    cb = cpu_reference_rate(steps=max(args.steps, 1), warmup=max(args.warmup, 0))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "HR frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sec_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -259,7 +260,7 @@ def run_ours(args):
             "kernel_shares": prof["shares"],
         }
         if world == 1:
-            line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(crop=(48, 64)).items() if k != "sec_per_step"}
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate().items() if k != "sec_per_step"}
             try:
                 line["ref_cuda"] = reference_cuda_rate(sd, 1)
             except Exception as e:       # baseline leg only; never hides the product number

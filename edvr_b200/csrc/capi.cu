@@ -207,6 +207,10 @@ static int launch_dcn(DcnParams& P, cudaStream_t st) {
                             ((P.Wo + DC_TILE_W - 1) / DC_TILE_W) * P.n_tiles_n;
     if (tiles == 0) return EB_OK;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    // keep the rest of the 228 KB for L1: the nine taps of a chunk re-read the same slab of x
+    static const int carve = (DC_SMEM_BYTES + 1024) * 100 / (228 * 1024) + 1;
+    cudaFuncSetAttribute(dcn_fused_kernel<OFF_NCHW_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(dcn_fused_kernel<OFF_PACK_F16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (P.off_mode == OFF_NCHW_F32) {
         if (int rc = set_smem(dcn_fused_kernel<OFF_NCHW_F32>, DC_SMEM_BYTES)) return rc;
         dcn_fused_kernel<OFF_NCHW_F32><<<grid, DC_THREADS, DC_SMEM_BYTES, st>>>(P);

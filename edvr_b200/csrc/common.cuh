@@ -195,4 +195,20 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// activation over a register tile with ONE dispatch (a per-element runtime switch compiles to a chain of
+// uniform branches per element and made the epilogues branch-latency bound, profiles/r01_conv_stats_*.log)
+template <int NV>
+__device__ __forceinline__ void act_inplace(float (&v)[NV], int act) {
+    if (act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.0f);
+    } else if (act == ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);     // == v > 0 ? v : 0.1 v
+    } else if (act == ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = sigmoidf_fast(v[j]);
+    }
+}
+
 }  // namespace eb

@@ -90,58 +90,68 @@ __device__ __forceinline__ void conv2_store_channel(const EpiParams& p, float (&
         }
     }
     if (!img_ok) return;
+    // Every lane of the warp holds the SAME 32 pixels (lanes differ by channel only), so all pixel-validity tests
+    // below are warp-uniform branches.  Pixels n0..n0+31 = 4 image rows x 8 columns.
+    const int xn = min(8, p.W - x0);                       // valid columns of this tile (>= 1)
     if (p.out_mode == OUT_SAME) {
-        if (p.res16 != nullptr) {
-            __half r[32];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int n = n0 + e, y = y0 + (n >> 3), x = x0 + (n & 7);
-                r[e] = __float2half(0.f);
-                if (y < p.H && x < p.W)
-                    r[e] = p.res16[((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.res_pix_stride + p.res_ch_off + co];
+        for (int r = 0; r < 4; ++r) {
+            const int y = y0 + (n0 >> 3) + r;
+            if (y >= p.H) break;
+            const size_t rowpix = (static_cast<size_t>(img) * p.H + y) * p.W + x0;
+            if (p.res16 != nullptr) {
+                const __half* rp = p.res16 + rowpix * p.res_pix_stride + p.res_ch_off + co;
+                __half t[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) t[c] = (c < xn) ? rp[static_cast<size_t>(c) * p.res_pix_stride] : __float2half(0.f);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[r * 8 + c] += __half2float(t[c]);
             }
+            if (p.res32 != nullptr) {
+                const float* rp = p.res32 + rowpix * p.res_pix_stride + p.res_ch_off + co;
+                float t[8];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] += __half2float(r[e]);
-        }
-        if (p.res32 != nullptr) {
-            float r[32];
+                for (int c = 0; c < 8; ++c) t[c] = (c < xn) ? __ldg(rp + static_cast<size_t>(c) * p.res_pix_stride) : 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int n = n0 + e, y = y0 + (n >> 3), x = x0 + (n & 7);
-                r[e] = 0.f;
-                if (y < p.H && x < p.W)
-                    r[e] = __ldg(p.res32 + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.res_pix_stride + p.res_ch_off + co);
+                for (int c = 0; c < 8; ++c) v[r * 8 + c] += t[c];
             }
+            if (p.out16 != nullptr) {
+                __half* op = p.out16 + rowpix * p.out16_pix_stride + p.out16_ch_off + co;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] += r[e];
-        }
+                for (int c = 0; c < 8; ++c)
+                    if (c < xn) op[static_cast<size_t>(c) * p.out16_pix_stride] = __float2half_rn(v[r * 8 + c]);
+            }
+            if (p.out32 != nullptr) {
+                float* op = p.out32 + rowpix * p.out32_pix_stride + p.out32_ch_off + co;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int n = n0 + e, y = y0 + (n >> 3), x = x0 + (n & 7);
-            if (y < p.H && x < p.W) {
-                const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
-                if (p.out16 != nullptr) p.out16[pix * p.out16_pix_stride + p.out16_ch_off + co] = __float2half_rn(v[e]);
-                if (p.out32 != nullptr) p.out32[pix * p.out32_pix_stride + p.out32_ch_off + co] = v[e];
+                for (int c = 0; c < 8; ++c)
+                    if (c < xn) op[static_cast<size_t>(c) * p.out32_pix_stride] = v[r * 8 + c];
             }
         }
     } else if (p.out_mode == OUT_PIXSHUF2) {
         // out[b, c, 2y+i, 2x+j] = in[b, 4c + 2i + j, y, x]
         const int cq = co >> 2, i = (co >> 1) & 1, j = co & 1, H2 = 2 * p.H, W2 = 2 * p.W;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int n = n0 + e, y = y0 + (n >> 3), x = x0 + (n & 7);
-            if (y < p.H && x < p.W)
-                p.out16[((static_cast<size_t>(img) * H2 + 2 * y + i) * W2 + 2 * x + j) * p.out16_pix_stride +
-                        p.out16_ch_off + cq] = __float2half_rn(v[e]);
+        for (int r = 0; r < 4; ++r) {
+            const int y = y0 + (n0 >> 3) + r;
+            if (y >= p.H) break;
+            __half* op = p.out16 + ((static_cast<size_t>(img) * H2 + 2 * y + i) * W2 + 2 * x0 + j) * p.out16_pix_stride +
+                         p.out16_ch_off + cq;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < xn) op[static_cast<size_t>(2 * c) * p.out16_pix_stride] = __float2half_rn(v[r * 8 + c]);
         }
-    } else {   // OUT_STRIDE2
+    } else {   // OUT_STRIDE2: tile origins are even, so even rows/columns are r, c in {0, 2, ..}
         const int Ho = (p.H + 1) >> 1, Wo = (p.W + 1) >> 1;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int n = n0 + e, y = y0 + (n >> 3), x = x0 + (n & 7);
-            if (y < p.H && x < p.W && !((y | x) & 1))
-                p.out16[((static_cast<size_t>(img) * Ho + (y >> 1)) * Wo + (x >> 1)) * p.out16_pix_stride +
-                        p.out16_ch_off + co] = __float2half_rn(v[e]);
+        for (int r = 0; r < 4; r += 2) {
+            const int y = y0 + (n0 >> 3) + r;
+            if (y >= p.H) break;
+            __half* op = p.out16 + ((static_cast<size_t>(img) * Ho + (y >> 1)) * Wo + (x0 >> 1)) * p.out16_pix_stride +
+                         p.out16_ch_off + co;
+#pragma unroll
+            for (int c = 0; c < 8; c += 2)
+                if (c < xn) op[static_cast<size_t>(c >> 1) * p.out16_pix_stride] = __float2half_rn(v[r * 8 + c]);
         }
     }
 }
@@ -284,7 +294,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
                 float v[32];
                 tmem_ld32(t0 + col, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + bias_c, act1);
+                for (int j = 0; j < 32; ++j) v[j] += bias_c;
+                act_inplace<32>(v, act1);
                 conv2_store_channel(P.epi, v, img, ty * C2_TH, tx * C2_TW, col, co, img < P.N);
             }
             tc_fence_before_sync();

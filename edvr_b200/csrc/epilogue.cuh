@@ -49,9 +49,8 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane_id() == 0) atomicAdd(p.absmean_acc, s);
         }
-    } else if (p.act != ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+    } else {
+        act_inplace<32>(v, p.act);
     }
     if (!valid) return;
 

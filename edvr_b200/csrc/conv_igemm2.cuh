@@ -6,11 +6,12 @@
 //     bandwidth instead of the 128 B/cycle an M128 x N128 pair of MMAs needs), and half as many instructions.
 //   * The pixel operand is the same halo-tile trick: one (32+2)x(8+2) halo of a 64-channel chunk is loaded once,
 //     every 3x3 tap is a start-address offset into it (rows of the canonical no-swizzle layout = pixels).
-//   * The accumulator is channel-major: an epilogue thread owns ONE output channel (its TMEM lane) for 32 pixels
-//     at a time.  A warp therefore touches 32 consecutive channels of one pixel per instruction: 64-byte (fp16) or
-//     128-byte (fp32) contiguous segments = whole 32-byte sectors, so bias / activation / residual / NHWC stores go
-//     straight from registers to global memory without a shared-memory transpose (the smem port is the scarce
-//     resource of this kernel).  PixelShuffle / stride-2 / DCN-record variants included.
+//   * The accumulator is channel-major, so the epilogue transposes through a small shared-memory slab: phase 1,
+//     each thread (= one TMEM lane = one channel) adds bias, applies the activation and writes 32 pixels of its
+//     channel as fp32 (conflict-free: lanes are consecutive channels); phase 2, each WARP owns one pixel and each
+//     lane 4 consecutive channels: residual loads and NHWC stores are 256/512 contiguous bytes per instruction
+//     (2-4 L1 wavefronts instead of the 32 a pixel-per-lane epilogue costs).  PixelShuffle / stride-2 /
+//     DCN-record variants included.
 // Same warp roles, mbarrier rings, bulk-copied pre-packed weights and persistent scheduling as conv_igemm.cuh.
 #pragma once
 #include "common.cuh"
@@ -21,12 +22,14 @@ namespace eb {
 
 constexpr int C2_TH = 32, C2_TW = 8;                   // pixel tile: 32 rows x 8 columns = 256 = MMA N
 constexpr int C2_A_BUFS = 2;
-constexpr int C2_W_STAGES = 6;
+constexpr int C2_W_STAGES = 5;
 constexpr int C2_PLANE_BYTES = 341 * 16;               // >= 34*10*16, odd number of 16-byte units
 constexpr int C2_A_BUF_BYTES = 8 * C2_PLANE_BYTES;     // 43648
 constexpr int C2_W_STAGE_BYTES = 128 * 128;            // 128 channels x 64 k x 2 B
 constexpr int C2_THREADS = 320;
-constexpr int C2_SMEM_BYTES = C2_A_BUFS * C2_A_BUF_BYTES + C2_W_STAGES * C2_W_STAGE_BYTES + 256;
+constexpr int C2_SLAB_FLOATS = 32 * 128;                // one 32-pixel x 128-channel fp32 slab
+constexpr int C2_SMEM_BYTES = C2_A_BUFS * C2_A_BUF_BYTES + C2_W_STAGES * C2_W_STAGE_BYTES +
+                              2 * C2_SLAB_FLOATS * 4 + 256;
 
 template <int HALO>
 __device__ __forceinline__ void conv2_load_halo(const ConvParams& P, int chunk, int img, int ty, int tx,
@@ -64,95 +67,60 @@ __device__ __forceinline__ void conv2_load_halo(const ConvParams& P, int chunk, 
     }
 }
 
-// Epilogue of one 32-pixel column block: this thread owns channel `co` (global packed index) of pixels
-// n0..n0+31 of the tile (n = 8*row + col).  v[] already holds bias + activation.
-__device__ __forceinline__ void conv2_store_channel(const EpiParams& p, float (&v)[32], int img, int y0, int x0,
-                                                    int n0, int co, bool img_ok) {
-    const int lane = lane_id();
+// Epilogue phase 2: this lane owns channels c0..c0+3 (packed index) of output pixel (img, y, x); the whole warp
+// shares the pixel, so every validity test is warp-uniform.  v already holds bias + activation.
+__device__ __forceinline__ void conv2_store4(const EpiParams& p, float4 v, int img, int y, int x, int c0, bool valid) {
     if (p.act == ACT_DCN_PACK) {
-        // packed record: channel j = co % 32 of each group: [0,18) offsets, [18,27) mask logits, rest pad
-        const int j = co & 31;
+        // packed record: channel j = c % 32 of each group: [0,18) offsets, [18,27) mask logits, rest pad
+        const int j0 = c0 & 31;
+        float* e = reinterpret_cast<float*>(&v);
         float s = 0.f;
-        if (j >= 18 && j < 27) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = sigmoidf_fast(v[e]);
-        } else if (j < 18 && p.absmean_acc != nullptr) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int n = n0 + e, y = y0 + (n >> 3), x = x0 + (n & 7);
-                s += (img_ok && y < p.H && x < p.W) ? fabsf(v[e]) : 0.f;
-            }
+        for (int i = 0; i < 4; ++i) {
+            const int j = j0 + i;
+            if (j < 18) s += fabsf(e[i]);
+            else if (j < 27) e[i] = sigmoidf_fast(e[i]);
         }
         if (p.absmean_acc != nullptr) {
+            s = valid ? s : 0.f;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) atomicAdd(p.absmean_acc, s);
+            if (lane_id() == 0 && valid) atomicAdd(p.absmean_acc, s);
         }
     }
-    if (!img_ok) return;
-    // Every lane of the warp holds the SAME 32 pixels (lanes differ by channel only), so all pixel-validity tests
-    // below are warp-uniform branches.  Pixels n0..n0+31 = 4 image rows x 8 columns.
-    const int xn = min(8, p.W - x0);                       // valid columns of this tile (>= 1)
+    if (!valid) return;
     if (p.out_mode == OUT_SAME) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int y = y0 + (n0 >> 3) + r;
-            if (y >= p.H) break;
-            const size_t rowpix = (static_cast<size_t>(img) * p.H + y) * p.W + x0;
-            if (p.res16 != nullptr) {
-                const __half* rp = p.res16 + rowpix * p.res_pix_stride + p.res_ch_off + co;
-                __half t[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) t[c] = (c < xn) ? rp[static_cast<size_t>(c) * p.res_pix_stride] : __float2half(0.f);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[r * 8 + c] += __half2float(t[c]);
-            }
-            if (p.res32 != nullptr) {
-                const float* rp = p.res32 + rowpix * p.res_pix_stride + p.res_ch_off + co;
-                float t[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) t[c] = (c < xn) ? __ldg(rp + static_cast<size_t>(c) * p.res_pix_stride) : 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[r * 8 + c] += t[c];
-            }
-            if (p.out16 != nullptr) {
-                __half* op = p.out16 + rowpix * p.out16_pix_stride + p.out16_ch_off + co;
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (c < xn) op[static_cast<size_t>(c) * p.out16_pix_stride] = __float2half_rn(v[r * 8 + c]);
-            }
-            if (p.out32 != nullptr) {
-                float* op = p.out32 + rowpix * p.out32_pix_stride + p.out32_ch_off + co;
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (c < xn) op[static_cast<size_t>(c) * p.out32_pix_stride] = v[r * 8 + c];
-            }
+        const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+        if (p.res16 != nullptr) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.res16 + pix * p.res_pix_stride + p.res_ch_off + c0));
+            const float2 a = unpack_h2(u.x), b = unpack_h2(u.y);
+            v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
         }
+        if (p.res32 != nullptr) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(p.res32 + pix * p.res_pix_stride + p.res_ch_off + c0));
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (p.out16 != nullptr)
+            *reinterpret_cast<uint2*>(p.out16 + pix * p.out16_pix_stride + p.out16_ch_off + c0) =
+                make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+        if (p.out32 != nullptr)
+            *reinterpret_cast<float4*>(p.out32 + pix * p.out32_pix_stride + p.out32_ch_off + c0) = v;
     } else if (p.out_mode == OUT_PIXSHUF2) {
-        // out[b, c, 2y+i, 2x+j] = in[b, 4c + 2i + j, y, x]
-        const int cq = co >> 2, i = (co >> 1) & 1, j = co & 1, H2 = 2 * p.H, W2 = 2 * p.W;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int y = y0 + (n0 >> 3) + r;
-            if (y >= p.H) break;
-            __half* op = p.out16 + ((static_cast<size_t>(img) * H2 + 2 * y + i) * W2 + 2 * x0 + j) * p.out16_pix_stride +
-                         p.out16_ch_off + cq;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < xn) op[static_cast<size_t>(2 * c) * p.out16_pix_stride] = __float2half_rn(v[r * 8 + c]);
-        }
-    } else {   // OUT_STRIDE2: tile origins are even, so even rows/columns are r, c in {0, 2, ..}
+        // out[b, c, 2y+i, 2x+j] = in[b, 4c + 2i + j, y, x]; this lane owns output channel c0/4
+        const int H2 = 2 * p.H, W2 = 2 * p.W;
+        __half* o = p.out16 + ((static_cast<size_t>(img) * H2 + 2 * y) * W2 + 2 * x) * p.out16_pix_stride +
+                    p.out16_ch_off + (c0 >> 2);
+        const size_t rs = static_cast<size_t>(W2) * p.out16_pix_stride;
+        o[0] = __float2half_rn(v.x);
+        o[p.out16_pix_stride] = __float2half_rn(v.y);
+        o[rs] = __float2half_rn(v.z);
+        o[rs + p.out16_pix_stride] = __float2half_rn(v.w);
+    } else {   // OUT_STRIDE2
+        if ((y | x) & 1) return;
         const int Ho = (p.H + 1) >> 1, Wo = (p.W + 1) >> 1;
-#pragma unroll
-        for (int r = 0; r < 4; r += 2) {
-            const int y = y0 + (n0 >> 3) + r;
-            if (y >= p.H) break;
-            __half* op = p.out16 + ((static_cast<size_t>(img) * Ho + (y >> 1)) * Wo + (x0 >> 1)) * p.out16_pix_stride +
-                         p.out16_ch_off + co;
-#pragma unroll
-            for (int c = 0; c < 8; c += 2)
-                if (c < xn) op[static_cast<size_t>(c >> 1) * p.out16_pix_stride] = __float2half_rn(v[r * 8 + c]);
-        }
+        const size_t opix = (static_cast<size_t>(img) * Ho + (y >> 1)) * Wo + (x >> 1);
+        *reinterpret_cast<uint2*>(p.out16 + opix * p.out16_pix_stride + p.out16_ch_off + c0) =
+            make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
     }
 }
 
@@ -178,7 +146,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* a_smem = smem;                                         // pixel halo chunks
     uint8_t* w_smem = smem + C2_A_BUFS * C2_A_BUF_BYTES;            // weight stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + C2_W_STAGES * C2_W_STAGE_BYTES);
+    float* slab = reinterpret_cast<float*>(w_smem + C2_W_STAGES * C2_W_STAGE_BYTES);      // 2 x [32 px][128 ch]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab + 2 * C2_SLAB_FLOATS);
     uint64_t* a_full = bars;                          // [2]
     uint64_t* a_empty = bars + 2;                     // [2]
     uint64_t* w_full = bars + 4;                      // [6]
@@ -291,12 +260,28 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 256u;
 #pragma unroll 1
             for (int col = 0; col < 256; col += 32) {
-                float v[32];
-                tmem_ld32(t0 + col, v);
+                float* sl = slab + ((col >> 5) & 1) * C2_SLAB_FLOATS;
+                {
+                    float v[32];
+                    tmem_ld32(t0 + col, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += bias_c;
-                act_inplace<32>(v, act1);
-                conv2_store_channel(P.epi, v, img, ty * C2_TH, tx * C2_TW, col, co, img < P.N);
+                    for (int j = 0; j < 32; ++j) v[j] += bias_c;
+                    act_inplace<32>(v, act1);
+                    // phase 1: channel (32q + lane) of pixels col..col+31 -> slab[pixel][channel]
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sl[j * 128 + 32 * q + lane] = v[j];
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // phase 2: warp q handles pixels q, q+4, ...; lane = 4 consecutive channels
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int pj = q + 4 * i;
+                    const int n = col + pj;
+                    const int y = ty * C2_TH + (n >> 3), x = tx * C2_TW + (n & 7);
+                    const bool valid = (img < P.N) && (y < P.H) && (x < P.W);
+                    const float4 v4 = *reinterpret_cast<const float4*>(sl + pj * 128 + lane * 4);
+                    conv2_store4(P.epi, v4, img, y, x, nt * 128 + lane * 4, valid);
+                }
             }
             tc_fence_before_sync();
             mbar_arrive(&acc_empty[ab]);

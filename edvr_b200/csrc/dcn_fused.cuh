@@ -11,9 +11,10 @@
 // the fp32 accumulator lives in TMEM and is drained by four epilogue warps (bias, activation,
 // NHWC fp16 and/or NCHW fp32 stores).  K is walked chunk-major: stage = (64-channel chunk, tap), so the nine
 // taps of a chunk re-read the same ~23 KB slab of x and hit L1.
-// Gather mapping (the L1TEX wavefront rate is the limiter of this kernel, profiles/r01_*): the 8 lanes of a
-// quarter-warp read the 8 consecutive 16-byte channel atoms of ONE sampled pixel = one full 128-byte line per
-// corner, instead of 32 lanes touching 32 different lines.
+// Gather mapping (L1TEX wavefronts and issue slots are the limiters of this kernel, profiles/r01_*): four lanes
+// read the 128 contiguous bytes (64 channels) of ONE sampled pixel per corner, each lane 32 bytes = one
+// deformable group when C/dg = 16, so the sampling geometry is computed once per 16 channels; offsets of the next
+// stage are prefetched while the current one is gathered; the fused fp16 pipeline blends with packed HFMA2.
 //
 // Sampling semantics (bit-for-bit the reference's decisions, fp32 coordinate math):
 //   h_im = ho*stride - pad + i*dil + dh;  sample iff h_im > -1 && w_im > -1 && h_im < H && w_im < W
@@ -61,9 +62,34 @@ struct DcnCorner {
     unsigned valid;       // bit c set if corner c contributes
 };
 
+struct DcnOff { float dh, dw, mk; };
+
+// (dh, dw, mask) of (pixel, deformable group g, tap) — the only global reads that precede the corner loads
 template <int OFFMODE>
-__device__ __forceinline__ DcnCorner dcn_corner(const DcnParams& P, int img, int ho, int wo,
-                                                bool pix_valid, int g, int tap) {
+__device__ __forceinline__ DcnOff dcn_fetch_off(const DcnParams& P, int img, int ho, int wo, bool pix_valid, int g, int tap) {
+    DcnOff o;
+    o.dh = o.dw = o.mk = 0.f;
+    if (!pix_valid) return o;
+    if (OFFMODE == OFF_NCHW_F32) {
+        const int K = P.kh * P.kw;
+        const size_t plane = static_cast<size_t>(P.Ho) * P.Wo;
+        const size_t pix = static_cast<size_t>(ho) * P.Wo + wo;
+        const float* ob = P.offset + (static_cast<size_t>(img) * P.dg + g) * 2 * K * plane + pix;
+        o.dh = __ldg(ob + static_cast<size_t>(2 * tap) * plane);
+        o.dw = __ldg(ob + static_cast<size_t>(2 * tap + 1) * plane);
+        o.mk = __ldg(P.mask + ((static_cast<size_t>(img) * P.dg + g) * K + tap) * plane + pix);
+    } else {
+        const __half* rec = P.offpack + ((static_cast<size_t>(img) * P.Ho + ho) * P.Wo + wo) * P.offpack_pix_stride + g * 32;
+        const __half2 hw = *reinterpret_cast<const __half2*>(rec + 2 * tap);
+        o.dh = __low2float(hw);
+        o.dw = __high2float(hw);
+        o.mk = __half2float(rec[18 + tap]);
+    }
+    return o;
+}
+
+__device__ __forceinline__ DcnCorner dcn_corner(const DcnParams& P, int img, int ho, int wo, bool pix_valid,
+                                                int tap, const DcnOff& o) {
     DcnCorner c;
     c.valid = 0;
     c.base = P.x;
@@ -71,38 +97,41 @@ __device__ __forceinline__ DcnCorner dcn_corner(const DcnParams& P, int img, int
     c.dH = P.W * P.x_pix_stride;
     c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0.f;
     if (!pix_valid) return c;
-    const int K = P.kh * P.kw;
-    float dh, dw, mk;
-    if (OFFMODE == OFF_NCHW_F32) {
-        const size_t plane = static_cast<size_t>(P.Ho) * P.Wo;
-        const size_t pix = static_cast<size_t>(ho) * P.Wo + wo;
-        const float* ob = P.offset + (static_cast<size_t>(img) * P.dg + g) * 2 * K * plane + pix;
-        dh = __ldg(ob + static_cast<size_t>(2 * tap) * plane);
-        dw = __ldg(ob + static_cast<size_t>(2 * tap + 1) * plane);
-        mk = __ldg(P.mask + ((static_cast<size_t>(img) * P.dg + g) * K + tap) * plane + pix);
-    } else {
-        const __half* rec = P.offpack +
-                            ((static_cast<size_t>(img) * P.Ho + ho) * P.Wo + wo) * P.offpack_pix_stride +
-                            g * 32;
-        const __half2 o = *reinterpret_cast<const __half2*>(rec + 2 * tap);
-        dh = __low2float(o);
-        dw = __high2float(o);
-        mk = __half2float(rec[18 + tap]);
-    }
     const int ki = tap / P.kw, kj = tap - ki * P.kw;
-    const float h_im = static_cast<float>(ho * P.stride - P.pad + ki * P.dil) + dh;
-    const float w_im = static_cast<float>(wo * P.stride - P.pad + kj * P.dil) + dw;
+    const float h_im = static_cast<float>(ho * P.stride - P.pad + ki * P.dil) + o.dh;
+    const float w_im = static_cast<float>(wo * P.stride - P.pad + kj * P.dil) + o.dw;
     if (!(h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(P.H) && w_im < static_cast<float>(P.W)))
         return c;
     const float hf = floorf(h_im), wf = floorf(w_im);
     const int hl = static_cast<int>(hf), wl = static_cast<int>(wf);
     const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-    c.w[0] = hh * hw * mk; c.w[1] = hh * lw * mk; c.w[2] = lh * hw * mk; c.w[3] = lh * lw * mk;
+    c.w[0] = hh * hw * o.mk; c.w[1] = hh * lw * o.mk; c.w[2] = lh * hw * o.mk; c.w[3] = lh * lw * o.mk;
     const bool t = hl >= 0, b = hl + 1 <= P.H - 1, l = wl >= 0, r = wl + 1 <= P.W - 1;
     c.valid = (t && l ? 1u : 0u) | (t && r ? 2u : 0u) | (b && l ? 4u : 0u) | (b && r ? 8u : 0u);
     c.base = P.x + P.x_ch_off +
              ((static_cast<long long>(img) * P.H + hl) * P.W + wl) * static_cast<long long>(P.x_pix_stride);
     return c;
+}
+
+// 8 channels x 4 corners in packed fp16 (fused fp16 pipeline only; the fp32-layout operator keeps fp32 math)
+__device__ __forceinline__ uint4 dcn_blend8_h2(uint4 u0, uint4 u1, uint4 u2, uint4 u3, const float (&w)[4]) {
+    const __half2 w0 = __float2half2_rn(w[0]), w1 = __float2half2_rn(w[1]), w2 = __float2half2_rn(w[2]),
+                  w3 = __float2half2_rn(w[3]);
+    uint4 r;
+    uint32_t* ro = reinterpret_cast<uint32_t*>(&r);
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&u0);
+    const uint32_t* b = reinterpret_cast<const uint32_t*>(&u1);
+    const uint32_t* c = reinterpret_cast<const uint32_t*>(&u2);
+    const uint32_t* d = reinterpret_cast<const uint32_t*>(&u3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __half2 acc = __hmul2(w0, *reinterpret_cast<const __half2*>(&a[i]));
+        acc = __hfma2(w1, *reinterpret_cast<const __half2*>(&b[i]), acc);
+        acc = __hfma2(w2, *reinterpret_cast<const __half2*>(&c[i]), acc);
+        acc = __hfma2(w3, *reinterpret_cast<const __half2*>(&d[i]), acc);
+        ro[i] = *reinterpret_cast<uint32_t*>(&acc);
+    }
+    return r;
 }
 
 __device__ __forceinline__ void dcn_blend8(float (&acc)[8], uint4 u, float w) {
@@ -120,7 +149,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
     uint8_t* b_smem = smem + DC_STAGES * DC_A_BYTES;
     float* bias_s = reinterpret_cast<float*>(b_smem + DC_STAGES * DC_B_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + DC_MAX_COUT);
-    uint64_t* full = bars;                       // [S]  256 gather arrivals + 1 expect_tx
+    uint64_t* full = bars;                       // [S]  8 gather-warp arrivals + 1 expect_tx
     uint64_t* empty = bars + DC_STAGES;          // [S]
     uint64_t* acc_full = bars + 2 * DC_STAGES;   // [2]
     uint64_t* acc_empty = acc_full + 2;          // [2]
@@ -140,7 +169,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
     if (has_bias)
         for (int i = threadIdx.x; i < cout_packed; i += blockDim.x) bias_s[i] = P.epi.bias[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < DC_STAGES; ++i) { mbar_init(&full[i], DC_GATHER_THREADS + 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < DC_STAGES; ++i) { mbar_init(&full[i], DC_GATHER_THREADS / 32 + 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
     }
@@ -219,57 +248,95 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
         }
     } else {
         // ================= gather warps (256 threads): build the A operand of each stage.
-        // lane -> (pixel slot = lane/8, channel atom kc = lane%8); a thread owns 4 pixels x 1 atom per stage.
+        // lane -> (pixel slot = lane/4, channel-atom pair kp = lane%4 -> atoms 2kp, 2kp+1 = 32 contiguous bytes);
+        // a thread owns 2 pixels per stage.  The 4 lanes of a pixel cover one full 128-byte line per corner.
         const int gw = warp - 6;                      // 0..7
-        const int kc = lane & 7;
-        int m[4], ho[4], wo[4];
-        bool pv[4];
+        const int kc0 = (lane & 3) * 2;
+        int m[2], ho[2], wo[2];
+        bool pv[2];
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int pt = tile / P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                m[i] = i * 32 + gw * 4 + (lane >> 3);
+            for (int i = 0; i < 2; ++i) {
+                m[i] = i * 64 + gw * 8 + (lane >> 2);
                 ho[i] = ty * DC_TILE_H + (m[i] >> 3);
                 wo[i] = tx * DC_TILE_W + (m[i] & 7);
                 pv[i] = (ho[i] < P.Ho) && (wo[i] < P.Wo);
             }
+            // software pipeline: the (dh, dw, mask) triples of stage st+1 are fetched while stage st is gathered
+            DcnOff nxt[2][2];
+            {
+                const int ch = kc0 * 8;
+                const int g0 = ch / P.cpg, g1 = (ch + 8) / P.cpg;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    nxt[i][0] = dcn_fetch_off<OFFMODE>(P, img, ho[i], wo[i], pv[i], g0, 0);
+                    nxt[i][1] = (g1 != g0) ? dcn_fetch_off<OFFMODE>(P, img, ho[i], wo[i], pv[i], g1, 0) : nxt[i][0];
+                }
+            }
             for (int st = 0; st < nstages; ++st, ++it) {
                 const int chunk = st / K, tap = st - chunk * K;
-                const int ch = chunk * 64 + kc * 8;
-                const int g = ch / P.cpg;
+                const int ch = chunk * 64 + kc0 * 8;
+                const int g0 = ch / P.cpg, g1 = (ch + 8) / P.cpg;
+                const bool two = g1 != g0;                       // cpg == 8: the two atoms belong to different groups
                 const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
-                // 1) sampling geometry of the 4 pixels (same group g, same tap)
-                DcnCorner cn[4];
+                DcnCorner cn[2][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cn[i] = dcn_corner<OFFMODE>(P, img, ho[i], wo[i], pv[i], g, tap);
-                // 2) all 16 corner loads in flight before anything is consumed
-                uint4 u[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const __half* b = cn[i].base + ch;
-                    u[i][0] = u[i][1] = u[i][2] = u[i][3] = make_uint4(0, 0, 0, 0);
-                    if (cn[i].valid & 1u) u[i][0] = ldg_nc_v4(b);
-                    if (cn[i].valid & 2u) u[i][1] = ldg_nc_v4(b + cn[i].dW);
-                    if (cn[i].valid & 4u) u[i][2] = ldg_nc_v4(b + cn[i].dH);
-                    if (cn[i].valid & 8u) u[i][3] = ldg_nc_v4(b + cn[i].dH + cn[i].dW);
+                for (int i = 0; i < 2; ++i) {
+                    cn[i][0] = dcn_corner(P, img, ho[i], wo[i], pv[i], tap, nxt[i][0]);
+                    cn[i][1] = two ? dcn_corner(P, img, ho[i], wo[i], pv[i], tap, nxt[i][1]) : cn[i][0];
                 }
-                // 3) the smem slot is needed only now
+                // all 16 corner loads in flight before anything is consumed
+                uint4 u[2][2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const DcnCorner& c = cn[i][a];
+                        const __half* b = c.base + ch + a * 8;
+                        u[i][a][0] = u[i][a][1] = u[i][a][2] = u[i][a][3] = make_uint4(0, 0, 0, 0);
+                        if (c.valid & 1u) u[i][a][0] = ldg_nc_v4(b);
+                        if (c.valid & 2u) u[i][a][1] = ldg_nc_v4(b + c.dW);
+                        if (c.valid & 4u) u[i][a][2] = ldg_nc_v4(b + c.dH);
+                        if (c.valid & 8u) u[i][a][3] = ldg_nc_v4(b + c.dH + c.dW);
+                    }
+                // prefetch next stage's offsets
+                if (st + 1 < nstages) {
+                    const int st1 = st + 1, chunk1 = st1 / K, tap1 = st1 - chunk1 * K;
+                    const int ch1 = chunk1 * 64 + kc0 * 8;
+                    const int h0 = ch1 / P.cpg, h1 = (ch1 + 8) / P.cpg;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        nxt[i][0] = dcn_fetch_off<OFFMODE>(P, img, ho[i], wo[i], pv[i], h0, tap1);
+                        nxt[i][1] = (h1 != h0) ? dcn_fetch_off<OFFMODE>(P, img, ho[i], wo[i], pv[i], h1, tap1) : nxt[i][0];
+                    }
+                }
+                // the smem slot is needed only now
                 mbar_wait(&empty[s], ph ^ 1u);
-                const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + kc * DC_A_LBO;
+                const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + kc0 * DC_A_LBO;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    dcn_blend8(acc, u[i][0], cn[i].w[0]);
-                    dcn_blend8(acc, u[i][1], cn[i].w[1]);
-                    dcn_blend8(acc, u[i][2], cn[i].w[2]);
-                    dcn_blend8(acc, u[i][3], cn[i].w[3]);
-                    sts_v4(dst + m[i] * 16, make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]),
-                                                       pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7])));
-                }
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        uint4 r;
+                        if (OFFMODE == OFF_PACK_F16) {
+                            r = dcn_blend8_h2(u[i][a][0], u[i][a][1], u[i][a][2], u[i][a][3], cn[i][a].w);
+                        } else {
+                            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            dcn_blend8(acc, u[i][a][0], cn[i][a].w[0]);
+                            dcn_blend8(acc, u[i][a][1], cn[i][a].w[1]);
+                            dcn_blend8(acc, u[i][a][2], cn[i][a].w[2]);
+                            dcn_blend8(acc, u[i][a][3], cn[i][a].w[3]);
+                            r = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]),
+                                           pack_h2(acc[6], acc[7]));
+                        }
+                        sts_v4(dst + a * DC_A_LBO + m[i] * 16, r);
+                    }
                 fence_proxy_async_smem();
-                mbar_arrive(&full[s]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
             }
         }
     }

@@ -199,6 +199,7 @@ int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksi
     P.wpack = static_cast<const __half*>(wpack);
     if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
     P.stats = stats;
+    { const char* e = getenv("EDVR_B200_DBG"); P.dbg = (stats != nullptr && e != nullptr) ? atoi(e) : 0; }
     return launch_conv(P, static_cast<cudaStream_t>(stream));
 }
 

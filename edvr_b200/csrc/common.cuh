@@ -59,15 +59,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(200000u)      // suspend-time hint (ns): sleep in hardware, do not poll
             : "memory");
         if (done) break;
         if (spin == 64) t0 = clock64();
         if (spin > 64 && (spin & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
+}
+
+// One lane polls, the warp follows: hundreds of threads polling the same mbarrier through the LSU/MIO path slow
+// every other shared/global access of the SM (measured: profiles/r01_conv_stats_*).  All lanes must call it.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31u) == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------- proxy / tcgen05 fences

@@ -50,6 +50,7 @@ struct ConvParams {
     const __half* wpack;
     EpiParams epi;
     unsigned long long* stats;   // optional [gridDim.x][16] cycle counters (profiling builds of the call only)
+    int dbg;                     // profiling only: bit0 skip epilogue global memory, bit1 skip phase 2, bit2 skip tmem loads
 };
 
 template <int HALO>
@@ -120,9 +121,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
     if (has_bias)
         for (int i = threadIdx.x; i < cout_packed; i += blockDim.x) bias_s[i] = P.epi.bias[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < CV_A_BUFS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < CV_A_BUFS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < CV_B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -197,10 +198,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
             for (int c = 0; c < nchunks; ++c, ++a_it) {
                 const uint32_t as = a_it % CV_A_BUFS, aph = (a_it / CV_A_BUFS) & 1u;
-                mbar_wait(&a_empty[as], aph ^ 1u);
+                mbar_wait_warp(&a_empty[as], aph ^ 1u);
                 conv_load_halo<HALO>(P, c, img, ty, tx, smem_u32(a_smem + as * CV_A_BUF_BYTES), tid);
                 fence_proxy_async_smem();   // generic-proxy stores -> visible to the MMA (async proxy)
-                mbar_arrive(&a_full[as]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[as]);
             }
         }
     } else {
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
             const int nt = tile % P.n_tiles_n, pt = tile / P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
             const uint32_t ab = acc_it & 1u;
-            mbar_wait(&acc_full[ab], (acc_it >> 1) & 1u);
+            mbar_wait_warp(&acc_full[ab], (acc_it >> 1) & 1u);
             tc_fence_after_sync();
             const int y = ty * CV_TILE + 4 * q + (lane >> 3);
 #pragma unroll 1
@@ -227,7 +229,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
                 }
             }
             tc_fence_before_sync();
-            mbar_arrive(&acc_empty[ab]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
         }
     }
 

@@ -126,22 +126,24 @@ __device__ __forceinline__ void conv2_store4(const EpiParams& p, float4 v, int i
 
 // cycle-counter slots of ConvParams.stats (per CTA): who waited on what
 enum : int { ST_MMA_TOTAL = 0, ST_MMA_WAIT_ACC = 1, ST_MMA_WAIT_A = 2, ST_MMA_WAIT_W = 3, ST_A_TOTAL = 4,
-             ST_A_WAIT_EMPTY = 5, ST_W_TOTAL = 6, ST_W_WAIT_EMPTY = 7, ST_E_TOTAL = 8, ST_E_WAIT_ACC = 9, ST_TILES = 10 };
+             ST_A_WAIT_EMPTY = 5, ST_W_TOTAL = 6, ST_W_WAIT_EMPTY = 7, ST_E_TOTAL = 8, ST_E_WAIT_ACC = 9, ST_TILES = 10, ST_E_TMEM = 11, ST_E_P1 = 12, ST_E_BAR = 13, ST_E_P2 = 14 };
 
-#define C2_TIMED_WAIT(bar, parity, slot)                                  \
+#define C2_TIMED_WAIT_(WAITFN, bar, parity, slot)                                  \
     do {                                                                   \
         if (P.stats != nullptr) {                                          \
             const long long t_ = clock64();                                \
-            mbar_wait(bar, parity);                                        \
+            WAITFN(bar, parity);                                           \
             st_acc[slot] += static_cast<unsigned long long>(clock64() - t_); \
         } else {                                                           \
-            mbar_wait(bar, parity);                                        \
+            WAITFN(bar, parity);                                           \
         }                                                                  \
     } while (0)
+#define C2_TIMED_WAIT(bar, parity, slot) C2_TIMED_WAIT_(mbar_wait, bar, parity, slot)
+#define C2_TIMED_WAIT_WARP(bar, parity, slot) C2_TIMED_WAIT_(mbar_wait_warp, bar, parity, slot)
 
 template <int HALO>
 __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvParams P) {
-    unsigned long long st_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long st_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long st_t0 = clock64();
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* a_smem = smem;                                         // pixel halo chunks
@@ -166,9 +168,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
     const bool has_bias = P.epi.bias != nullptr;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C2_A_BUFS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < C2_A_BUFS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < C2_W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -238,10 +240,11 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
             for (int c = 0; c < nchunks; ++c, ++a_it) {
                 const uint32_t as = a_it % C2_A_BUFS, aph = (a_it / C2_A_BUFS) & 1u;
-                C2_TIMED_WAIT(&a_empty[as], aph ^ 1u, ST_A_WAIT_EMPTY);
+                C2_TIMED_WAIT_WARP(&a_empty[as], aph ^ 1u, ST_A_WAIT_EMPTY);
                 conv2_load_halo<HALO>(P, c, img, ty, tx, smem_u32(a_smem + as * C2_A_BUF_BYTES), tid);
                 fence_proxy_async_smem();
-                mbar_arrive(&a_full[as]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[as]);
             }
         }
     } else {
@@ -255,15 +258,22 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
             const int co = nt * 128 + 32 * q + lane;
             const float bias_c = has_bias ? __ldg(P.epi.bias + co) : 0.f;
             const int act1 = (P.epi.act == ACT_DCN_PACK) ? ACT_NONE : P.epi.act;
-            C2_TIMED_WAIT(&acc_full[ab], (acc_it >> 1) & 1u, ST_E_WAIT_ACC);
+            C2_TIMED_WAIT_WARP(&acc_full[ab], (acc_it >> 1) & 1u, ST_E_WAIT_ACC);
             tc_fence_after_sync();
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 256u;
 #pragma unroll 1
             for (int col = 0; col < 256; col += 32) {
                 float* sl = slab + ((col >> 5) & 1) * C2_SLAB_FLOATS;
+                long long tq = P.stats ? clock64() : 0;
                 {
                     float v[32];
-                    tmem_ld32(t0 + col, v);
+                    if (P.dbg & 4) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    } else {
+                        tmem_ld32(t0 + col, v);
+                    }
+                    if (P.stats) { const long long t = clock64(); st_acc[ST_E_TMEM] += t - tq; tq = t; }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += bias_c;
                     act_inplace<32>(v, act1);
@@ -271,20 +281,25 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
 #pragma unroll
                     for (int j = 0; j < 32; ++j) sl[j * 128 + 32 * q + lane] = v[j];
                 }
+                if (P.stats) { const long long t = clock64(); st_acc[ST_E_P1] += t - tq; tq = t; }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (P.stats) { const long long t = clock64(); st_acc[ST_E_BAR] += t - tq; tq = t; }
+                if (P.dbg & 2) continue;
                 // phase 2: warp q handles pixels q, q+4, ...; lane = 4 consecutive channels
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int pj = q + 4 * i;
                     const int n = col + pj;
                     const int y = ty * C2_TH + (n >> 3), x = tx * C2_TW + (n & 7);
-                    const bool valid = (img < P.N) && (y < P.H) && (x < P.W);
+                    const bool valid = (img < P.N) && (y < P.H) && (x < P.W) && !(P.dbg & 1);
                     const float4 v4 = *reinterpret_cast<const float4*>(sl + pj * 128 + lane * 4);
                     conv2_store4(P.epi, v4, img, y, x, nt * 128 + lane * 4, valid);
                 }
+                if (P.stats) st_acc[ST_E_P2] += clock64() - tq;
             }
             tc_fence_before_sync();
-            mbar_arrive(&acc_empty[ab]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
         }
     }
 
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
         if (warp == 1) { o[ST_MMA_TOTAL] = tot; o[ST_MMA_WAIT_ACC] = st_acc[ST_MMA_WAIT_ACC]; o[ST_MMA_WAIT_A] = st_acc[ST_MMA_WAIT_A]; o[ST_MMA_WAIT_W] = st_acc[ST_MMA_WAIT_W]; }
         if (warp == 2) { o[ST_A_TOTAL] = tot; o[ST_A_WAIT_EMPTY] = st_acc[ST_A_WAIT_EMPTY]; }
         if (warp == 0) { o[ST_W_TOTAL] = tot; o[ST_W_WAIT_EMPTY] = st_acc[ST_W_WAIT_EMPTY]; }
-        if (warp == 6) { o[ST_E_TOTAL] = tot; o[ST_E_WAIT_ACC] = st_acc[ST_E_WAIT_ACC]; o[ST_TILES] = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x; }
+        if (warp == 6) { o[ST_E_TMEM] = st_acc[ST_E_TMEM]; o[ST_E_P1] = st_acc[ST_E_P1]; o[ST_E_BAR] = st_acc[ST_E_BAR]; o[ST_E_P2] = st_acc[ST_E_P2]; o[ST_E_TOTAL] = tot; o[ST_E_WAIT_ACC] = st_acc[ST_E_WAIT_ACC]; o[ST_TILES] = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x; }
     }
     tc_fence_before_sync();
     __syncthreads();

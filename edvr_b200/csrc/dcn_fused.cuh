@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
         for (int i = threadIdx.x; i < cout_packed; i += blockDim.x) bias_s[i] = P.epi.bias[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < DC_STAGES; ++i) { mbar_init(&full[i], DC_GATHER_THREADS / 32 + 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 256);
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             const int nt = tile % P.n_tiles_n, pt = tile / P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
             const uint32_t ab = acc_it & 1u;
-            mbar_wait(&acc_full[ab], (acc_it >> 1) & 1u);
+            mbar_wait_warp(&acc_full[ab], (acc_it >> 1) & 1u);
             tc_fence_after_sync();
             const int y = ty * DC_TILE_H + 4 * q + (lane >> 3);
             const int x = tx * DC_TILE_W + (lane & 7);
@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                 epi_store32(P.epi, has_bias ? bias_s : nullptr, v, img, y, x, nt * P.BN + cc, valid);
             }
             tc_fence_before_sync();
-            mbar_arrive(&acc_empty[ab]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
         }
     } else {
         // ================= gather warps (256 threads): build the A operand of each stage.
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                     }
                 }
                 // the smem slot is needed only now
-                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_wait_warp(&empty[s], ph ^ 1u);
                 const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + kc0 * DC_A_LBO;
 #pragma unroll
                 for (int i = 0; i < 2; ++i)

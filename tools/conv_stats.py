@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 from edvr_b200 import _lib as L, ops  # noqa: E402
 
 NAMES = ["mma_total", "mma_wait_acc", "mma_wait_a", "mma_wait_w", "a_total", "a_wait_empty", "w_total",
-         "w_wait_empty", "epi_total", "epi_wait_acc", "tiles"]
+         "w_wait_empty", "epi_total", "epi_wait_acc", "tiles", "e_tmem", "e_p1", "e_bar", "e_p2"]
 
 
 def time_it(fn, iters=20):
@@ -39,6 +39,8 @@ def conv_case(N, H, W, cin, cout, k, res32=False, label=""):
         print(f"{label} {variant}: N={N} {H}x{W} {cin}->{cout} k{k} res32={res32}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s", flush=True)
     os.environ["EDVR_B200_CONV_V1"] = "0"
     if pc.BN == 128:
+      for dbg in ([0, 1, 2, 6] if label.startswith("trunk conv1") else [0]):
+        os.environ["EDVR_B200_DBG"] = str(dbg)
         stats = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
         arr = (L.Src * 1)(ops._src(x))
         e = ops._epi(pc.b, ops.ACT_RELU, out, stream, None, stream)
@@ -48,10 +50,10 @@ def conv_case(N, H, W, cin, cout, k, res32=False, label=""):
         st = stats.view(148, 16).double()
         used = st[:, 10] > 0
         m = st[used].mean(0)
-        print("   per-CTA mean cycles:", {n: int(m[i]) for i, n in enumerate(NAMES)}, flush=True)
         tiles = float(m[10])
-        print(f"   cycles/tile: mma_total {m[0]/tiles:.0f}  wait_acc {m[1]/tiles:.0f} wait_a {m[2]/tiles:.0f} wait_w {m[3]/tiles:.0f} | "
-              f"A idle {m[5]/tiles:.0f} of {m[4]/tiles:.0f} | W idle {m[7]/tiles:.0f} | epi wait {m[9]/tiles:.0f} of {m[8]/tiles:.0f}", flush=True)
+        print(f"   dbg={dbg} cycles/tile: mma_total {m[0]/tiles:.0f}  wait_acc {m[1]/tiles:.0f} wait_a {m[2]/tiles:.0f} wait_w {m[3]/tiles:.0f} | "
+              f"A idle {m[5]/tiles:.0f} of {m[4]/tiles:.0f} | W idle {m[7]/tiles:.0f} | epi wait {m[9]/tiles:.0f} of {m[8]/tiles:.0f} | "
+              f"epi: tmem {m[11]/tiles:.0f} p1 {m[12]/tiles:.0f} bar {m[13]/tiles:.0f} p2 {m[14]/tiles:.0f}", flush=True)
 
 
 def dcn_case(N, H, W, C, dg=8):

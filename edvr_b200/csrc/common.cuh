@@ -59,10 +59,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(200000u)      // suspend-time hint (ns): sleep in hardware, do not poll
+            : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
         if (spin == 64) t0 = clock64();
@@ -70,12 +70,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// One lane polls, the warp follows: hundreds of threads polling the same mbarrier through the LSU/MIO path slow
-// every other shared/global access of the SM (measured: profiles/r01_conv_stats_*).  All lanes must call it.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-    if ((threadIdx.x & 31u) == 0) mbar_wait(bar, parity);
-    __syncwarp();
-}
+// Whole-warp wait.  Every lane polls: electing one lane + __syncwarp (and try_wait suspend-time hints) measured
+// 20-50 % SLOWER on B200 (profiles/r01_conv_stats_warp_elected.log) - the wake-up latency dominates.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 
 // ---------------------------------------------------------------- proxy / tcgen05 fences
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -250,14 +250,29 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
     } else {
         // ================= epilogue: 4 warps, warp q owns TMEM lanes (= channels) 32q..32q+31
         const int q = warp & 3;
+        // every parameter the inner loops need lives in a register: with one epilogue warp per scheduler the
+        // latency of a constant-bank load or a 64-bit multiply inside the loop is fully exposed (r01_conv_stats)
+        const EpiParams E = P.epi;
+        const int H = P.H, W = P.W, NIMG = P.N, dbg = P.dbg;
+        const bool same = E.out_mode == OUT_SAME;
+        const bool pack = E.act == ACT_DCN_PACK;
+        const int act1 = pack ? ACT_NONE : E.act;
+        const long long ps16 = E.out16_pix_stride, ps32 = E.out32_pix_stride, psr = E.res_pix_stride;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
             const int nt = tile % P.n_tiles_n, pt = tile / P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
             const uint32_t ab = acc_it & 1u;
-            const int co = nt * 128 + 32 * q + lane;
-            const float bias_c = has_bias ? __ldg(P.epi.bias + co) : 0.f;
-            const int act1 = (P.epi.act == ACT_DCN_PACK) ? ACT_NONE : P.epi.act;
+            const float bias_c = has_bias ? __ldg(E.bias + nt * 128 + 32 * q + lane) : 0.f;
+            // phase-2 ownership: this lane = channels c0..c0+3, this warp = pixel column xq of every slab row pair
+            const int c0 = nt * 128 + lane * 4;
+            const int x0 = tx * C2_TW, y0 = ty * C2_TH;
+            const bool img_ok = img < NIMG;
+            const long long pix0 = (static_cast<long long>(img) * H + y0) * W + x0;      // pixel index of the tile origin
+            __half* o16 = (E.out16 != nullptr) ? E.out16 + E.out16_ch_off + c0 + pix0 * ps16 : nullptr;
+            float* o32 = (E.out32 != nullptr) ? E.out32 + E.out32_ch_off + c0 + pix0 * ps32 : nullptr;
+            const __half* r16 = (E.res16 != nullptr) ? E.res16 + E.res_ch_off + c0 + pix0 * psr : nullptr;
+            const float* r32 = (E.res32 != nullptr) ? E.res32 + E.res_ch_off + c0 + pix0 * psr : nullptr;
             C2_TIMED_WAIT_WARP(&acc_full[ab], (acc_it >> 1) & 1u, ST_E_WAIT_ACC);
             tc_fence_after_sync();
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 256u;
@@ -267,7 +282,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
                 long long tq = P.stats ? clock64() : 0;
                 {
                     float v[32];
-                    if (P.dbg & 4) {
+                    if (dbg & 4) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = 0.f;
                     } else {
@@ -284,16 +299,56 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
                 if (P.stats) { const long long t = clock64(); st_acc[ST_E_P1] += t - tq; tq = t; }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (P.stats) { const long long t = clock64(); st_acc[ST_E_BAR] += t - tq; tq = t; }
-                if (P.dbg & 2) continue;
-                // phase 2: warp q handles pixels q, q+4, ...; lane = 4 consecutive channels
+                if (dbg & 2) continue;
+                // phase 2: warp q handles pixels q, q+4, ... of the slab: row = i/2, column = 4*(i&1) + q
+                const int yb = (col >> 3);                         // first tile row of this slab
+                if (same) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int pj = q + 4 * i;
-                    const int n = col + pj;
-                    const int y = ty * C2_TH + (n >> 3), x = tx * C2_TW + (n & 7);
-                    const bool valid = (img < P.N) && (y < P.H) && (x < P.W) && !(P.dbg & 1);
-                    const float4 v4 = *reinterpret_cast<const float4*>(sl + pj * 128 + lane * 4);
-                    conv2_store4(P.epi, v4, img, y, x, nt * 128 + lane * 4, valid);
+                    for (int i = 0; i < 8; ++i) {
+                        const int ry = yb + (i >> 1), rx = 4 * (i & 1) + q;
+                        const bool valid = img_ok && (y0 + ry < H) && (x0 + rx < W) && !(dbg & 1);
+                        float4 v = *reinterpret_cast<const float4*>(sl + (q + 4 * i) * 128 + lane * 4);
+                        if (pack) {
+                            float* e = reinterpret_cast<float*>(&v);
+                            const int j0 = c0 & 31;
+                            float s = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int j = j0 + k;
+                                if (j < 18) s += fabsf(e[k]);
+                                else if (j < 27) e[k] = sigmoidf_fast(e[k]);
+                            }
+                            if (E.absmean_acc != nullptr) {
+                                s = valid ? s : 0.f;
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                                if (lane == 0 && valid) atomicAdd(E.absmean_acc, s);
+                            }
+                        }
+                        if (valid) {
+                            const long long pofs = static_cast<long long>(ry) * W + rx;
+                            if (r16 != nullptr) {
+                                const uint2 u = __ldg(reinterpret_cast<const uint2*>(r16 + pofs * psr));
+                                const float2 a = unpack_h2(u.x), b = unpack_h2(u.y);
+                                v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+                            }
+                            if (r32 != nullptr) {
+                                const float4 r = __ldg(reinterpret_cast<const float4*>(r32 + pofs * psr));
+                                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+                            }
+                            if (o16 != nullptr)
+                                *reinterpret_cast<uint2*>(o16 + pofs * ps16) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+                            if (o32 != nullptr) *reinterpret_cast<float4*>(o32 + pofs * ps32) = v;
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 8; ++i) {
+                        const int y = y0 + yb + (i >> 1), x = x0 + 4 * (i & 1) + q;
+                        const bool valid = img_ok && (y < H) && (x < W) && !(dbg & 1);
+                        const float4 v4 = *reinterpret_cast<const float4*>(sl + (q + 4 * i) * 128 + lane * 4);
+                        conv2_store4(E, v4, img, y, x, c0, valid);
+                    }
                 }
                 if (P.stats) st_acc[ST_E_P2] += clock64() - tq;
             }

@@ -64,55 +64,6 @@ struct DcnCorner {
 
 struct DcnOff { float dh, dw, mk; };
 
-// (dh, dw, mask) of (pixel, deformable group g, tap) — the only global reads that precede the corner loads
-template <int OFFMODE>
-__device__ __forceinline__ DcnOff dcn_fetch_off(const DcnParams& P, int img, int ho, int wo, bool pix_valid, int g, int tap) {
-    DcnOff o;
-    o.dh = o.dw = o.mk = 0.f;
-    if (!pix_valid) return o;
-    if (OFFMODE == OFF_NCHW_F32) {
-        const int K = P.kh * P.kw;
-        const size_t plane = static_cast<size_t>(P.Ho) * P.Wo;
-        const size_t pix = static_cast<size_t>(ho) * P.Wo + wo;
-        const float* ob = P.offset + (static_cast<size_t>(img) * P.dg + g) * 2 * K * plane + pix;
-        o.dh = __ldg(ob + static_cast<size_t>(2 * tap) * plane);
-        o.dw = __ldg(ob + static_cast<size_t>(2 * tap + 1) * plane);
-        o.mk = __ldg(P.mask + ((static_cast<size_t>(img) * P.dg + g) * K + tap) * plane + pix);
-    } else {
-        const __half* rec = P.offpack + ((static_cast<size_t>(img) * P.Ho + ho) * P.Wo + wo) * P.offpack_pix_stride + g * 32;
-        const __half2 hw = *reinterpret_cast<const __half2*>(rec + 2 * tap);
-        o.dh = __low2float(hw);
-        o.dw = __high2float(hw);
-        o.mk = __half2float(rec[18 + tap]);
-    }
-    return o;
-}
-
-__device__ __forceinline__ DcnCorner dcn_corner(const DcnParams& P, int img, int ho, int wo, bool pix_valid,
-                                                int tap, const DcnOff& o) {
-    DcnCorner c;
-    c.valid = 0;
-    c.base = P.x;
-    c.dW = P.x_pix_stride;
-    c.dH = P.W * P.x_pix_stride;
-    c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0.f;
-    if (!pix_valid) return c;
-    const int ki = tap / P.kw, kj = tap - ki * P.kw;
-    const float h_im = static_cast<float>(ho * P.stride - P.pad + ki * P.dil) + o.dh;
-    const float w_im = static_cast<float>(wo * P.stride - P.pad + kj * P.dil) + o.dw;
-    if (!(h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(P.H) && w_im < static_cast<float>(P.W)))
-        return c;
-    const float hf = floorf(h_im), wf = floorf(w_im);
-    const int hl = static_cast<int>(hf), wl = static_cast<int>(wf);
-    const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-    c.w[0] = hh * hw * o.mk; c.w[1] = hh * lw * o.mk; c.w[2] = lh * hw * o.mk; c.w[3] = lh * lw * o.mk;
-    const bool t = hl >= 0, b = hl + 1 <= P.H - 1, l = wl >= 0, r = wl + 1 <= P.W - 1;
-    c.valid = (t && l ? 1u : 0u) | (t && r ? 2u : 0u) | (b && l ? 4u : 0u) | (b && r ? 8u : 0u);
-    c.base = P.x + P.x_ch_off +
-             ((static_cast<long long>(img) * P.H + hl) * P.W + wl) * static_cast<long long>(P.x_pix_stride);
-    return c;
-}
-
 // 8 channels x 4 corners in packed fp16 (fused fp16 pipeline only; the fp32-layout operator keeps fp32 math)
 __device__ __forceinline__ uint4 dcn_blend8_h2(uint4 u0, uint4 u1, uint4 u2, uint4 u3, const float (&w)[4]) {
     const __half2 w0 = __float2half2_rn(w[0]), w1 = __float2half2_rn(w[1]), w2 = __float2half2_rn(w[2]),
@@ -251,93 +202,157 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
         // ================= gather warps (256 threads): build the A operand of each stage.
         // lane -> (pixel slot = lane/4, channel-atom pair kp = lane%4 -> atoms 2kp, 2kp+1 = 32 contiguous bytes);
         // a thread owns 2 pixels per stage.  The 4 lanes of a pixel cover one full 128-byte line per corner.
+        // All kernel parameters used below are copied to registers first: with two gather warps per scheduler
+        // every constant-bank load / integer division inside the stage loop is exposed latency.
         const int gw = warp - 6;                      // 0..7
         const int kc0 = (lane & 3) * 2;
-        int m[2], ho[2], wo[2];
-        bool pv[2];
+        const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo, strd = P.stride, pad = P.pad, dil = P.dil;
+        const int kw = P.kw, cpg = P.cpg, dg = P.dg;
+        const float fH = static_cast<float>(H), fW = static_cast<float>(W);
+        const long long xps = P.x_pix_stride, xrow = static_cast<long long>(W) * xps;
+        const __half* const xview = P.x + P.x_ch_off;
+        const long long plane = static_cast<long long>(Ho) * Wo;
+        const float* const off_f = P.offset;
+        const float* const msk_f = P.mask;
+        const __half* const off_h = P.offpack;
+        const long long ops = P.offpack_pix_stride;
+
+        struct Pix { int m, hb, wb; bool ok; const __half* rec; const float* ob; const float* mb; };
+        auto fetch = [&](const Pix& px, int g, int tap) -> DcnOff {
+            DcnOff o;
+            o.dh = o.dw = o.mk = 0.f;
+            if (px.ok) {
+                if (OFFMODE == OFF_NCHW_F32) {
+                    const float* ob = px.ob + (static_cast<long long>(g) * 2 * K + 2 * tap) * plane;
+                    o.dh = __ldg(ob);
+                    o.dw = __ldg(ob + plane);
+                    o.mk = __ldg(px.mb + (static_cast<long long>(g) * K + tap) * plane);
+                } else {
+                    const __half* rec = px.rec + g * 32;
+                    const __half2 hw2 = *reinterpret_cast<const __half2*>(rec + 2 * tap);
+                    o.dh = __low2float(hw2);
+                    o.dw = __high2float(hw2);
+                    o.mk = __half2float(rec[18 + tap]);
+                }
+            }
+            return o;
+        };
+        auto corner = [&](const Pix& px, const __half* ximg, int ki, int kj, const DcnOff& o) -> DcnCorner {
+            DcnCorner c;
+            c.valid = 0;
+            c.base = ximg;
+            c.dW = static_cast<int>(xps);
+            c.dH = static_cast<int>(xrow);
+            c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0.f;
+            const float h_im = static_cast<float>(px.hb + ki * dil) + o.dh;
+            const float w_im = static_cast<float>(px.wb + kj * dil) + o.dw;
+            if (px.ok && h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW) {
+                const float hf = floorf(h_im), wf = floorf(w_im);
+                const int hl = static_cast<int>(hf), wl = static_cast<int>(wf);
+                const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+                c.w[0] = hh * hw * o.mk; c.w[1] = hh * lw * o.mk; c.w[2] = lh * hw * o.mk; c.w[3] = lh * lw * o.mk;
+                const bool t = hl >= 0, b = hl + 1 <= H - 1, l = wl >= 0, r = wl + 1 <= W - 1;
+                c.valid = (t && l ? 1u : 0u) | (t && r ? 2u : 0u) | (b && l ? 4u : 0u) | (b && r ? 8u : 0u);
+                c.base = ximg + hl * xrow + wl * xps;
+            }
+            return c;
+        };
+
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int pt = tile / P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
+            const __half* const ximg = xview + static_cast<long long>(img) * H * xrow;
+            Pix px[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                m[i] = i * 64 + gw * 8 + (lane >> 2);
-                ho[i] = ty * DC_TILE_H + (m[i] >> 3);
-                wo[i] = tx * DC_TILE_W + (m[i] & 7);
-                pv[i] = (ho[i] < P.Ho) && (wo[i] < P.Wo);
+                px[i].m = i * 64 + gw * 8 + (lane >> 2);
+                const int ho = ty * DC_TILE_H + (px[i].m >> 3), wo = tx * DC_TILE_W + (px[i].m & 7);
+                px[i].ok = (ho < Ho) && (wo < Wo);
+                px[i].hb = ho * strd - pad;
+                px[i].wb = wo * strd - pad;
+                const long long pix = static_cast<long long>(ho) * Wo + wo;
+                px[i].rec = (OFFMODE == OFF_PACK_F16) ? off_h + (static_cast<long long>(img) * plane + pix) * ops : nullptr;
+                px[i].ob = (OFFMODE == OFF_NCHW_F32) ? off_f + static_cast<long long>(img) * dg * 2 * K * plane + pix : nullptr;
+                px[i].mb = (OFFMODE == OFF_NCHW_F32) ? msk_f + static_cast<long long>(img) * dg * K * plane + pix : nullptr;
             }
-            // software pipeline: the (dh, dw, mask) triples of stage st+1 are fetched while stage st is gathered
+            // software pipeline: the (dh, dw, mask) triples of the NEXT stage are fetched while this one is gathered
+            int g0 = (kc0 * 8) / cpg, g1 = (kc0 * 8 + 8) / cpg;
             DcnOff nxt[2][2];
-            {
-                const int ch = kc0 * 8;
-                const int g0 = ch / P.cpg, g1 = (ch + 8) / P.cpg;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    nxt[i][0] = dcn_fetch_off<OFFMODE>(P, img, ho[i], wo[i], pv[i], g0, 0);
-                    nxt[i][1] = (g1 != g0) ? dcn_fetch_off<OFFMODE>(P, img, ho[i], wo[i], pv[i], g1, 0) : nxt[i][0];
-                }
+            for (int i = 0; i < 2; ++i) {
+                nxt[i][0] = fetch(px[i], g0, 0);
+                nxt[i][1] = (g1 != g0) ? fetch(px[i], g1, 0) : nxt[i][0];
             }
-            for (int st = 0; st < nstages; ++st, ++it) {
-                const int chunk = st / K, tap = st - chunk * K;
+            for (int chunk = 0; chunk < nchunks; ++chunk) {
                 const int ch = chunk * 64 + kc0 * 8;
-                const int g0 = ch / P.cpg, g1 = (ch + 8) / P.cpg;
-                const bool two = g1 != g0;                       // cpg == 8: the two atoms belong to different groups
-                const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
-                DcnCorner cn[2][2];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    cn[i][0] = dcn_corner(P, img, ho[i], wo[i], pv[i], tap, nxt[i][0]);
-                    cn[i][1] = two ? dcn_corner(P, img, ho[i], wo[i], pv[i], tap, nxt[i][1]) : cn[i][0];
-                }
-                // all 16 corner loads in flight before anything is consumed
-                uint4 u[2][2][4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        const DcnCorner& c = cn[i][a];
-                        const __half* b = c.base + ch + a * 8;
-                        u[i][a][0] = u[i][a][1] = u[i][a][2] = u[i][a][3] = make_uint4(0, 0, 0, 0);
-                        if (c.valid & 1u) u[i][a][0] = ldg_nc_v4(b);
-                        if (c.valid & 2u) u[i][a][1] = ldg_nc_v4(b + c.dW);
-                        if (c.valid & 4u) u[i][a][2] = ldg_nc_v4(b + c.dH);
-                        if (c.valid & 8u) u[i][a][3] = ldg_nc_v4(b + c.dH + c.dW);
-                    }
-                // prefetch next stage's offsets
-                if (st + 1 < nstages) {
-                    const int st1 = st + 1, chunk1 = st1 / K, tap1 = st1 - chunk1 * K;
-                    const int ch1 = chunk1 * 64 + kc0 * 8;
-                    const int h0 = ch1 / P.cpg, h1 = (ch1 + 8) / P.cpg;
+                const bool two = g1 != g0;                     // cpg == 8: the two atoms belong to different groups
+                const int chn = ch + 64;
+                const int ng0 = (chunk + 1 < nchunks) ? chn / cpg : g0, ng1 = (chunk + 1 < nchunks) ? (chn + 8) / cpg : g1;
+                int ki = 0, kj = 0;
+                for (int tap = 0; tap < K; ++tap, ++it) {
+                    const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
+                    DcnCorner cn[2][2];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        nxt[i][0] = dcn_fetch_off<OFFMODE>(P, img, ho[i], wo[i], pv[i], h0, tap1);
-                        nxt[i][1] = (h1 != h0) ? dcn_fetch_off<OFFMODE>(P, img, ho[i], wo[i], pv[i], h1, tap1) : nxt[i][0];
+                        cn[i][0] = corner(px[i], ximg, ki, kj, nxt[i][0]);
+                        cn[i][1] = two ? corner(px[i], ximg, ki, kj, nxt[i][1]) : cn[i][0];
                     }
-                }
-                // the smem slot is needed only now
-                mbar_wait_warp(&empty[s], ph ^ 1u);
-                const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + kc0 * DC_A_LBO;
+                    // all 16 corner loads in flight before anything is consumed
+                    uint4 u[2][2][4];
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+                    for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        uint4 r;
-                        if (OFFMODE == OFF_PACK_F16) {
-                            r = dcn_blend8_h2(u[i][a][0], u[i][a][1], u[i][a][2], u[i][a][3], cn[i][a].w);
-                        } else {
-                            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            dcn_blend8(acc, u[i][a][0], cn[i][a].w[0]);
-                            dcn_blend8(acc, u[i][a][1], cn[i][a].w[1]);
-                            dcn_blend8(acc, u[i][a][2], cn[i][a].w[2]);
-                            dcn_blend8(acc, u[i][a][3], cn[i][a].w[3]);
-                            r = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]),
-                                           pack_h2(acc[6], acc[7]));
+                        for (int a = 0; a < 2; ++a) {
+                            const DcnCorner& c = cn[i][a];
+                            const __half* b = c.base + ch + a * 8;
+                            u[i][a][0] = u[i][a][1] = u[i][a][2] = u[i][a][3] = make_uint4(0, 0, 0, 0);
+                            if (c.valid & 1u) u[i][a][0] = ldg_nc_v4(b);
+                            if (c.valid & 2u) u[i][a][1] = ldg_nc_v4(b + c.dW);
+                            if (c.valid & 4u) u[i][a][2] = ldg_nc_v4(b + c.dH);
+                            if (c.valid & 8u) u[i][a][3] = ldg_nc_v4(b + c.dH + c.dW);
                         }
-                        sts_v4(dst + a * DC_A_LBO + m[i] * 16, r);
+                    // prefetch the next stage's offsets (next tap of this chunk, or tap 0 of the next chunk)
+                    {
+                        const bool last_tap = tap + 1 == K;
+                        const int t1 = last_tap ? 0 : tap + 1;
+                        const int h0 = last_tap ? ng0 : g0, h1 = last_tap ? ng1 : g1;
+                        if (!(last_tap && chunk + 1 == nchunks)) {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                nxt[i][0] = fetch(px[i], h0, t1);
+                                nxt[i][1] = (h1 != h0) ? fetch(px[i], h1, t1) : nxt[i][0];
+                            }
+                        }
                     }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+                    if (++kj == kw) { kj = 0; ++ki; }
+                    // the smem slot is needed only now
+                    mbar_wait_warp(&empty[s], ph ^ 1u);
+                    const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + kc0 * DC_A_LBO;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int a = 0; a < 2; ++a) {
+                            uint4 r;
+                            if (OFFMODE == OFF_PACK_F16) {
+                                r = dcn_blend8_h2(u[i][a][0], u[i][a][1], u[i][a][2], u[i][a][3], cn[i][a].w);
+                            } else {
+                                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                dcn_blend8(acc, u[i][a][0], cn[i][a].w[0]);
+                                dcn_blend8(acc, u[i][a][1], cn[i][a].w[1]);
+                                dcn_blend8(acc, u[i][a][2], cn[i][a].w[2]);
+                                dcn_blend8(acc, u[i][a][3], cn[i][a].w[3]);
+                                r = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]),
+                                               pack_h2(acc[6], acc[7]));
+                            }
+                            sts_v4(dst + a * DC_A_LBO + px[i].m * 16, r);
+                        }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
+                }
+                g0 = ng0;
+                g1 = ng1;
             }
         }
     }

@@ -6,12 +6,10 @@
 //     bandwidth instead of the 128 B/cycle an M128 x N128 pair of MMAs needs), and half as many instructions.
 //   * The pixel operand is the same halo-tile trick: one (32+2)x(8+2) halo of a 64-channel chunk is loaded once,
 //     every 3x3 tap is a start-address offset into it (rows of the canonical no-swizzle layout = pixels).
-//   * The accumulator is channel-major, so the epilogue transposes through a small shared-memory slab: phase 1,
-//     each thread (= one TMEM lane = one channel) adds bias, applies the activation and writes 32 pixels of its
-//     channel as fp32 (conflict-free: lanes are consecutive channels); phase 2, each WARP owns one pixel and each
-//     lane 4 consecutive channels: residual loads and NHWC stores are 256/512 contiguous bytes per instruction
-//     (2-4 L1 wavefronts instead of the 32 a pixel-per-lane epilogue costs).  PixelShuffle / stride-2 /
-//     DCN-record variants included.
+//   * The accumulator is channel-major: an epilogue thread owns ONE output channel (its TMEM lane) for 32 pixels
+//     at a time, so a warp touches 32 consecutive channels of one pixel per instruction (one L1 wavefront) and
+//     bias / activation / residual / NHWC stores go straight from registers to global memory.  PixelShuffle /
+//     stride-2 / DCN-record variants included.
 // Same warp roles, mbarrier rings, bulk-copied pre-packed weights and persistent scheduling as conv_igemm.cuh.
 #pragma once
 #include "common.cuh"
@@ -22,14 +20,12 @@ namespace eb {
 
 constexpr int C2_TH = 32, C2_TW = 8;                   // pixel tile: 32 rows x 8 columns = 256 = MMA N
 constexpr int C2_A_BUFS = 2;
-constexpr int C2_W_STAGES = 5;
+constexpr int C2_W_STAGES = 6;
 constexpr int C2_PLANE_BYTES = 341 * 16;               // >= 34*10*16, odd number of 16-byte units
 constexpr int C2_A_BUF_BYTES = 8 * C2_PLANE_BYTES;     // 43648
 constexpr int C2_W_STAGE_BYTES = 128 * 128;            // 128 channels x 64 k x 2 B
 constexpr int C2_THREADS = 320;
-constexpr int C2_SLAB_FLOATS = 32 * 128;                // one 32-pixel x 128-channel fp32 slab
-constexpr int C2_SMEM_BYTES = C2_A_BUFS * C2_A_BUF_BYTES + C2_W_STAGES * C2_W_STAGE_BYTES +
-                              2 * C2_SLAB_FLOATS * 4 + 256;
+constexpr int C2_SMEM_BYTES = C2_A_BUFS * C2_A_BUF_BYTES + C2_W_STAGES * C2_W_STAGE_BYTES + 256;
 
 template <int HALO>
 __device__ __forceinline__ void conv2_load_halo(const ConvParams& P, int chunk, int img, int ty, int tx,
@@ -67,63 +63,6 @@ __device__ __forceinline__ void conv2_load_halo(const ConvParams& P, int chunk, 
     }
 }
 
-// Epilogue phase 2: this lane owns channels c0..c0+3 (packed index) of output pixel (img, y, x); the whole warp
-// shares the pixel, so every validity test is warp-uniform.  v already holds bias + activation.
-__device__ __forceinline__ void conv2_store4(const EpiParams& p, float4 v, int img, int y, int x, int c0, bool valid) {
-    if (p.act == ACT_DCN_PACK) {
-        // packed record: channel j = c % 32 of each group: [0,18) offsets, [18,27) mask logits, rest pad
-        const int j0 = c0 & 31;
-        float* e = reinterpret_cast<float*>(&v);
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int j = j0 + i;
-            if (j < 18) s += fabsf(e[i]);
-            else if (j < 27) e[i] = sigmoidf_fast(e[i]);
-        }
-        if (p.absmean_acc != nullptr) {
-            s = valid ? s : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane_id() == 0 && valid) atomicAdd(p.absmean_acc, s);
-        }
-    }
-    if (!valid) return;
-    if (p.out_mode == OUT_SAME) {
-        const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
-        if (p.res16 != nullptr) {
-            const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.res16 + pix * p.res_pix_stride + p.res_ch_off + c0));
-            const float2 a = unpack_h2(u.x), b = unpack_h2(u.y);
-            v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
-        }
-        if (p.res32 != nullptr) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(p.res32 + pix * p.res_pix_stride + p.res_ch_off + c0));
-            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-        }
-        if (p.out16 != nullptr)
-            *reinterpret_cast<uint2*>(p.out16 + pix * p.out16_pix_stride + p.out16_ch_off + c0) =
-                make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
-        if (p.out32 != nullptr)
-            *reinterpret_cast<float4*>(p.out32 + pix * p.out32_pix_stride + p.out32_ch_off + c0) = v;
-    } else if (p.out_mode == OUT_PIXSHUF2) {
-        // out[b, c, 2y+i, 2x+j] = in[b, 4c + 2i + j, y, x]; this lane owns output channel c0/4
-        const int H2 = 2 * p.H, W2 = 2 * p.W;
-        __half* o = p.out16 + ((static_cast<size_t>(img) * H2 + 2 * y) * W2 + 2 * x) * p.out16_pix_stride +
-                    p.out16_ch_off + (c0 >> 2);
-        const size_t rs = static_cast<size_t>(W2) * p.out16_pix_stride;
-        o[0] = __float2half_rn(v.x);
-        o[p.out16_pix_stride] = __float2half_rn(v.y);
-        o[rs] = __float2half_rn(v.z);
-        o[rs + p.out16_pix_stride] = __float2half_rn(v.w);
-    } else {   // OUT_STRIDE2
-        if ((y | x) & 1) return;
-        const int Ho = (p.H + 1) >> 1, Wo = (p.W + 1) >> 1;
-        const size_t opix = (static_cast<size_t>(img) * Ho + (y >> 1)) * Wo + (x >> 1);
-        *reinterpret_cast<uint2*>(p.out16 + opix * p.out16_pix_stride + p.out16_ch_off + c0) =
-            make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
-    }
-}
-
 // cycle-counter slots of ConvParams.stats (per CTA): who waited on what
 enum : int { ST_MMA_TOTAL = 0, ST_MMA_WAIT_ACC = 1, ST_MMA_WAIT_A = 2, ST_MMA_WAIT_W = 3, ST_A_TOTAL = 4,
              ST_A_WAIT_EMPTY = 5, ST_W_TOTAL = 6, ST_W_WAIT_EMPTY = 7, ST_E_TOTAL = 8, ST_E_WAIT_ACC = 9, ST_TILES = 10, ST_E_TMEM = 11, ST_E_P1 = 12, ST_E_BAR = 13, ST_E_P2 = 14 };
@@ -148,8 +87,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* a_smem = smem;                                         // pixel halo chunks
     uint8_t* w_smem = smem + C2_A_BUFS * C2_A_BUF_BYTES;            // weight stages
-    float* slab = reinterpret_cast<float*>(w_smem + C2_W_STAGES * C2_W_STAGE_BYTES);      // 2 x [32 px][128 ch]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(slab + 2 * C2_SLAB_FLOATS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + C2_W_STAGES * C2_W_STAGE_BYTES);
     uint64_t* a_full = bars;                          // [2]
     uint64_t* a_empty = bars + 2;                     // [2]
     uint64_t* w_full = bars + 4;                      // [6]
@@ -248,13 +186,16 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
             }
         }
     } else {
-        // ================= epilogue: 4 warps, warp q owns TMEM lanes (= channels) 32q..32q+31
+        // ================= epilogue: 4 warps, warp q owns TMEM lanes (= channels) 32q..32q+31.
+        // A thread keeps ONE channel `co` for 32 pixels at a time; a warp therefore touches 32 consecutive channels
+        // of one pixel per instruction = 64 (fp16) / 128 (fp32) contiguous bytes = ONE L1 wavefront, and nothing goes
+        // through shared memory (its port is already saturated by the MMA operands; a smem-staged transpose was
+        // measured slower, profiles/r01_conv_stats_*).  Every parameter is hoisted into registers: with one
+        // epilogue warp per scheduler a constant-bank load or 64-bit multiply inside the loops is exposed latency.
         const int q = warp & 3;
-        // every parameter the inner loops need lives in a register: with one epilogue warp per scheduler the
-        // latency of a constant-bank load or a 64-bit multiply inside the loop is fully exposed (r01_conv_stats)
         const EpiParams E = P.epi;
         const int H = P.H, W = P.W, NIMG = P.N, dbg = P.dbg;
-        const bool same = E.out_mode == OUT_SAME;
+        const int mode = E.out_mode;
         const bool pack = E.act == ACT_DCN_PACK;
         const int act1 = pack ? ACT_NONE : E.act;
         const long long ps16 = E.out16_pix_stride, ps32 = E.out32_pix_stride, psr = E.res_pix_stride;
@@ -263,91 +204,118 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
             const int nt = tile % P.n_tiles_n, pt = tile / P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
             const uint32_t ab = acc_it & 1u;
-            const float bias_c = has_bias ? __ldg(E.bias + nt * 128 + 32 * q + lane) : 0.f;
-            // phase-2 ownership: this lane = channels c0..c0+3, this warp = pixel column xq of every slab row pair
-            const int c0 = nt * 128 + lane * 4;
+            const int co = nt * 128 + 32 * q + lane;
+            const float bias_c = has_bias ? __ldg(E.bias + co) : 0.f;
             const int x0 = tx * C2_TW, y0 = ty * C2_TH;
-            const bool img_ok = img < NIMG;
-            const long long pix0 = (static_cast<long long>(img) * H + y0) * W + x0;      // pixel index of the tile origin
-            __half* o16 = (E.out16 != nullptr) ? E.out16 + E.out16_ch_off + c0 + pix0 * ps16 : nullptr;
-            float* o32 = (E.out32 != nullptr) ? E.out32 + E.out32_ch_off + c0 + pix0 * ps32 : nullptr;
-            const __half* r16 = (E.res16 != nullptr) ? E.res16 + E.res_ch_off + c0 + pix0 * psr : nullptr;
-            const float* r32 = (E.res32 != nullptr) ? E.res32 + E.res_ch_off + c0 + pix0 * psr : nullptr;
+            const int xn = min(C2_TW, W - x0);                               // valid columns (warp-uniform)
+            const bool img_ok = (img < NIMG) && !(dbg & 1);
+            const long long pix0 = (static_cast<long long>(img) * H + y0) * W + x0;
+            __half* o16 = nullptr;
+            float* o32 = nullptr;
+            const __half* r16 = nullptr;
+            const float* r32 = nullptr;
+            long long ops16 = ps16, orow16 = static_cast<long long>(W) * ps16;   // element strides of the fp16 output
+            if (mode == OUT_SAME) {
+                if (E.out16 != nullptr) o16 = E.out16 + E.out16_ch_off + co + pix0 * ps16;
+                if (E.out32 != nullptr) o32 = E.out32 + E.out32_ch_off + co + pix0 * ps32;
+                if (E.res16 != nullptr) r16 = E.res16 + E.res_ch_off + co + pix0 * psr;
+                if (E.res32 != nullptr) r32 = E.res32 + E.res_ch_off + co + pix0 * psr;
+            } else if (mode == OUT_PIXSHUF2) {
+                // out[b, c, 2y+i, 2x+j] = in[b, 4c + 2i + j, y, x]  (edvr_arch.py:351,410-411)
+                const int i = (co >> 1) & 1, j = co & 1;
+                o16 = E.out16 + E.out16_ch_off + (co >> 2) +
+                      ((static_cast<long long>(img) * 2 * H + 2 * y0 + i) * (2 * W) + 2 * x0 + j) * ps16;
+                ops16 = 2 * ps16;
+                orow16 = 2 * static_cast<long long>(2 * W) * ps16;
+            } else {   // OUT_STRIDE2: even pixels only; tile origins are even
+                const int Wo = (W + 1) >> 1, Hos = (H + 1) >> 1;
+                o16 = E.out16 + E.out16_ch_off + co +
+                      ((static_cast<long long>(img) * Hos + (y0 >> 1)) * Wo + (x0 >> 1)) * ps16;
+                orow16 = static_cast<long long>(Wo) * ps16;      // per TWO input rows
+            }
             C2_TIMED_WAIT_WARP(&acc_full[ab], (acc_it >> 1) & 1u, ST_E_WAIT_ACC);
             tc_fence_after_sync();
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 256u;
 #pragma unroll 1
             for (int col = 0; col < 256; col += 32) {
-                float* sl = slab + ((col >> 5) & 1) * C2_SLAB_FLOATS;
                 long long tq = P.stats ? clock64() : 0;
-                {
-                    float v[32];
-                    if (dbg & 4) {
+                float v[32];
+                tmem_ld32(t0 + col, v);
+                if (P.stats) { const long long t = clock64(); st_acc[ST_E_TMEM] += t - tq; tq = t; }
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                    } else {
-                        tmem_ld32(t0 + col, v);
+                for (int j = 0; j < 32; ++j) v[j] += bias_c;
+                act_inplace<32>(v, act1);
+                const int yb = col >> 3;                                   // first tile row of these 32 pixels
+                if (pack) {
+                    // packed DCN record: channel j = co % 32 = lane: [0,18) offsets, [18,27) mask logits, rest pad
+                    float s = 0.f;
+                    if (lane >= 18 && lane < 27) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = sigmoidf_fast(v[e]);
+                    } else if (lane < 18 && E.absmean_acc != nullptr && img_ok) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) s += ((y0 + yb + (e >> 3) < H) && ((e & 7) < xn)) ? fabsf(v[e]) : 0.f;
                     }
-                    if (P.stats) { const long long t = clock64(); st_acc[ST_E_TMEM] += t - tq; tq = t; }
+                    if (E.absmean_acc != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += bias_c;
-                    act_inplace<32>(v, act1);
-                    // phase 1: channel (32q + lane) of pixels col..col+31 -> slab[pixel][channel]
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sl[j * 128 + 32 * q + lane] = v[j];
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                        if (lane == 0 && img_ok) atomicAdd(E.absmean_acc, s);
+                    }
                 }
                 if (P.stats) { const long long t = clock64(); st_acc[ST_E_P1] += t - tq; tq = t; }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (P.stats) { const long long t = clock64(); st_acc[ST_E_BAR] += t - tq; tq = t; }
-                if (dbg & 2) continue;
-                // phase 2: warp q handles pixels q, q+4, ... of the slab: row = i/2, column = 4*(i&1) + q
-                const int yb = (col >> 3);                         // first tile row of this slab
-                if (same) {
+                if (img_ok && !(dbg & 2)) {
+                    if (mode == OUT_SAME) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int ry = yb + (i >> 1), rx = 4 * (i & 1) + q;
-                        const bool valid = img_ok && (y0 + ry < H) && (x0 + rx < W) && !(dbg & 1);
-                        float4 v = *reinterpret_cast<const float4*>(sl + (q + 4 * i) * 128 + lane * 4);
-                        if (pack) {
-                            float* e = reinterpret_cast<float*>(&v);
-                            const int j0 = c0 & 31;
-                            float s = 0.f;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const int j = j0 + k;
-                                if (j < 18) s += fabsf(e[k]);
-                                else if (j < 27) e[k] = sigmoidf_fast(e[k]);
-                            }
-                            if (E.absmean_acc != nullptr) {
-                                s = valid ? s : 0.f;
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                                if (lane == 0 && valid) atomicAdd(E.absmean_acc, s);
-                            }
-                        }
-                        if (valid) {
-                            const long long pofs = static_cast<long long>(ry) * W + rx;
+                        for (int r = 0; r < 4; ++r) {
+                            if (y0 + yb + r >= H) break;
+                            const long long rofs = static_cast<long long>(yb + r) * W;
                             if (r16 != nullptr) {
-                                const uint2 u = __ldg(reinterpret_cast<const uint2*>(r16 + pofs * psr));
-                                const float2 a = unpack_h2(u.x), b = unpack_h2(u.y);
-                                v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+                                const __half* rp = r16 + rofs * psr;
+                                __half t[8];
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) t[c] = (c < xn) ? rp[c * psr] : __float2half(0.f);
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) v[r * 8 + c] += __half2float(t[c]);
                             }
                             if (r32 != nullptr) {
-                                const float4 r = __ldg(reinterpret_cast<const float4*>(r32 + pofs * psr));
-                                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+                                const float* rp = r32 + rofs * psr;
+                                float t[8];
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) t[c] = (c < xn) ? __ldg(rp + c * psr) : 0.f;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) v[r * 8 + c] += t[c];
                             }
-                            if (o16 != nullptr)
-                                *reinterpret_cast<uint2*>(o16 + pofs * ps16) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
-                            if (o32 != nullptr) *reinterpret_cast<float4*>(o32 + pofs * ps32) = v;
+                            if (o16 != nullptr) {
+                                __half* op = o16 + rofs * ps16;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    if (c < xn) op[c * ps16] = __float2half_rn(v[r * 8 + c]);
+                            }
+                            if (o32 != nullptr) {
+                                float* op = o32 + rofs * ps32;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    if (c < xn) op[c * ps32] = v[r * 8 + c];
+                            }
                         }
-                    }
-                } else {
-#pragma unroll 1
-                    for (int i = 0; i < 8; ++i) {
-                        const int y = y0 + yb + (i >> 1), x = x0 + 4 * (i & 1) + q;
-                        const bool valid = img_ok && (y < H) && (x < W) && !(dbg & 1);
-                        const float4 v4 = *reinterpret_cast<const float4*>(sl + (q + 4 * i) * 128 + lane * 4);
-                        conv2_store4(E, v4, img, y, x, c0, valid);
+                    } else if (mode == OUT_PIXSHUF2) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (y0 + yb + r >= H) break;
+                            __half* op = o16 + static_cast<long long>(yb + r) * orow16;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                if (c < xn) op[c * ops16] = __float2half_rn(v[r * 8 + c]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; r += 2) {
+                            if (y0 + yb + r >= H) break;
+                            __half* op = o16 + static_cast<long long>((yb + r) >> 1) * orow16;
+#pragma unroll
+                            for (int c = 0; c < 8; c += 2)
+                                if (c < xn) op[(c >> 1) * ops16] = __float2half_rn(v[r * 8 + c]);
+                        }
                     }
                 }
                 if (P.stats) st_acc[ST_E_P2] += clock64() - tq;

@@ -143,17 +143,40 @@ static bool conv_force_v1() {
 
 static int launch_conv(const ConvParams& P, cudaStream_t st) {
     if (P.N == 0) return EB_OK;
+    // epilogue kind of the transposed kernel (conv_igemm2.cuh); combinations it does not cover use the generic kernel
+    int ek = -1;
     if (P.BN == 128 && P.epi.out_nchw == nullptr && !conv_force_v1()) {
-        // transposed kernel: M = 128 output channels, N = 256 pixels (32 x 8 tile)
+        const EpiParams& e = P.epi;
+        if (e.out_mode == OUT_PIXSHUF2) ek = EK_PIXSHUF;
+        else if (e.out_mode == OUT_STRIDE2) ek = EK_STRIDE2;
+        else if (e.act == ACT_DCN_PACK) { if (e.out16 && !e.out32 && !e.res16 && !e.res32) ek = EK_PACK; }
+        else if (e.out32 || e.res32) { if (!e.res16) ek = EK_F32; }
+        else if (e.out16) ek = EK_PLAIN;
+    }
+    if (ek >= 0) {
         const long long tiles2 = static_cast<long long>(P.N) * ((P.H + C2_TH - 1) / C2_TH) * ((P.W + C2_TW - 1) / C2_TW) * P.n_tiles_n;
         const int grid2 = static_cast<int>(tiles2 < num_sms() ? tiles2 : num_sms());
-        if (P.taps == 9) {
-            if (int rc = set_smem(conv_igemm2_kernel<1>, C2_SMEM_BYTES)) return rc;
-            conv_igemm2_kernel<1><<<grid2, C2_THREADS, C2_SMEM_BYTES, st>>>(P);
-        } else {
-            if (int rc = set_smem(conv_igemm2_kernel<0>, C2_SMEM_BYTES)) return rc;
-            conv_igemm2_kernel<0><<<grid2, C2_THREADS, C2_SMEM_BYTES, st>>>(P);
+        const bool halo = P.taps == 9, stats = P.stats != nullptr;
+#define EB_LAUNCH_C2(HALO_, EK_, ST_)                                                                  \
+        do {                                                                                           \
+            if (int rc = set_smem(conv_igemm2_kernel<HALO_, EK_, ST_>, C2_SMEM_BYTES)) return rc;      \
+            conv_igemm2_kernel<HALO_, EK_, ST_><<<grid2, C2_THREADS, C2_SMEM_BYTES, st>>>(P);          \
+        } while (0)
+#define EB_DISPATCH_C2(EK_)                                                                            \
+        do {                                                                                           \
+            if (stats && halo) EB_LAUNCH_C2(1, EK_, true);                                             \
+            else if (halo) EB_LAUNCH_C2(1, EK_, false);                                                \
+            else EB_LAUNCH_C2(0, EK_, false);                                                          \
+        } while (0)
+        switch (ek) {
+            case EK_PLAIN: EB_DISPATCH_C2(EK_PLAIN); break;
+            case EK_F32: EB_DISPATCH_C2(EK_F32); break;
+            case EK_PACK: EB_DISPATCH_C2(EK_PACK); break;
+            case EK_PIXSHUF: EB_DISPATCH_C2(EK_PIXSHUF); break;
+            default: EB_DISPATCH_C2(EK_STRIDE2); break;
         }
+#undef EB_DISPATCH_C2
+#undef EB_LAUNCH_C2
         return check_launch("conv_igemm2");
     }
     const long long tiles = static_cast<long long>(P.N) * ((P.H + 15) / 16) * ((P.W + 15) / 16) * P.n_tiles_n;

@@ -52,11 +52,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 // Bounded wait: a protocol bug must become a trap (an error the host sees), never a hang.
+// NOT inlined: the kernels are warp-specialised with 10+ wait sites each and instruction-cache misses were a
+// first-order cost (conv_igemm2 was 77 KB of SASS, profiles/r01_ncu_conv2_icache.txt).
 // Polling uses the NON-blocking mbarrier.test_wait plus a short __nanosleep back-off: a blocking try_wait parks
 // inside the memory-instruction (MIO) queue, and with several waiting warps per SM every real shared/global
 // access of the other roles queued behind them (~100 cycles per store measured, profiles/r01_conv_stats_*).
 template <int SLEEP_NS = 32>
-__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
+__device__ __noinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     long long t0 = 0;

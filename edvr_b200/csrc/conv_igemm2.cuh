@@ -69,7 +69,7 @@ enum : int { ST_MMA_TOTAL = 0, ST_MMA_WAIT_ACC = 1, ST_MMA_WAIT_A = 2, ST_MMA_WA
 
 #define C2_TIMED_WAIT_(WAITFN, bar, parity, slot)                                  \
     do {                                                                   \
-        if (P.stats != nullptr) {                                          \
+        if (STATS) {                                                       \
             const long long t_ = clock64();                                \
             WAITFN(bar, parity);                                           \
             st_acc[slot] += static_cast<unsigned long long>(clock64() - t_); \
@@ -80,10 +80,17 @@ enum : int { ST_MMA_TOTAL = 0, ST_MMA_WAIT_ACC = 1, ST_MMA_WAIT_A = 2, ST_MMA_WA
 #define C2_TIMED_WAIT(bar, parity, slot) C2_TIMED_WAIT_(mbar_wait, bar, parity, slot)
 #define C2_TIMED_WAIT_WARP(bar, parity, slot) C2_TIMED_WAIT_(mbar_wait_warp, bar, parity, slot)
 
-template <int HALO>
+// epilogue kinds: one compact instantiation per kind keeps every role's loop inside the instruction cache
+enum : int { EK_PLAIN = 0,    // fp16 NHWC out (+ optional fp16 residual)
+             EK_F32 = 1,      // fp32 residual stream in/out (+ optional fp16 copy): trunk blocks
+             EK_PACK = 2,     // conv_offset: packed DCN record (sigmoid on mask logits, |offset| sum)
+             EK_PIXSHUF = 3,  // PixelShuffle(2) store
+             EK_STRIDE2 = 4 };// even-pixel store
+
+template <int HALO, int EK, bool STATS>
 __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvParams P) {
     unsigned long long st_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const long long st_t0 = clock64();
+    const long long st_t0 = STATS ? clock64() : 0;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* a_smem = smem;                                         // pixel halo chunks
     uint8_t* w_smem = smem + C2_A_BUFS * C2_A_BUF_BYTES;            // weight stages
@@ -189,15 +196,13 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
         // ================= epilogue: 4 warps, warp q owns TMEM lanes (= channels) 32q..32q+31.
         // A thread keeps ONE channel `co` for 32 pixels at a time; a warp therefore touches 32 consecutive channels
         // of one pixel per instruction = 64 (fp16) / 128 (fp32) contiguous bytes = ONE L1 wavefront, and nothing goes
-        // through shared memory (its port is already saturated by the MMA operands; a smem-staged transpose was
-        // measured slower, profiles/r01_conv_stats_*).  Every parameter is hoisted into registers: with one
-        // epilogue warp per scheduler a constant-bank load or 64-bit multiply inside the loops is exposed latency.
+        // through shared memory (its port is already saturated by the MMA operands).  Every parameter is hoisted
+        // into registers and the code is specialised per epilogue kind (EK): with one epilogue warp per scheduler,
+        // constant-bank loads, 64-bit multiplies and instruction-cache misses inside the loop are exposed latency.
         const int q = warp & 3;
         const EpiParams E = P.epi;
-        const int H = P.H, W = P.W, NIMG = P.N, dbg = P.dbg;
-        const int mode = E.out_mode;
-        const bool pack = E.act == ACT_DCN_PACK;
-        const int act1 = pack ? ACT_NONE : E.act;
+        const int H = P.H, W = P.W, NIMG = P.N, dbg = STATS ? P.dbg : 0;
+        const int act1 = (EK == EK_PACK) ? ACT_NONE : E.act;
         const long long ps16 = E.out16_pix_stride, ps32 = E.out32_pix_stride, psr = E.res_pix_stride;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
@@ -215,19 +220,19 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
             const __half* r16 = nullptr;
             const float* r32 = nullptr;
             long long ops16 = ps16, orow16 = static_cast<long long>(W) * ps16;   // element strides of the fp16 output
-            if (mode == OUT_SAME) {
+            if (EK == EK_PLAIN || EK == EK_F32 || EK == EK_PACK) {
                 if (E.out16 != nullptr) o16 = E.out16 + E.out16_ch_off + co + pix0 * ps16;
-                if (E.out32 != nullptr) o32 = E.out32 + E.out32_ch_off + co + pix0 * ps32;
-                if (E.res16 != nullptr) r16 = E.res16 + E.res_ch_off + co + pix0 * psr;
-                if (E.res32 != nullptr) r32 = E.res32 + E.res_ch_off + co + pix0 * psr;
-            } else if (mode == OUT_PIXSHUF2) {
+                if (EK == EK_F32 && E.out32 != nullptr) o32 = E.out32 + E.out32_ch_off + co + pix0 * ps32;
+                if (EK == EK_PLAIN && E.res16 != nullptr) r16 = E.res16 + E.res_ch_off + co + pix0 * psr;
+                if (EK == EK_F32 && E.res32 != nullptr) r32 = E.res32 + E.res_ch_off + co + pix0 * psr;
+            } else if (EK == EK_PIXSHUF) {
                 // out[b, c, 2y+i, 2x+j] = in[b, 4c + 2i + j, y, x]  (edvr_arch.py:351,410-411)
                 const int i = (co >> 1) & 1, j = co & 1;
                 o16 = E.out16 + E.out16_ch_off + (co >> 2) +
                       ((static_cast<long long>(img) * 2 * H + 2 * y0 + i) * (2 * W) + 2 * x0 + j) * ps16;
                 ops16 = 2 * ps16;
                 orow16 = 2 * static_cast<long long>(2 * W) * ps16;
-            } else {   // OUT_STRIDE2: even pixels only; tile origins are even
+            } else {   // EK_STRIDE2: even pixels only; tile origins are even
                 const int Wo = (W + 1) >> 1, Hos = (H + 1) >> 1;
                 o16 = E.out16 + E.out16_ch_off + co +
                       ((static_cast<long long>(img) * Hos + (y0 >> 1)) * Wo + (x0 >> 1)) * ps16;
@@ -238,15 +243,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 256u;
 #pragma unroll 1
             for (int col = 0; col < 256; col += 32) {
-                long long tq = P.stats ? clock64() : 0;
+                long long tq = STATS ? clock64() : 0;
                 float v[32];
                 tmem_ld32(t0 + col, v);
-                if (P.stats) { const long long t = clock64(); st_acc[ST_E_TMEM] += t - tq; tq = t; }
+                if (STATS) { const long long t = clock64(); st_acc[ST_E_TMEM] += t - tq; tq = t; }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] += bias_c;
                 act_inplace<32>(v, act1);
                 const int yb = col >> 3;                                   // first tile row of these 32 pixels
-                if (pack) {
+                if (EK == EK_PACK) {
                     // packed DCN record: channel j = co % 32 = lane: [0,18) offsets, [18,27) mask logits, rest pad
                     float s = 0.f;
                     if (lane >= 18 && lane < 27) {
@@ -262,14 +267,14 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
                         if (lane == 0 && img_ok) atomicAdd(E.absmean_acc, s);
                     }
                 }
-                if (P.stats) { const long long t = clock64(); st_acc[ST_E_P1] += t - tq; tq = t; }
+                if (STATS) { const long long t = clock64(); st_acc[ST_E_P1] += t - tq; tq = t; }
                 if (img_ok && !(dbg & 2)) {
-                    if (mode == OUT_SAME) {
+                    if (EK == EK_PLAIN || EK == EK_PACK) {
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
                             if (y0 + yb + r >= H) break;
                             const long long rofs = static_cast<long long>(yb + r) * W;
-                            if (r16 != nullptr) {
+                            if (EK == EK_PLAIN && r16 != nullptr) {
                                 const __half* rp = r16 + rofs * psr;
                                 __half t[8];
 #pragma unroll
@@ -277,6 +282,16 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) v[r * 8 + c] += __half2float(t[c]);
                             }
+                            __half* op = o16 + rofs * ps16;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                if (c < xn) op[c * ps16] = __float2half_rn(v[r * 8 + c]);
+                        }
+                    } else if (EK == EK_F32) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (y0 + yb + r >= H) break;
+                            const long long rofs = static_cast<long long>(yb + r) * W;
                             if (r32 != nullptr) {
                                 const float* rp = r32 + rofs * psr;
                                 float t[8];
@@ -298,7 +313,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
                                     if (c < xn) op[c * ps32] = v[r * 8 + c];
                             }
                         }
-                    } else if (mode == OUT_PIXSHUF2) {
+                    } else if (EK == EK_PIXSHUF) {
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
                             if (y0 + yb + r >= H) break;
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
                         }
                     }
                 }
-                if (P.stats) st_acc[ST_E_P2] += clock64() - tq;
+                if (STATS) st_acc[ST_E_P2] += clock64() - tq;
             }
             tc_fence_before_sync();
             __syncwarp();
@@ -326,7 +341,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
         }
     }
 
-    if (P.stats != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6)) {
+    if (STATS && P.stats != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6)) {
         unsigned long long* o = P.stats + static_cast<size_t>(blockIdx.x) * 16;
         const unsigned long long tot = static_cast<unsigned long long>(clock64() - st_t0);
         if (warp == 1) { o[ST_MMA_TOTAL] = tot; o[ST_MMA_WAIT_ACC] = st_acc[ST_MMA_WAIT_ACC]; o[ST_MMA_WAIT_A] = st_acc[ST_MMA_WAIT_A]; o[ST_MMA_WAIT_W] = st_acc[ST_MMA_WAIT_W]; }

@@ -181,13 +181,20 @@ static int launch_conv(const ConvParams& P, cudaStream_t st) {
     }
     const long long tiles = static_cast<long long>(P.N) * ((P.H + 15) / 16) * ((P.W + 15) / 16) * P.n_tiles_n;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    if (P.taps == 9) {
-        if (int rc = set_smem(conv_igemm_kernel<1>, CV_SMEM_BYTES)) return rc;
-        conv_igemm_kernel<1><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
-    } else {
-        if (int rc = set_smem(conv_igemm_kernel<0>, CV_SMEM_BYTES)) return rc;
-        conv_igemm_kernel<0><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    // pixel-major kernel: compact instantiations for the common epilogues, generic one for everything else
+    int ek1 = EK_GENERIC;
+    {
+        const EpiParams& e = P.epi;
+        if (e.out_mode == OUT_SAME && e.act != ACT_DCN_PACK && e.out16 && !e.out32 && !e.res32 && !e.out_nchw) ek1 = EK_PLAIN;
     }
+#define EB_LAUNCH_C1(HALO_, EK_)                                                                       \
+    do {                                                                                               \
+        if (int rc = set_smem(conv_igemm_kernel<HALO_, EK_>, CV_SMEM_BYTES)) return rc;                \
+        conv_igemm_kernel<HALO_, EK_><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);                     \
+    } while (0)
+    if (P.taps == 9) { if (ek1 == EK_PLAIN) EB_LAUNCH_C1(1, EK_PLAIN); else EB_LAUNCH_C1(1, EK_GENERIC); }
+    else             { if (ek1 == EK_PLAIN) EB_LAUNCH_C1(0, EK_PLAIN); else EB_LAUNCH_C1(0, EK_GENERIC); }
+#undef EB_LAUNCH_C1
     return check_launch("conv_igemm");
 }
 
@@ -233,15 +240,18 @@ static int launch_dcn(DcnParams& P, cudaStream_t st) {
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     // keep the rest of the 228 KB for L1: the nine taps of a chunk re-read the same slab of x
     static const int carve = (DC_SMEM_BYTES + 1024) * 100 / (228 * 1024) + 1;
-    cudaFuncSetAttribute(dcn_fused_kernel<OFF_NCHW_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    cudaFuncSetAttribute(dcn_fused_kernel<OFF_PACK_F16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    if (P.off_mode == OFF_NCHW_F32) {
-        if (int rc = set_smem(dcn_fused_kernel<OFF_NCHW_F32>, DC_SMEM_BYTES)) return rc;
-        dcn_fused_kernel<OFF_NCHW_F32><<<grid, DC_THREADS, DC_SMEM_BYTES, st>>>(P);
-    } else {
-        if (int rc = set_smem(dcn_fused_kernel<OFF_PACK_F16>, DC_SMEM_BYTES)) return rc;
-        dcn_fused_kernel<OFF_PACK_F16><<<grid, DC_THREADS, DC_SMEM_BYTES, st>>>(P);
-    }
+    const bool nchw = P.epi.out_nchw != nullptr;
+    if (nchw && (P.epi.out16 || P.epi.out32 || P.epi.res16 || P.epi.res32)) return fail(EB_ERR_UNSUPPORTED, "dcn: NCHW output excludes other outputs");
+    if (!nchw && (!P.epi.out16 || P.epi.out32 || P.epi.res32 || P.epi.res16)) return fail(EB_ERR_UNSUPPORTED, "dcn: NHWC fp16 output only");
+#define EB_LAUNCH_DCN(OFF_, EK_)                                                                                     \
+    do {                                                                                                             \
+        cudaFuncSetAttribute(dcn_fused_kernel<OFF_, EK_>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);    \
+        if (int rc = set_smem(dcn_fused_kernel<OFF_, EK_>, DC_SMEM_BYTES)) return rc;                                \
+        dcn_fused_kernel<OFF_, EK_><<<grid, DC_THREADS, DC_SMEM_BYTES, st>>>(P);                                     \
+    } while (0)
+    if (P.off_mode == OFF_NCHW_F32) { if (nchw) EB_LAUNCH_DCN(OFF_NCHW_F32, EK_NCHW); else EB_LAUNCH_DCN(OFF_NCHW_F32, EK_PLAIN); }
+    else                            { if (nchw) EB_LAUNCH_DCN(OFF_PACK_F16, EK_NCHW); else EB_LAUNCH_DCN(OFF_PACK_F16, EK_PLAIN); }
+#undef EB_LAUNCH_DCN
     return check_launch("dcn_fused");
 }
 

@@ -89,7 +89,7 @@ __device__ __forceinline__ void conv_load_halo(const ConvParams& P, int chunk, i
     }
 }
 
-template <int HALO>
+template <int HALO, int EK>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* a_smem = smem;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
                 for (int cc = 0; cc < P.BN; cc += 32) {
                     float v[32];
                     tmem_ld32(t0 + cc, v);
-                    epi_store32(P.epi, has_bias ? bias_s : nullptr, v, img, y, x, nt * P.BN + cc, valid);
+                    epi_store32<EK>(P.epi, has_bias ? bias_s : nullptr, v, img, y, x, nt * P.BN + cc, valid);
                 }
             }
             tc_fence_before_sync();

@@ -63,6 +63,14 @@ __device__ __forceinline__ void conv2_load_halo(const ConvParams& P, int chunk, 
     }
 }
 
+// v[i] with a runtime index, as a select tree (edge tiles only; avoids spilling the register tile to local memory)
+__device__ __forceinline__ float sel32(const float (&v)[32], int i) {
+    float r = v[0];
+#pragma unroll
+    for (int k = 1; k < 32; ++k) r = (i == k) ? v[k] : r;
+    return r;
+}
+
 // cycle-counter slots of ConvParams.stats (per CTA): who waited on what
 enum : int { ST_MMA_TOTAL = 0, ST_MMA_WAIT_ACC = 1, ST_MMA_WAIT_A = 2, ST_MMA_WAIT_W = 3, ST_A_TOTAL = 4,
              ST_A_WAIT_EMPTY = 5, ST_W_TOTAL = 6, ST_W_WAIT_EMPTY = 7, ST_E_TOTAL = 8, ST_E_WAIT_ACC = 9, ST_TILES = 10, ST_E_TMEM = 11, ST_E_P1 = 12, ST_E_BAR = 13, ST_E_P2 = 14 };
@@ -77,15 +85,8 @@ enum : int { ST_MMA_TOTAL = 0, ST_MMA_WAIT_ACC = 1, ST_MMA_WAIT_A = 2, ST_MMA_WA
             WAITFN(bar, parity);                                           \
         }                                                                  \
     } while (0)
-#define C2_TIMED_WAIT(bar, parity, slot) C2_TIMED_WAIT_(mbar_wait, bar, parity, slot)
+#define C2_TIMED_WAIT(bar, parity, slot) C2_TIMED_WAIT_(mbar_wait_t<0>, bar, parity, slot)
 #define C2_TIMED_WAIT_WARP(bar, parity, slot) C2_TIMED_WAIT_(mbar_wait_warp, bar, parity, slot)
-
-// epilogue kinds: one compact instantiation per kind keeps every role's loop inside the instruction cache
-enum : int { EK_PLAIN = 0,    // fp16 NHWC out (+ optional fp16 residual)
-             EK_F32 = 1,      // fp32 residual stream in/out (+ optional fp16 copy): trunk blocks
-             EK_PACK = 2,     // conv_offset: packed DCN record (sigmoid on mask logits, |offset| sum)
-             EK_PIXSHUF = 3,  // PixelShuffle(2) store
-             EK_STRIDE2 = 4 };// even-pixel store
 
 template <int HALO, int EK, bool STATS>
 __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvParams P) {
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
             const int x0 = tx * C2_TW, y0 = ty * C2_TH;
             const int xn = min(C2_TW, W - x0);                               // valid columns (warp-uniform)
             const bool img_ok = (img < NIMG) && !(dbg & 1);
+            const bool interior = (xn == C2_TW) && (y0 + C2_TH <= H);
             const long long pix0 = (static_cast<long long>(img) * H + y0) * W + x0;
             __half* o16 = nullptr;
             float* o32 = nullptr;
@@ -270,47 +272,70 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
                 if (STATS) { const long long t = clock64(); st_acc[ST_E_P1] += t - tq; tq = t; }
                 if (img_ok && !(dbg & 2)) {
                     if (EK == EK_PLAIN || EK == EK_PACK) {
+                        if (interior) {
+                            // full tile: straight-line code, no predicates (keeps the loop inside the L0 I-cache)
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (y0 + yb + r >= H) break;
-                            const long long rofs = static_cast<long long>(yb + r) * W;
-                            if (EK == EK_PLAIN && r16 != nullptr) {
-                                const __half* rp = r16 + rofs * psr;
-                                __half t[8];
+                            for (int r = 0; r < 4; ++r) {
+                                const long long rofs = static_cast<long long>(yb + r) * W;
+                                if (EK == EK_PLAIN && r16 != nullptr) {
+                                    const __half* rp = r16 + rofs * psr;
+                                    __half t[8];
 #pragma unroll
-                                for (int c = 0; c < 8; ++c) t[c] = (c < xn) ? rp[c * psr] : __float2half(0.f);
+                                    for (int c = 0; c < 8; ++c) t[c] = rp[c * psr];
 #pragma unroll
-                                for (int c = 0; c < 8; ++c) v[r * 8 + c] += __half2float(t[c]);
-                            }
-                            __half* op = o16 + rofs * ps16;
-#pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                if (c < xn) op[c * ps16] = __float2half_rn(v[r * 8 + c]);
-                        }
-                    } else if (EK == EK_F32) {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (y0 + yb + r >= H) break;
-                            const long long rofs = static_cast<long long>(yb + r) * W;
-                            if (r32 != nullptr) {
-                                const float* rp = r32 + rofs * psr;
-                                float t[8];
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) t[c] = (c < xn) ? __ldg(rp + c * psr) : 0.f;
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) v[r * 8 + c] += t[c];
-                            }
-                            if (o16 != nullptr) {
+                                    for (int c = 0; c < 8; ++c) v[r * 8 + c] += __half2float(t[c]);
+                                }
                                 __half* op = o16 + rofs * ps16;
 #pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    if (c < xn) op[c * ps16] = __float2half_rn(v[r * 8 + c]);
+                                for (int c = 0; c < 8; ++c) op[c * ps16] = __float2half_rn(v[r * 8 + c]);
                             }
-                            if (o32 != nullptr) {
-                                float* op = o32 + rofs * ps32;
+                        } else {
+#pragma unroll 1
+                            for (int r = 0; r < 4; ++r) {
+                                if (y0 + yb + r >= H) break;
+                                const long long rofs = static_cast<long long>(yb + r) * W;
+                                for (int c = 0; c < xn; ++c) {
+                                    float val = sel32(v, r * 8 + c);
+                                    if (EK == EK_PLAIN && r16 != nullptr) val += __half2float(r16[(rofs + c) * psr]);
+                                    o16[(rofs + c) * ps16] = __float2half_rn(val);
+                                }
+                            }
+                        }
+                    } else if (EK == EK_F32) {
+                        if (interior) {
 #pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    if (c < xn) op[c * ps32] = v[r * 8 + c];
+                            for (int r = 0; r < 4; ++r) {
+                                const long long rofs = static_cast<long long>(yb + r) * W;
+                                if (r32 != nullptr) {
+                                    const float* rp = r32 + rofs * psr;
+                                    float t[8];
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) t[c] = __ldg(rp + c * psr);
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) v[r * 8 + c] += t[c];
+                                }
+                                if (o16 != nullptr) {
+                                    __half* op = o16 + rofs * ps16;
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) op[c * ps16] = __float2half_rn(v[r * 8 + c]);
+                                }
+                                if (o32 != nullptr) {
+                                    float* op = o32 + rofs * ps32;
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) op[c * ps32] = v[r * 8 + c];
+                                }
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int r = 0; r < 4; ++r) {
+                                if (y0 + yb + r >= H) break;
+                                const long long rofs = static_cast<long long>(yb + r) * W;
+                                for (int c = 0; c < xn; ++c) {
+                                    float val = sel32(v, r * 8 + c);
+                                    if (r32 != nullptr) val += __ldg(r32 + (rofs + c) * psr);
+                                    if (o16 != nullptr) o16[(rofs + c) * ps16] = __float2half_rn(val);
+                                    if (o32 != nullptr) o32[(rofs + c) * ps32] = val;
+                                }
                             }
                         }
                     } else if (EK == EK_PIXSHUF) {

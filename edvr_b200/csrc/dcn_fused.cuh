@@ -93,7 +93,7 @@ __device__ __forceinline__ void dcn_blend8(float (&acc)[8], uint4 u, float w) {
     acc[6] = fmaf(w, d.x, acc[6]); acc[7] = fmaf(w, d.y, acc[7]);
 }
 
-template <int OFFMODE>
+template <int OFFMODE, int EK>
 __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* a_smem = smem;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             for (int cc = 0; cc < P.BN; cc += 32) {
                 float v[32];
                 tmem_ld32(t0 + cc, v);
-                epi_store32(P.epi, has_bias ? bias_s : nullptr, v, img, y, x, nt * P.BN + cc, valid);
+                epi_store32<EK>(P.epi, has_bias ? bias_s : nullptr, v, img, y, x, nt * P.BN + cc, valid);
             }
             tc_fence_before_sync();
             __syncwarp();

@@ -8,6 +8,16 @@ namespace eb {
 
 enum : int { OUT_SAME = 0, OUT_PIXSHUF2 = 1, OUT_STRIDE2 = 2 };
 
+// Epilogue kinds.  Kernels are instantiated per kind so that each role's loop stays inside the instruction cache
+// (a single do-everything epilogue made the conv kernels 40-77 KB of SASS; profiles/r01_ncu_conv2_icache.txt).
+enum : int { EK_PLAIN = 0,    // fp16 NHWC out (+ optional fp16 residual)
+             EK_F32 = 1,      // fp32 residual stream in/out (+ optional fp16 copy): trunk blocks
+             EK_PACK = 2,     // conv_offset: packed DCN record (sigmoid on mask logits, |offset| sum)
+             EK_PIXSHUF = 3,  // PixelShuffle(2) store
+             EK_STRIDE2 = 4,  // even-pixel store
+             EK_NCHW = 5,     // fp32 NCHW out (reference operator layout)
+             EK_GENERIC = 6 };// any combination, resolved at run time
+
 struct EpiParams {
     const float* bias;        // [cout_packed] or nullptr
     int act;                  // ACT_*
@@ -29,6 +39,7 @@ struct EpiParams {
 
 // v: 32 consecutive accumulator channels [c0, c0+32) of output pixel (img, y, x).
 // Every lane of the warp must call this (shuffles inside); `valid` masks the memory traffic.
+template <int EK = EK_GENERIC>
 __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __restrict__ bias_s,
                                             float (&v)[32], int img, int y, int x, int c0,
                                             bool valid) {
@@ -36,7 +47,8 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += bias_s[c0 + j];
     }
-    if (p.act == ACT_DCN_PACK) {
+    constexpr bool G = EK == EK_GENERIC;
+    if ((G || EK == EK_PACK) && p.act == ACT_DCN_PACK) {
         // channel j of each 32-group: [0,18) offsets (dh,dw per tap), [18,27) mask logits, rest pad
         float s = 0.f;
 #pragma unroll
@@ -55,7 +67,7 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
     if (!valid) return;
 
     const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
-    if (p.res16 != nullptr) {
+    if ((G || EK == EK_PLAIN) && p.res16 != nullptr) {
         const __half* r = p.res16 + pix * p.res_pix_stride + p.res_ch_off + c0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -65,7 +77,7 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
             v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
         }
     }
-    if (p.res32 != nullptr) {
+    if ((G || EK == EK_F32) && p.res32 != nullptr) {
         const float4* r = reinterpret_cast<const float4*>(p.res32 + pix * p.res_pix_stride +
                                                           p.res_ch_off + c0);
 #pragma unroll
@@ -75,21 +87,21 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
         }
     }
 
-    if (p.out_mode == OUT_SAME) {
-        if (p.out16 != nullptr) {
+    if ((G && p.out_mode == OUT_SAME) || EK == EK_PLAIN || EK == EK_F32 || EK == EK_PACK || EK == EK_NCHW) {
+        if (EK != EK_NCHW && p.out16 != nullptr) {
             uint4* o = reinterpret_cast<uint4*>(p.out16 + pix * p.out16_pix_stride + p.out16_ch_off + c0);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 o[q] = make_uint4(pack_h2(v[q * 8 + 0], v[q * 8 + 1]), pack_h2(v[q * 8 + 2], v[q * 8 + 3]),
                                   pack_h2(v[q * 8 + 4], v[q * 8 + 5]), pack_h2(v[q * 8 + 6], v[q * 8 + 7]));
         }
-        if (p.out32 != nullptr) {
+        if ((G || EK == EK_F32) && p.out32 != nullptr) {
             float4* o = reinterpret_cast<float4*>(p.out32 + pix * p.out32_pix_stride + p.out32_ch_off + c0);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
                 o[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
-        if (p.out_nchw != nullptr) {
+        if ((G || EK == EK_NCHW) && p.out_nchw != nullptr) {
             const size_t plane = static_cast<size_t>(p.H) * p.W;
             float* o = p.out_nchw + (static_cast<size_t>(img) * p.nchw_C + c0) * plane +
                        static_cast<size_t>(y) * p.W + x;
@@ -97,7 +109,7 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
             for (int j = 0; j < 32; ++j)
                 if (c0 + j < p.nchw_C) o[j * plane] = v[j];
         }
-    } else if (p.out_mode == OUT_PIXSHUF2) {
+    } else if ((G && p.out_mode == OUT_PIXSHUF2) || EK == EK_PIXSHUF) {
         // nn.PixelShuffle(2): out[b, c, 2y+i, 2x+j] = in[b, 4c + 2i + j, y, x]
         // (/root/reference/basicsr/models/archs/edvr_arch.py:351,410-411)
         const int H2 = 2 * p.H, W2 = 2 * p.W;

@@ -157,17 +157,23 @@ static int launch_conv(const ConvParams& P, cudaStream_t st) {
         const long long tiles2 = static_cast<long long>(P.N) * ((P.H + C2_TH - 1) / C2_TH) * ((P.W + C2_TW - 1) / C2_TW) * P.n_tiles_n;
         const int grid2 = static_cast<int>(tiles2 < num_sms() ? tiles2 : num_sms());
         const bool halo = P.taps == 9, stats = P.stats != nullptr;
-#define EB_LAUNCH_C2(HALO_, EK_, ST_)                                                                  \
+#define EB_LAUNCH_C2(HALO_, EK_, ST_, PS_)                                                             \
         do {                                                                                           \
-            if (int rc = set_smem(conv_igemm2_kernel<HALO_, EK_, ST_>, C2_SMEM_BYTES)) return rc;      \
-            conv_igemm2_kernel<HALO_, EK_, ST_><<<grid2, C2_THREADS, C2_SMEM_BYTES, st>>>(P);          \
+            if (int rc = set_smem(conv_igemm2_kernel<HALO_, EK_, ST_, PS_>, C2_SMEM_BYTES)) return rc; \
+            conv_igemm2_kernel<HALO_, EK_, ST_, PS_><<<grid2, C2_THREADS, C2_SMEM_BYTES, st>>>(P);     \
         } while (0)
 #define EB_DISPATCH_C2(EK_)                                                                            \
         do {                                                                                           \
-            if (stats && halo) EB_LAUNCH_C2(1, EK_, true);                                             \
-            else if (halo) EB_LAUNCH_C2(1, EK_, false);                                                \
-            else EB_LAUNCH_C2(0, EK_, false);                                                          \
+            if (stats && halo) EB_LAUNCH_C2(1, EK_, true, 0);                                          \
+            else if (halo && ps == 128) EB_LAUNCH_C2(1, EK_, false, 128);                              \
+            else if (halo && ps == 256) EB_LAUNCH_C2(1, EK_, false, 256);                              \
+            else if (halo) EB_LAUNCH_C2(1, EK_, false, 0);                                             \
+            else if (ps == 128) EB_LAUNCH_C2(0, EK_, false, 128);                                      \
+            else EB_LAUNCH_C2(0, EK_, false, 0);                                                       \
         } while (0)
+        // compile-time pixel stride when every tensor the epilogue touches agrees on it
+        int ps = P.epi.out16 ? P.epi.out16_pix_stride : (P.epi.out32 ? P.epi.out32_pix_stride : 0);
+        if ((P.epi.out32 && P.epi.out32_pix_stride != ps) || ((P.epi.res16 || P.epi.res32) && P.epi.res_pix_stride != ps)) ps = 0;
         switch (ek) {
             case EK_PLAIN: EB_DISPATCH_C2(EK_PLAIN); break;
             case EK_F32: EB_DISPATCH_C2(EK_F32); break;

@@ -54,9 +54,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // Bounded wait: a protocol bug must become a trap (an error the host sees), never a hang.
 // NOT inlined: the kernels are warp-specialised with 10+ wait sites each and instruction-cache misses were a
 // first-order cost (conv_igemm2 was 77 KB of SASS, profiles/r01_ncu_conv2_icache.txt).
-// Polling uses the NON-blocking mbarrier.test_wait plus a short __nanosleep back-off: a blocking try_wait parks
-// inside the memory-instruction (MIO) queue, and with several waiting warps per SM every real shared/global
-// access of the other roles queued behind them (~100 cycles per store measured, profiles/r01_conv_stats_*).
+// Blocking try_wait (hardware sleep).  A non-blocking test_wait + __nanosleep back-off and warp-elected polling
+// were both measured slower (wake-up latency; profiles/r01_conv_stats_*).
 template <int SLEEP_NS = 32>
 __device__ __noinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -65,7 +64,7 @@ __device__ __noinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity)
@@ -76,7 +75,7 @@ __device__ __noinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
         if (spin > 64 && (spin & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_t<32>(bar, parity); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_t<0>(bar, parity); }
 
 // Whole-warp wait.  Every lane polls: electing one lane + __syncwarp (and try_wait suspend-time hints) measured
 // 20-50 % SLOWER on B200 (profiles/r01_conv_stats_warp_elected.log) - the wake-up latency dominates.

@@ -88,7 +88,10 @@ enum : int { ST_MMA_TOTAL = 0, ST_MMA_WAIT_ACC = 1, ST_MMA_WAIT_A = 2, ST_MMA_WA
 #define C2_TIMED_WAIT(bar, parity, slot) C2_TIMED_WAIT_(mbar_wait_t<0>, bar, parity, slot)
 #define C2_TIMED_WAIT_WARP(bar, parity, slot) C2_TIMED_WAIT_(mbar_wait_warp, bar, parity, slot)
 
-template <int HALO, int EK, bool STATS>
+// PS: pixel stride (elements) of the output / residual tensors when it is a compile-time constant (0 = runtime).
+// With a constant stride the 8 pixels of a tile row are addressed as [row pointer + immediate]; with a runtime
+// stride the compiler recomputes one address register pair per access and consecutive stores serialise on it.
+template <int HALO, int EK, bool STATS, int PS>
 __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvParams P) {
     unsigned long long st_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long st_t0 = STATS ? clock64() : 0;
@@ -204,7 +207,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv_igemm2_kernel(const ConvPa
         const EpiParams E = P.epi;
         const int H = P.H, W = P.W, NIMG = P.N, dbg = STATS ? P.dbg : 0;
         const int act1 = (EK == EK_PACK) ? ACT_NONE : E.act;
-        const long long ps16 = E.out16_pix_stride, ps32 = E.out32_pix_stride, psr = E.res_pix_stride;
+        const long long ps16 = PS ? PS : E.out16_pix_stride, ps32 = PS ? PS : E.out32_pix_stride,
+                        psr = PS ? PS : E.res_pix_stride;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
             const int nt = tile % P.n_tiles_n, pt = tile / P.n_tiles_n;

@@ -141,11 +141,21 @@ static bool conv_force_v1() {
     return e != nullptr && e[0] == '1';
 }
 
+static bool conv_force_v2() {
+    const char* e = getenv("EDVR_B200_CONV_V2");
+    return e != nullptr && e[0] == '1';
+}
+
 static int launch_conv(const ConvParams& P, cudaStream_t st) {
     if (P.N == 0) return EB_OK;
     // epilogue kind of the transposed kernel (conv_igemm2.cuh); combinations it does not cover use the generic kernel
     int ek = -1;
-    if (P.BN == 128 && P.epi.out_nchw == nullptr && !conv_force_v1()) {
+    // measured on B200 (profiles/r01_conv_stats_*): the channel-major kernel wins when the K loop is long
+    // (Cin >= 256: the per-tile epilogue is amortised) and for the PixelShuffle store; the pixel-major kernel
+    // (16-byte stores, 8x fewer store instructions per thread) wins elsewhere.
+    const int cin_total = P.src[0].C + (P.nsrc > 1 ? P.src[1].C : 0);
+    const bool prefer_v2 = conv_force_v2() || (P.taps == 9 && (cin_total >= 256 || P.epi.out_mode == OUT_PIXSHUF2)) || P.stats != nullptr;
+    if (P.BN == 128 && P.epi.out_nchw == nullptr && !conv_force_v1() && prefer_v2) {
         const EpiParams& e = P.epi;
         if (e.out_mode == OUT_PIXSHUF2) ek = EK_PIXSHUF;
         else if (e.out_mode == OUT_STRIDE2) ek = EK_STRIDE2;

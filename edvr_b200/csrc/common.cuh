@@ -52,12 +52,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 // Bounded wait: a protocol bug must become a trap (an error the host sees), never a hang.
-// NOT inlined: the kernels are warp-specialised with 10+ wait sites each and instruction-cache misses were a
-// first-order cost (conv_igemm2 was 77 KB of SASS, profiles/r01_ncu_conv2_icache.txt).
+// Inlined: a __noinline__ version (to shrink the code) added ~200 cycles per pipeline stage to the MMA issuer.
 // Blocking try_wait (hardware sleep).  A non-blocking test_wait + __nanosleep back-off and warp-elected polling
 // were both measured slower (wake-up latency; profiles/r01_conv_stats_*).
 template <int SLEEP_NS = 32>
-__device__ __noinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     long long t0 = 0;

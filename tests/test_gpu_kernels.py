@@ -71,9 +71,11 @@ CONV_CASES = [
 
 @pytest.fixture(params=["v2_transposed", "v1_pixel_major"])
 def conv_variant(request, monkeypatch):
-    """Cout tiles of 128 run conv_igemm2 (channel-major accumulator) by default; EDVR_B200_CONV_V1=1 forces the
-    pixel-major kernel, which also serves every other tile width.  Both must pass the same cases."""
+    """Cout tiles of 128 may run conv_igemm2 (channel-major accumulator; picked automatically for long K loops and
+    PixelShuffle stores, forced here with EDVR_B200_CONV_V2=1) or the pixel-major kernel (EDVR_B200_CONV_V1=1), which
+    also serves every other tile width.  Both must pass the same cases."""
     monkeypatch.setenv("EDVR_B200_CONV_V1", "1" if request.param == "v1_pixel_major" else "0")
+    monkeypatch.setenv("EDVR_B200_CONV_V2", "0" if request.param == "v1_pixel_major" else "1")
     return request.param
 
 

@@ -35,6 +35,7 @@ def conv_case(N, H, W, cin, cout, k, res32=False, label=""):
     fl = 2.0 * N * H * W * cout * cin * k * k
     for variant in ("v2", "v1"):
         os.environ["EDVR_B200_CONV_V1"] = "1" if variant == "v1" else "0"
+        os.environ["EDVR_B200_CONV_V2"] = "0" if variant == "v1" else "1"
         ms = time_it(lambda: ops.conv2d(pc, [x], out16=out, act=ops.ACT_RELU, res32=stream, out32=stream))
         print(f"{label} {variant}: N={N} {H}x{W} {cin}->{cout} k{k} res32={res32}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s", flush=True)
     os.environ["EDVR_B200_CONV_V1"] = "0"

@@ -27,7 +27,7 @@ class Epilogue(ctypes.Structure):
                 ("out16", c_void_p), ("out16_pix_stride", c_int), ("out16_ch_off", c_int),
                 ("out32", c_void_p), ("out32_pix_stride", c_int), ("out32_ch_off", c_int),
                 ("out_nchw", c_void_p), ("nchw_C", c_int), ("out_mode", c_int),
-                ("absmean_acc", c_void_p)]
+                ("absmean_acc", c_void_p), ("f32_blocked", c_int)]
 
 
 _SIGS = {
@@ -55,7 +55,9 @@ _SIGS = {
                               c_void_p, c_int, c_int, c_void_p]),
     "eb_pool_max_avg": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "eb_tsa_temporal": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "eb_tsa_modulate": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "eb_tsa_modulate": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_int, c_void_p]),
+    "eb_f32_blocked_elems": (c_size_t, [c_int] * 4),
     "eb_add": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

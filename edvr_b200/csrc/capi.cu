@@ -77,6 +77,10 @@ int fill_epi(const eb_epilogue_t* e, int H, int W, int cout_packed, EpiParams* o
     o->nchw_C = e->nchw_C;
     o->out_mode = e->out_mode;
     o->absmean_acc = e->absmean_acc;
+    o->f32_blocked = e->f32_blocked;
+    if (e->f32_blocked && (e->out_mode != EB_OUT_SAME || (e->out32 && (e->out32_pix_stride % 32 || e->out32_ch_off % 32)) ||
+                           (e->res32 && (e->res_pix_stride % 32 || e->res_ch_off % 32)) || e->res16))
+        return fail(EB_ERR_UNSUPPORTED, "f32_blocked needs OUT_SAME, C %% 32 == 0, and no fp16 residual");
     if (e->act < EB_ACT_NONE || e->act > EB_ACT_SIGMOID) return fail(EB_ERR_UNSUPPORTED, "act %d", e->act);
     if (e->out_mode < EB_OUT_SAME || e->out_mode > EB_OUT_STRIDE2)
         return fail(EB_ERR_UNSUPPORTED, "out_mode %d", e->out_mode);
@@ -155,7 +159,7 @@ static int launch_conv(const ConvParams& P, cudaStream_t st) {
     // (16-byte stores, 8x fewer store instructions per thread) wins elsewhere.
     const int cin_total = P.src[0].C + (P.nsrc > 1 ? P.src[1].C : 0);
     const bool prefer_v2 = conv_force_v2() || (P.taps == 9 && (cin_total >= 256 || P.epi.out_mode == OUT_PIXSHUF2)) || P.stats != nullptr;
-    if (P.BN == 128 && P.epi.out_nchw == nullptr && !conv_force_v1() && prefer_v2) {
+    if (P.BN == 128 && P.epi.out_nchw == nullptr && !P.epi.f32_blocked && !conv_force_v1() && prefer_v2) {
         const EpiParams& e = P.epi;
         if (e.out_mode == OUT_PIXSHUF2) ek = EK_PIXSHUF;
         else if (e.out_mode == OUT_STRIDE2) ek = EK_STRIDE2;
@@ -202,14 +206,15 @@ static int launch_conv(const ConvParams& P, cudaStream_t st) {
     {
         const EpiParams& e = P.epi;
         if (e.out_mode == OUT_SAME && e.act != ACT_DCN_PACK && e.out16 && !e.out32 && !e.res32 && !e.out_nchw) ek1 = EK_PLAIN;
+        else if (e.out_mode == OUT_SAME && e.act != ACT_DCN_PACK && (e.out32 || e.res32) && !e.res16 && !e.out_nchw) ek1 = EK_F32;
     }
 #define EB_LAUNCH_C1(HALO_, EK_)                                                                       \
     do {                                                                                               \
         if (int rc = set_smem(conv_igemm_kernel<HALO_, EK_>, CV_SMEM_BYTES)) return rc;                \
         conv_igemm_kernel<HALO_, EK_><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);                     \
     } while (0)
-    if (P.taps == 9) { if (ek1 == EK_PLAIN) EB_LAUNCH_C1(1, EK_PLAIN); else EB_LAUNCH_C1(1, EK_GENERIC); }
-    else             { if (ek1 == EK_PLAIN) EB_LAUNCH_C1(0, EK_PLAIN); else EB_LAUNCH_C1(0, EK_GENERIC); }
+    if (P.taps == 9) { if (ek1 == EK_PLAIN) EB_LAUNCH_C1(1, EK_PLAIN); else if (ek1 == EK_F32) EB_LAUNCH_C1(1, EK_F32); else EB_LAUNCH_C1(1, EK_GENERIC); }
+    else             { if (ek1 == EK_PLAIN) EB_LAUNCH_C1(0, EK_PLAIN); else if (ek1 == EK_F32) EB_LAUNCH_C1(0, EK_F32); else EB_LAUNCH_C1(0, EK_GENERIC); }
 #undef EB_LAUNCH_C1
     return check_launch("conv_igemm");
 }
@@ -575,17 +580,23 @@ int eb_tsa_temporal(const void* emb, const void* emb_ref, const void* aligned, v
     return check_launch("tsa_temporal");
 }
 
+size_t eb_f32_blocked_elems(int N, int H, int W, int C) {
+    return static_cast<size_t>(N) * ((H + 15) / 16) * ((W + 15) / 16) * 256 * static_cast<size_t>(C);
+}
+
 int eb_tsa_modulate(const void* feat, int fps, int fco, const void* attn, const void* attn_add, void* out16,
-                    float* out32, int npix, int C, void* stream) {
+                    float* out32, int N, int H, int W, int C, int f32_blocked, void* stream) {
+    const long long npix = static_cast<long long>(N) * H * W;
+    if (f32_blocked && C % 32) return fail(EB_ERR_UNSUPPORTED, "tsa_modulate: blocked fp32 output needs C %% 32 == 0");
     if (!view_ok(feat, fps, fco, C) || !attn || !attn_add || (!out16 && !out32) || !al16(attn) || !al16(attn_add) ||
         (out16 && !al16(out16)) || (out32 && !al16(out32)))
         return fail(EB_ERR_ALIGNMENT, "tsa_modulate: bad view");
     if (npix < 0) return fail(EB_ERR_INVALID_SHAPE, "tsa_modulate: npix");
     if (npix == 0) return EB_OK;
-    const long long items = static_cast<long long>(npix) * (C / 8);
+    const long long items = npix * (C / 8);
     tsa_modulate_kernel<<<grid_1d(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(feat), fps, fco, static_cast<const __half*>(attn),
-        static_cast<const __half*>(attn_add), static_cast<__half*>(out16), out32, npix, C);
+        static_cast<const __half*>(attn_add), static_cast<__half*>(out16), out32, npix, C, H, W, f32_blocked);
     return check_launch("tsa_modulate");
 }
 

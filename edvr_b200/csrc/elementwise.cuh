@@ -3,6 +3,7 @@
 // 16-byte vectors (8 halfs); fp32 math inside.
 #pragma once
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace eb {
 
@@ -335,7 +336,7 @@ __global__ void tsa_temporal_kernel(const __half* __restrict__ emb, const __half
 __global__ void tsa_modulate_kernel(const __half* __restrict__ feat, int fps, int fco,
                                     const __half* __restrict__ attn, const __half* __restrict__ attn_add,
                                     __half* __restrict__ out16, float* __restrict__ out32,
-                                    long long npix, int C) {
+                                    long long npix, int C, int H, int W, int f32_blocked) {
     const int groups = C / 8;
     const long long total = npix * groups;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -350,9 +351,16 @@ __global__ void tsa_modulate_kernel(const __half* __restrict__ feat, int fps, in
         for (int e = 0; e < 8; ++e) r.v[e] = f.v[e] * (1.0f / (1.0f + __expf(-a.v[e]))) * 2.f + d.v[e];
         if (out16) h8_store(out16 + pix * C + g * 8, r);
         if (out32) {
-            float4* o = reinterpret_cast<float4*>(out32 + pix * C + g * 8);
-            o[0] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-            o[1] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+            if (f32_blocked) {
+                const int x = pix % W, y = (pix / W) % H, img = pix / (static_cast<long long>(W) * H);
+                float* o = out32 + blocked32_block(img, y, x, g >> 2, H, W, C) + ((g & 3) * 2) * 128;
+                *reinterpret_cast<float4*>(o) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+                *reinterpret_cast<float4*>(o + 128) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+            } else {
+                float4* o = reinterpret_cast<float4*>(out32 + pix * C + g * 8);
+                o[0] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+                o[1] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+            }
         }
     }
 }

@@ -35,7 +35,17 @@ struct EpiParams {
     int nchw_C;
     int out_mode;             // OUT_*
     float* absmean_acc;       // ACT_DCN_PACK: sum |offset| accumulator (optional)
+    int f32_blocked;          // res32 / out32 in the tile-blocked layout (blocked32_offset)
 };
+
+// Tile-blocked fp32 layout: float index of (pixel (img,y,x), channel c) for an [N,H,W,C] tensor, C % 32 == 0.
+// Block = (16x16 tile, 16x8 half `sub`, 32-pixel quarter q, 32-channel chunk): [8 float4 slots][32 pixels][4 floats].
+__host__ __device__ __forceinline__ long long blocked32_block(int img, int y, int x, int chunk, int H, int W, int C) {
+    const int tiles_x = (W + 15) >> 4, tiles_y = (H + 15) >> 4;
+    const long long tile = (static_cast<long long>(img) * tiles_y + (y >> 4)) * tiles_x + (x >> 4);
+    const int sub = (x >> 3) & 1, m = ((y & 15) << 3) | (x & 7);
+    return (((tile * 2 + sub) * 4 + (m >> 5)) * (C >> 5) + chunk) * 1024 + (m & 31) * 4;
+}
 
 // v: 32 consecutive accumulator channels [c0, c0+32) of output pixel (img, y, x).
 // Every lane of the warp must call this (shuffles inside); `valid` masks the memory traffic.
@@ -77,12 +87,16 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
             v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
         }
     }
+    // blocked fp32 stream: this thread's 32 channels are 8 float4 slots, 512 B apart, lanes 16 B apart
+    const long long blk = ((G || EK == EK_F32) && p.f32_blocked)
+        ? blocked32_block(img, y, x, (p.res_ch_off + c0) >> 5, p.H, p.W, p.res_pix_stride) : 0;
     if ((G || EK == EK_F32) && p.res32 != nullptr) {
-        const float4* r = reinterpret_cast<const float4*>(p.res32 + pix * p.res_pix_stride +
-                                                          p.res_ch_off + c0);
+        const float4* r = p.f32_blocked ? reinterpret_cast<const float4*>(p.res32 + blk)
+                                        : reinterpret_cast<const float4*>(p.res32 + pix * p.res_pix_stride + p.res_ch_off + c0);
+        const int rs = p.f32_blocked ? 32 : 1;          // float4 stride between consecutive 4-channel slots
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            float4 f = __ldg(r + q);
+            float4 f = __ldg(r + q * rs);
             v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
         }
     }
@@ -96,10 +110,13 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
                                   pack_h2(v[q * 8 + 4], v[q * 8 + 5]), pack_h2(v[q * 8 + 6], v[q * 8 + 7]));
         }
         if ((G || EK == EK_F32) && p.out32 != nullptr) {
-            float4* o = reinterpret_cast<float4*>(p.out32 + pix * p.out32_pix_stride + p.out32_ch_off + c0);
+            const long long blko = p.f32_blocked ? blocked32_block(img, y, x, (p.out32_ch_off + c0) >> 5, p.H, p.W, p.out32_pix_stride) : 0;
+            float4* o = p.f32_blocked ? reinterpret_cast<float4*>(p.out32 + blko)
+                                      : reinterpret_cast<float4*>(p.out32 + pix * p.out32_pix_stride + p.out32_ch_off + c0);
+            const int os = p.f32_blocked ? 32 : 1;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                o[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                o[q * os] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
         if ((G || EK == EK_NCHW) && p.out_nchw != nullptr) {
             const size_t plane = static_cast<size_t>(p.H) * p.W;

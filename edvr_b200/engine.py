@@ -36,6 +36,14 @@ class _Arena:
             self.bufs[key] = t
         return View(t)
 
+    def blocked32(self, name, N, H, W, C):
+        key = (name, "b32", N, H, W, C)
+        t = self.bufs.get(key)
+        if t is None:
+            t = ops.Blocked32(N, H, W, C, self.device)
+            self.bufs[key] = t
+        return t
+
     def f32(self, name, *shape):
         key = (name,) + tuple(shape)
         t = self.bufs.get(key)
@@ -282,7 +290,7 @@ class EDVREngine:
 
         # ---- fusion
         fused16 = a.act("fused16", B, h, w, C)
-        trunk32 = a.f32("trunk32", B, h, w, C)
+        trunk32 = a.blocked32("trunk32", B, h, w, C)      # fp32 residual stream, tile-blocked private layout
         if self.with_tsa:
             run_tsa(a, p, "fusion.", aligned, B, T, self.center, fused16, trunk32)
         else:

@@ -131,6 +131,26 @@ def _src(v, div=1, mul=1, keep=0, add=0):
     return L.Src(v.t.data_ptr(), v.C, v.pix_stride, v.ch_off, div, mul, keep, add)
 
 
+class Blocked32:
+    """fp32 [N,H,W,C] tensor in the library's private tile-blocked layout (eb_f32_blocked_elems)."""
+
+    def __init__(self, N, H, W, C, device="cuda"):
+        self.N, self.H, self.W, self.C = N, H, W, C
+        n = L.lib().eb_f32_blocked_elems(N, H, W, C)
+        self.t = torch.zeros(n, dtype=torch.float32, device=device)
+
+    def to_nhwc(self):
+        """Un-block into a dense [N,H,W,C] tensor (tests / debugging only)."""
+        N, H, W, C = self.N, self.H, self.W, self.C
+        ty, tx = (H + 15) // 16, (W + 15) // 16
+        # [tile n, ty, tx][sub 2][q 4][chunk C/32][f4 8][lane 32][e 4]
+        v = self.t.view(N, ty, tx, 2, 4, C // 32, 8, 32, 4)
+        # lane = (row_in_q 4, col 8); pixel y = q*4 + row_in_q, x = sub*8 + col; channel = chunk*32 + f4*4 + e
+        v = v.view(N, ty, tx, 2, 4, C // 32, 8, 4, 8, 4).permute(0, 1, 4, 7, 2, 3, 8, 5, 6, 9)
+        v = v.reshape(N, ty * 16, tx * 16, C)
+        return v[:, :H, :W, :].contiguous()
+
+
 def _epi(pc_bias, act, out16=None, out32=None, res16=None, res32=None, out_nchw=None, nchw_C=0,
          out_mode=OUT_SAME, absmean=None):
     e = L.Epilogue()
@@ -138,6 +158,13 @@ def _epi(pc_bias, act, out16=None, out32=None, res16=None, res32=None, out_nchw=
     e.act = act
     if res16 is not None:
         e.res16, e.res_pix_stride, e.res_ch_off = res16.t.data_ptr(), res16.pix_stride, res16.ch_off
+    if isinstance(res32, Blocked32) or isinstance(out32, Blocked32):
+        e.f32_blocked = 1
+        if res32 is not None:
+            e.res32, e.res_pix_stride, e.res_ch_off = res32.t.data_ptr(), res32.C, 0
+        if out32 is not None:
+            e.out32, e.out32_pix_stride, e.out32_ch_off = out32.t.data_ptr(), out32.C, 0
+        res32 = out32 = None
     if res32 is not None:
         e.res32, e.res_pix_stride, e.res_ch_off = res32.data_ptr(), res32.shape[3], 0
     if out16 is not None:
@@ -228,11 +255,12 @@ def tsa_temporal(emb, emb_ref, aligned, dst, B, T):
 
 
 def tsa_modulate(feat, attn, attn_add, out16=None, out32=None):
-    npix = attn.N * attn.H * attn.W
+    blocked = isinstance(out32, Blocked32)
+    o32 = out32.t if blocked else out32
     with _Rec("tsa_modulate", 1):
         L.check(L.lib().eb_tsa_modulate(L.ptr(feat.t), feat.pix_stride, feat.ch_off, L.ptr(attn.t), L.ptr(attn_add.t),
-                                        L.ptr(None if out16 is None else out16.t), L.ptr(out32), npix, attn.C,
-                                        L.stream_ptr()), "eb_tsa_modulate")
+                                        L.ptr(None if out16 is None else out16.t), L.ptr(o32), attn.N, attn.H, attn.W,
+                                        attn.C, 1 if blocked else 0, L.stream_ptr()), "eb_tsa_modulate")
 
 
 def mdcn_forward(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, workspace=None):

@@ -67,6 +67,7 @@ typedef struct {
     int nchw_C;
     int out_mode;
     float* absmean_acc;       /* optional: sum |offset| (EB_ACT_DCN_PACK), for the >50 warning */
+    int f32_blocked;          /* res32/out32 use the tile-blocked private layout of eb_f32_blocked_elems() */
 } eb_epilogue_t;
 
 /* ---- library info ------------------------------------------------------------------- */
@@ -90,6 +91,12 @@ int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, co
 /* same, plus per-CTA cycle counters (device uint64 [148][16]; who waited on which pipeline barrier) */
 int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack,
                     int BN, int n_tiles_n, const eb_epilogue_t* epi, unsigned long long* stats, void* stream);
+
+/* Tile-blocked fp32 layout of the trunk's residual stream (private to this library: written by eb_tsa_modulate or a
+ * conv epilogue, read/updated in place by eb_conv2d epilogues).  Pixels are grouped exactly as the pixel-major conv
+ * epilogue owns them (16x16 tiles -> two 16x8 halves -> four 32-pixel quarters -> 32-channel chunks), so that every
+ * warp-level float4 access is 512 contiguous bytes.  Returns the number of floats to allocate for [N,H,W,C]. */
+size_t eb_f32_blocked_elems(int N, int H, int W, int C);
 
 /* ---- DCNv2 forward on NHWC fp16 input with packed fp16 offsets/mask (fused pipeline) ---- */
 int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
@@ -136,7 +143,8 @@ int eb_tsa_temporal(const void* emb, const void* emb_ref, const void* aligned, v
                     int H, int W, int C, void* stream);
 /* TSA output (edvr_arch.py:210-213): out = feat * sigmoid(attn) * 2 + attn_add; fp16 + fp32 copies */
 int eb_tsa_modulate(const void* feat, int feat_pix_stride, int feat_ch_off, const void* attn,
-                    const void* attn_add, void* out16, float* out32, int npix, int C, void* stream);
+                    const void* attn_add, void* out16, float* out32, int N, int H, int W, int C, int f32_blocked,
+                    void* stream);
 /* dst = a + b (NHWC fp16 views) */
 int eb_add(const void* a, int a_pix_stride, int a_ch_off, const void* b, int b_pix_stride,
            int b_ch_off, void* dst, int dst_pix_stride, int dst_ch_off, int npix, int C, void* stream);

@@ -139,6 +139,27 @@ def test_conv_fp32_residual_stream_and_dual_output(ops, conv_variant):
     assert rel_err(ops.nhwc_to_nchw(out16).cpu(), want.cpu())[0] < TOL
 
 
+def test_blocked_fp32_stream_roundtrip(ops):
+    """The trunk's private tile-blocked fp32 layout: written by tsa_modulate, updated in place by a conv epilogue,
+    un-blocked here with plain index math (ragged H, W exercise partial tiles)."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    N, C, H, W = 2, 128, 37, 21
+    feat, attn, add = (torch.randn(N, C, H, W, device="cuda", generator=g).half().float() for _ in range(3))
+    stream = ops.Blocked32(N, H, W, C)
+    o16 = ops.new_act(N, H, W, C)
+    ops.tsa_modulate(ops.nchw_to_nhwc(feat), ops.nchw_to_nhwc(attn), ops.nchw_to_nhwc(add), out16=o16, out32=stream)
+    want0 = feat * torch.sigmoid(attn) * 2 + add
+    assert rel_err(stream.to_nhwc().permute(0, 3, 1, 2).cpu(), want0.cpu())[0] < 1e-5
+    x = torch.randn(N, C, H, W, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, device="cuda", generator=g) / 34
+    b = torch.randn(C, device="cuda", generator=g) * 0.1
+    out16 = ops.new_act(N, H, W, C)
+    ops.conv2d(ops.pack_conv(w, b), [ops.nchw_to_nhwc(x)], out16=out16, out32=stream, res32=stream)
+    want = stream_ref = want0 + F.conv2d(x.half().double(), w.half().double(), b.double(), 1, 1).float()
+    assert rel_err(stream.to_nhwc().permute(0, 3, 1, 2).cpu(), want.cpu())[0] < 1e-5
+    assert rel_err(ops.nhwc_to_nchw(out16).cpu(), want.cpu())[0] < TOL
+
+
 def test_stride2_conv_matches_torch_stride2(ops):
     """OUT_STRIDE2 must equal a real stride-2/pad-1 conv (edvr_arch.py:329,331)."""
     x = torch.randn(2, 64, 26, 34, device="cuda")

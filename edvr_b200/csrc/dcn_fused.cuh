@@ -12,10 +12,9 @@
 // NHWC fp16 and/or NCHW fp32 stores).  K is walked chunk-major: stage = (64-channel chunk, tap), so the nine
 // taps of a chunk re-read the same ~23 KB slab of x and hit L1.
 // Gather mapping (L1TEX wavefronts and issue slots are the limiters of this kernel, profiles/r01_*): four lanes
-// read 64 contiguous bytes of ONE sampled pixel per load instruction (whole sectors, each fetched once); with
-// C/dg = 16 lane pairs split the sampling-geometry work of the two groups they touch and trade it by shuffle;
-// offsets of the next stage are prefetched while the current one is gathered; the fused fp16 pipeline blends
-// with packed HFMA2.
+// read the 128 contiguous bytes (64 channels) of ONE sampled pixel per corner, each lane 32 bytes = one
+// deformable group when C/dg = 16, so the sampling geometry is computed once per 16 channels; offsets of the next
+// stage are prefetched while the current one is gathered; the fused fp16 pipeline blends with packed HFMA2.
 //
 // Sampling semantics (bit-for-bit the reference's decisions, fp32 coordinate math):
 //   h_im = ho*stride - pad + i*dil + dh;  sample iff h_im > -1 && w_im > -1 && h_im < H && w_im < W
@@ -27,7 +26,7 @@
 namespace eb {
 
 constexpr int DC_STAGES = 4;             // 4 x 32 KB: leaves ~90 KB of the SM's L1 for the gather
-constexpr int DC_A_LBO = 128 * 16 + 32;  // plane pitch (+32 B: 4 atom-lanes x 2 pixels of a quarter-warp hit 8 distinct bank groups)
+constexpr int DC_A_LBO = 128 * 16 + 16;  // plane pitch (+16 B: the 8 kc-lanes of a pixel hit 8 different bank groups)
 constexpr int DC_A_BYTES = 8 * DC_A_LBO; // 8 planes x 128 rows x 16 B (+ pad)
 constexpr int DC_B_BYTES = 128 * 128;    // BN(<=128) rows x 64 ch x 2 B
 constexpr int DC_THREADS = 448;          // 14 warps
@@ -201,17 +200,14 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
         }
     } else {
         // ================= gather warps (256 threads): build the A operand of each stage.
-        // lane -> (pixel slot = lane/4, kp = lane%4); the lane owns channel atoms kp and kp+4 of its 2 pixels, so
-        // one load instruction covers 64 contiguous bytes per sampled pixel (whole 32-byte sectors, each fetched
-        // once).  With 16 channels per deformable group the two atoms belong to groups kp/2 and kp/2+2: lanes
-        // (2j, 2j+1) each compute the sampling geometry of ONE of them and trade it with a warp shuffle.
+        // lane -> (pixel slot = lane/4, channel-atom pair kp = lane%4 -> atoms 2kp, 2kp+1 = 32 contiguous bytes);
+        // a thread owns 2 pixels per stage.  The 4 lanes of a pixel cover one full 128-byte line per corner.
         // All kernel parameters used below are copied to registers first: with two gather warps per scheduler
         // every constant-bank load / integer division inside the stage loop is exposed latency.
         const int gw = warp - 6;                      // 0..7
-        const int kp = lane & 3;
+        const int kc0 = (lane & 3) * 2;
         const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo, strd = P.stride, pad = P.pad, dil = P.dil;
         const int kw = P.kw, cpg = P.cpg, dg = P.dg;
-        const bool share = cpg == 16;                 // pair-sharing fast path
         const float fH = static_cast<float>(H), fW = static_cast<float>(W);
         const long long xps = P.x_pix_stride, xrow = static_cast<long long>(W) * xps;
         const __half* const xview = P.x + P.x_ch_off;
@@ -261,18 +257,6 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             }
             return c;
         };
-        auto swap_with_partner = [&](const DcnCorner& c) -> DcnCorner {     // lane ^ 1 holds the other group's geometry
-            DcnCorner o;
-            unsigned long long b = reinterpret_cast<unsigned long long>(c.base);
-            b = __shfl_xor_sync(0xffffffffu, b, 1);
-            o.base = reinterpret_cast<const __half*>(b);
-            o.dW = c.dW;
-            o.dH = c.dH;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o.w[i] = __shfl_xor_sync(0xffffffffu, c.w[i], 1);
-            o.valid = __shfl_xor_sync(0xffffffffu, c.valid, 1);
-            return o;
-        };
 
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -292,37 +276,27 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                 px[i].ob = (OFFMODE == OFF_NCHW_F32) ? off_f + static_cast<long long>(img) * dg * 2 * K * plane + pix : nullptr;
                 px[i].mb = (OFFMODE == OFF_NCHW_F32) ? msk_f + static_cast<long long>(img) * dg * K * plane + pix : nullptr;
             }
-            // groups of this lane's two atoms in chunk 0; `gm` = the one this lane computes on the sharing path
-            int gA = (kp * 8) / cpg, gB = (kp * 8 + 32) / cpg;
             // software pipeline: the (dh, dw, mask) triples of the NEXT stage are fetched while this one is gathered
+            int g0 = (kc0 * 8) / cpg, g1 = (kc0 * 8 + 8) / cpg;
             DcnOff nxt[2][2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                if (share) {
-                    nxt[i][0] = fetch(px[i], (kp & 1) ? gB : gA, 0);
-                } else {
-                    nxt[i][0] = fetch(px[i], gA, 0);
-                    nxt[i][1] = fetch(px[i], gB, 0);
-                }
+                nxt[i][0] = fetch(px[i], g0, 0);
+                nxt[i][1] = (g1 != g0) ? fetch(px[i], g1, 0) : nxt[i][0];
             }
             for (int chunk = 0; chunk < nchunks; ++chunk) {
-                const int ch = chunk * 64 + kp * 8;               // channel of atom kp; atom kp+4 is 32 channels later
-                const int ngA = (ch + 64) / cpg, ngB = (ch + 96) / cpg;
+                const int ch = chunk * 64 + kc0 * 8;
+                const bool two = g1 != g0;                     // cpg == 8: the two atoms belong to different groups
+                const int chn = ch + 64;
+                const int ng0 = (chunk + 1 < nchunks) ? chn / cpg : g0, ng1 = (chunk + 1 < nchunks) ? (chn + 8) / cpg : g1;
                 int ki = 0, kj = 0;
                 for (int tap = 0; tap < K; ++tap, ++it) {
                     const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
                     DcnCorner cn[2][2];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        if (share) {
-                            const DcnCorner mine = corner(px[i], ximg, ki, kj, nxt[i][0]);
-                            const DcnCorner other = swap_with_partner(mine);
-                            cn[i][0] = (kp & 1) ? other : mine;          // geometry of group gA (atom kp)
-                            cn[i][1] = (kp & 1) ? mine : other;          // geometry of group gB (atom kp+4)
-                        } else {
-                            cn[i][0] = corner(px[i], ximg, ki, kj, nxt[i][0]);
-                            cn[i][1] = corner(px[i], ximg, ki, kj, nxt[i][1]);
-                        }
+                        cn[i][0] = corner(px[i], ximg, ki, kj, nxt[i][0]);
+                        cn[i][1] = two ? corner(px[i], ximg, ki, kj, nxt[i][1]) : cn[i][0];
                     }
                     // all 16 corner loads in flight before anything is consumed
                     uint4 u[2][2][4];
@@ -331,7 +305,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
 #pragma unroll
                         for (int a = 0; a < 2; ++a) {
                             const DcnCorner& c = cn[i][a];
-                            const __half* b = c.base + ch + a * 32;
+                            const __half* b = c.base + ch + a * 8;
                             u[i][a][0] = u[i][a][1] = u[i][a][2] = u[i][a][3] = make_uint4(0, 0, 0, 0);
                             if (c.valid & 1u) u[i][a][0] = ldg_nc_v4(b);
                             if (c.valid & 2u) u[i][a][1] = ldg_nc_v4(b + c.dW);
@@ -342,23 +316,19 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                     {
                         const bool last_tap = tap + 1 == K;
                         const int t1 = last_tap ? 0 : tap + 1;
-                        const int hA = last_tap ? ngA : gA, hB = last_tap ? ngB : gB;
+                        const int h0 = last_tap ? ng0 : g0, h1 = last_tap ? ng1 : g1;
                         if (!(last_tap && chunk + 1 == nchunks)) {
 #pragma unroll
                             for (int i = 0; i < 2; ++i) {
-                                if (share) {
-                                    nxt[i][0] = fetch(px[i], (kp & 1) ? hB : hA, t1);
-                                } else {
-                                    nxt[i][0] = fetch(px[i], hA, t1);
-                                    nxt[i][1] = fetch(px[i], hB, t1);
-                                }
+                                nxt[i][0] = fetch(px[i], h0, t1);
+                                nxt[i][1] = (h1 != h0) ? fetch(px[i], h1, t1) : nxt[i][0];
                             }
                         }
                     }
                     if (++kj == kw) { kj = 0; ++ki; }
                     // the smem slot is needed only now
                     mbar_wait_warp(&empty[s], ph ^ 1u);
-                    const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + kp * DC_A_LBO;
+                    const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + kc0 * DC_A_LBO;
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -375,14 +345,14 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                                 r = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]),
                                                pack_h2(acc[6], acc[7]));
                             }
-                            sts_v4(dst + a * 4 * DC_A_LBO + px[i].m * 16, r);
+                            sts_v4(dst + a * DC_A_LBO + px[i].m * 16, r);
                         }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full[s]);
                 }
-                gA = ngA;
-                gB = ngB;
+                g0 = ng0;
+                g1 = ng1;
             }
         }
     }

@@ -106,3 +106,42 @@ def test_drop_in_modules_state_dict_and_forward():
     assert float((y - ref).abs().max() / ref.abs().max()) < 5e-3
     with pytest.raises(AssertionError, match="multiple of 4"):
         net(torch.rand(1, 3, 3, 18, 24).cuda())
+
+
+def test_training_step_gradients_vs_oracle_graph():
+    """BASELINE cfg 5 (reduced): one Charbonnier-loss training step through the drop-in modules with autograd ON.
+    The graph runs differentiable PyTorch ops around OUR DCN forward + backward kernels (edvr_b200.dcn); gradients
+    are compared with the oracle graph differentiated through torchvision's deform_conv2d (fp32, TF32 off).
+    Offsets are kept away from the -1 edge by the random conv_offset init."""
+    from edvr_b200.edvr import EDVR
+    from oracle import edvr_ref
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    kw = dict(num_feat=64, num_frame=3, deformable_groups=8, num_extract_block=1, num_reconstruct_block=2)
+    sd = edvr_ref.make_state_dict(**kw, seed=7)
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(2, 3, 3, 16, 16, generator=g).cuda()
+    gt = torch.rand(2, 3, 64, 64, generator=g).cuda()
+
+    def charbonnier(p, t):       # losses.py:24-25 with reduction='sum' (train_EDVR_L_x4_SR_REDS.yml:90-93)
+        return torch.sqrt((p - t) ** 2 + 1e-12).sum()
+
+    net = EDVR(center_frame_idx=None, **kw).cuda().train()
+    net.load_state_dict(sd, strict=True)
+    loss = charbonnier(net(x), gt)
+    loss.backward()
+
+    ref_params = {k: v.clone().cuda().requires_grad_(True) for k, v in sd.items()}
+    with torch.enable_grad():
+        out_ref = edvr_ref.edvr_forward.__wrapped__(ref_params, x)      # un-decorated (no_grad) forward
+        loss_ref = charbonnier(out_ref, gt)
+    loss_ref.backward()
+    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 1e-3
+    named = dict(net.named_parameters())
+    for key in ("conv_first.weight", "pcd_align.dcn_pack.l1.weight", "pcd_align.dcn_pack.l1.conv_offset.weight",
+                "pcd_align.cas_dcnpack.bias", "fusion.feat_fusion.weight", "reconstruction.1.conv2.weight",
+                "conv_last.weight"):
+        a, b = named[key].grad, ref_params[key].grad
+        err = float((a - b).norm() / b.norm().clamp_min(1e-20))
+        print(f"grad {key}: rel-L2 {err:.2e}")
+        assert err < 2e-2, (key, err)

@@ -307,7 +307,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips", type=int, default=8, help="clips per GPU per step")
+    ap.add_argument("--clips", type=int, default=4, help="clips per GPU per step (8 runs into the 1 kW power cap)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -136,7 +136,7 @@ def test_training_step_gradients_vs_oracle_graph():
         out_ref = edvr_ref.edvr_forward.__wrapped__(ref_params, x)      # un-decorated (no_grad) forward
         loss_ref = charbonnier(out_ref, gt)
     loss_ref.backward()
-    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 1e-3
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 1e-3
     named = dict(net.named_parameters())
     for key in ("conv_first.weight", "pcd_align.dcn_pack.l1.weight", "pcd_align.dcn_pack.l1.conv_offset.weight",
                 "pcd_align.cas_dcnpack.bias", "fusion.feat_fusion.weight", "reconstruction.1.conv2.weight",

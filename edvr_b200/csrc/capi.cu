@@ -205,16 +205,31 @@ static int launch_conv(const ConvParams& P, cudaStream_t st) {
     int ek1 = EK_GENERIC;
     {
         const EpiParams& e = P.epi;
-        if (e.out_mode == OUT_SAME && e.act != ACT_DCN_PACK && e.out16 && !e.out32 && !e.res32 && !e.out_nchw) ek1 = EK_PLAIN;
-        else if (e.out_mode == OUT_SAME && e.act != ACT_DCN_PACK && (e.out32 || e.res32) && !e.res16 && !e.out_nchw) ek1 = EK_F32;
+        const bool plain_out = e.out16 && !e.out32 && !e.res32 && !e.out_nchw;
+        if (e.out_mode == OUT_PIXSHUF2) ek1 = EK_PIXSHUF;
+        else if (e.out_mode == OUT_STRIDE2) ek1 = EK_STRIDE2;
+        else if (e.act == ACT_DCN_PACK) { if (plain_out && !e.res16) ek1 = EK_PACK; }
+        else if (plain_out) ek1 = EK_PLAIN;
+        else if ((e.out32 || e.res32) && !e.res16 && !e.out_nchw) ek1 = EK_F32;
     }
 #define EB_LAUNCH_C1(HALO_, EK_)                                                                       \
     do {                                                                                               \
         if (int rc = set_smem(conv_igemm_kernel<HALO_, EK_>, CV_SMEM_BYTES)) return rc;                \
         conv_igemm_kernel<HALO_, EK_><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);                     \
     } while (0)
-    if (P.taps == 9) { if (ek1 == EK_PLAIN) EB_LAUNCH_C1(1, EK_PLAIN); else if (ek1 == EK_F32) EB_LAUNCH_C1(1, EK_F32); else EB_LAUNCH_C1(1, EK_GENERIC); }
-    else             { if (ek1 == EK_PLAIN) EB_LAUNCH_C1(0, EK_PLAIN); else if (ek1 == EK_F32) EB_LAUNCH_C1(0, EK_F32); else EB_LAUNCH_C1(0, EK_GENERIC); }
+#define EB_DISPATCH_C1(HALO_)                                                                          \
+    do {                                                                                               \
+        switch (ek1) {                                                                                 \
+            case EK_PLAIN: EB_LAUNCH_C1(HALO_, EK_PLAIN); break;                                       \
+            case EK_F32: EB_LAUNCH_C1(HALO_, EK_F32); break;                                           \
+            case EK_PACK: EB_LAUNCH_C1(HALO_, EK_PACK); break;                                         \
+            case EK_PIXSHUF: EB_LAUNCH_C1(HALO_, EK_PIXSHUF); break;                                   \
+            case EK_STRIDE2: EB_LAUNCH_C1(HALO_, EK_STRIDE2); break;                                   \
+            default: EB_LAUNCH_C1(HALO_, EK_GENERIC); break;                                           \
+        }                                                                                              \
+    } while (0)
+    if (P.taps == 9) EB_DISPATCH_C1(1); else EB_DISPATCH_C1(0);
+#undef EB_DISPATCH_C1
 #undef EB_LAUNCH_C1
     return check_launch("conv_igemm");
 }

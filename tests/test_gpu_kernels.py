@@ -398,3 +398,56 @@ def test_b1_extension_shim_signature_and_inplace_semantics(ops, golden_dir):
                                           t["mask"].cpu(), out.cpu(), e, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, True)
     with pytest.raises(NotImplementedError):
         ext.deform_conv_forward()
+
+
+# ---------------------------------------------------------------- full-size, size-independent properties
+def test_dcn_full_size_zero_offset_unit_mask_equals_dense_conv(ops):
+    """BASELINE L1 size (1x128x180x320): with zero offsets and mask == 1 the DCN is a plain 3x3 convolution
+    (deform_conv_cuda_kernel.cu:608-628 with dh = dw = 0) - checked against fp32 cuDNN and against our own dense kernel."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    N, C, H, W, dg = 1, 128, 180, 320, 8
+    x = torch.randn(N, C, H, W, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, device="cuda", generator=g) / 34
+    b = torch.randn(C, device="cuda", generator=g) * 0.1
+    off = torch.zeros(N, dg * 18, H, W, device="cuda")
+    mask = torch.ones(N, dg * 9, H, W, device="cuda")
+    y = ops.mdcn_forward(x, off, mask, w, b, 1, 1, 1, 1, dg)
+    torch.backends.cudnn.allow_tf32 = False
+    want = F.conv2d(x.half().float(), w.half().float(), b, padding=1)
+    e = rel_err(y.cpu(), want.cpu())
+    assert e[0] < TOL and e[1] < TOL, e
+    dense = ops.new_act(N, H, W, C)
+    ops.conv2d(ops.pack_conv(w, b), [ops.nchw_to_nhwc(x)], out16=dense)
+    assert rel_err(ops.nhwc_to_nchw(dense).cpu(), y.cpu())[0] < TOL
+
+
+def test_dcn_full_size_linearity_and_determinism(ops):
+    """At the L1 size: linear in x (and in the weights) for fixed offsets/mask, and bit-identical across runs
+    (no atomics in the forward path)."""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    N, C, H, W, dg = 1, 128, 180, 320, 8
+    x1, x2 = (torch.randn(N, C, H, W, device="cuda", generator=g).half().float() for _ in range(2))
+    off = torch.randn(N, dg * 18, H, W, device="cuda", generator=g) * 3
+    mask = torch.sigmoid(torch.randn(N, dg * 9, H, W, device="cuda", generator=g))
+    w = torch.randn(C, C, 3, 3, device="cuda", generator=g) / 34
+    f = lambda xx, ww: ops.mdcn_forward(xx, off, mask, ww, None, 1, 1, 1, 1, dg)
+    y1, y2, y12 = f(x1, w), f(x2, w), f(x1 + x2, w)
+    assert rel_err((y1 + y2).cpu(), y12.cpu())[0] < 2e-3
+    assert rel_err((2 * y1).cpu(), f(x1, 2 * w).cpu())[0] < 1e-6        # exact power-of-two scaling
+    assert torch.equal(f(x1, w), y1)
+
+
+def test_edvr_full_size_shape_determinism_and_batch_consistency():
+    """cfg 3 at full size (7x3x180x320 -> 720x1280): output shape, run-to-run bit equality, and every clip of a
+    batch equals the same clip run alone (clips are independent units)."""
+    from edvr_b200.engine import EDVREngine
+    from oracle import edvr_ref
+    sd = edvr_ref.make_state_dict(num_feat=128, num_frame=7, num_reconstruct_block=40, seed=0)
+    eng = EDVREngine(sd, num_frame=7)
+    x = torch.rand(2, 7, 3, 180, 320, generator=torch.Generator().manual_seed(0)).cuda()
+    y = eng.forward(x).clone()
+    assert y.shape == (2, 3, 720, 1280) and torch.isfinite(y).all()
+    assert torch.equal(eng.forward(x), y)
+    y0 = eng.forward(x[:1].contiguous())
+    assert torch.equal(y0[0], y[0])
+    assert float(eng.offset_absmeans().max()) < 50

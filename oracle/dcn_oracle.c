@@ -20,7 +20,7 @@
  * deform_conv2d (forward, grad_input, grad_mask, grad_weight, grad_bias everywhere;
  * grad_offset away from the exact -1 coordinate, where the reference returns 0 and
  * torchvision does not) and against tests/golden/dcn_ref_cuda_*.npz, produced by the
- * UNMODIFIED reference CUDA extension on a B200 (oracle/make_golden_ref_cuda.py).
+ * UNMODIFIED reference CUDA extension on a B200 (tools/first_light.py, section refext).
  *
  * The arithmetic is fp32 at the interface with fp64 accumulation inside the
  * contractions, so the oracle is at least as accurate as the reference's SGEMM.
@@ -33,15 +33,15 @@
 typedef struct {
     int N, C, H, W;          /* input  [N,C,H,W]                          */
     int Cout, kh, kw;        /* weight [Cout, C/groups, kh, kw]            */
-    int stride, pad, dil;    /* v2 API uses one int for both axes          */
+    int sh, sw, ph, pw, dh, dw; /* stride / pad / dilation per axis (v2 passes equal pairs) */
     int groups, dg;          /* weight groups, deformable groups           */
     int Ho, Wo;              /* derived                                    */
 } dcn_shape;
 
 static void derive(dcn_shape *s)
 {
-    s->Ho = (s->H + 2 * s->pad - (s->dil * (s->kh - 1) + 1)) / s->stride + 1;
-    s->Wo = (s->W + 2 * s->pad - (s->dil * (s->kw - 1) + 1)) / s->stride + 1;
+    s->Ho = (s->H + 2 * s->ph - (s->dh * (s->kh - 1) + 1)) / s->sh + 1;
+    s->Wo = (s->W + 2 * s->pw - (s->dw * (s->kw - 1) + 1)) / s->sw + 1;
 }
 
 /* kernel.cu:467-497 — corners outside [0,H-1]x[0,W-1] contribute zero */
@@ -101,7 +101,7 @@ static void im2col_sample(const dcn_shape *s, const float *x, const float *off,
         const int g = c / cpg;
         const float *im = x + (size_t)c * s->H * s->W;
         const float *og = off + (size_t)g * 2 * K * HW;
-        const float *mg = msk + (size_t)g * K * HW;
+        const float *mg = msk ? msk + (size_t)g * K * HW : NULL;   /* NULL: DCNv1 (no modulation) */
         for (int ho = 0; ho < s->Ho; ++ho)
             for (int wo = 0; wo < s->Wo; ++wo) {
                 const int p = ho * s->Wo + wo;
@@ -110,9 +110,9 @@ static void im2col_sample(const dcn_shape *s, const float *x, const float *off,
                         const int k = i * s->kw + j;
                         const float dh = og[(size_t)(2 * k) * HW + p];
                         const float dw = og[(size_t)(2 * k + 1) * HW + p];
-                        const float m = mg[(size_t)k * HW + p];
-                        const float h_im = ho * s->stride - s->pad + i * s->dil + dh;
-                        const float w_im = wo * s->stride - s->pad + j * s->dil + dw;
+                        const float m = mg ? mg[(size_t)k * HW + p] : 1.0f;
+                        const float h_im = ho * s->sh - s->ph + i * s->dh + dh;
+                        const float w_im = wo * s->sw - s->pw + j * s->dw + dw;
                         float v = 0;
                         if (h_im > -1 && w_im > -1 && h_im < s->H && w_im < s->W)
                             v = bilinear(im, s->H, s->W, h_im, w_im);
@@ -123,14 +123,16 @@ static void im2col_sample(const dcn_shape *s, const float *x, const float *off,
 }
 
 /* returns 0 on success, negative on invalid arguments */
-int dcn_oracle_forward(const float *x, const float *offset, const float *mask,
-                       const float *weight, const float *bias /* may be NULL */,
-                       float *out, int N, int C, int H, int W, int Cout, int kh,
-                       int kw, int stride, int pad, int dil, int groups, int dg)
+/* General form: per-axis stride/pad/dilation, mask may be NULL (== DCNv1,
+ * deform_conv_cuda_kernel.cu:190-243 — same sampling rule without the modulation). */
+int dcn_oracle_forward_ex(const float *x, const float *offset, const float *mask,
+                          const float *weight, const float *bias /* may be NULL */,
+                          float *out, int N, int C, int H, int W, int Cout, int kh,
+                          int kw, int sh, int sw, int ph, int pw, int dh, int dw, int groups, int dg)
 {
-    dcn_shape s = {N, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg, 0, 0};
+    dcn_shape s = {N, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, groups, dg, 0, 0};
     if (N < 0 || C <= 0 || Cout <= 0 || groups <= 0 || dg <= 0 || C % groups ||
-        Cout % groups || C % dg || stride <= 0)
+        Cout % groups || C % dg || sh <= 0 || sw <= 0)
         return -1;
     derive(&s);
     if (s.Ho <= 0 || s.Wo <= 0) return -2;
@@ -140,7 +142,7 @@ int dcn_oracle_forward(const float *x, const float *offset, const float *mask,
     if (!col) return -3;
     for (int n = 0; n < N; ++n) {
         im2col_sample(&s, x + (size_t)n * C * H * W, offset + (size_t)n * dg * 2 * K * HW,
-                      mask + (size_t)n * dg * K * HW, col);
+                      mask ? mask + (size_t)n * dg * K * HW : NULL, col);
         /* deform_conv_cuda.cpp:550-568: out[n][g] = W[g].flatten(1) @ col[g] + bias */
 #pragma omp parallel for schedule(static)
         for (int co = 0; co < Cout; ++co) {
@@ -162,18 +164,30 @@ int dcn_oracle_forward(const float *x, const float *offset, const float *mask,
     return 0;
 }
 
-/* grad_weight / grad_bias are ACCUMULATED into (caller zero-fills), like
- * deform_conv_cuda.cpp:659-671; the other three grads are overwritten. */
-int dcn_oracle_backward(const float *x, const float *offset, const float *mask,
-                        const float *weight, const float *grad_out, float *grad_x,
-                        float *grad_offset, float *grad_mask, float *grad_weight,
-                        float *grad_bias /* may be NULL */, int N, int C, int H, int W,
-                        int Cout, int kh, int kw, int stride, int pad, int dil,
-                        int groups, int dg)
+int dcn_oracle_forward(const float *x, const float *offset, const float *mask,
+                       const float *weight, const float *bias, float *out, int N, int C, int H,
+                       int W, int Cout, int kh, int kw, int stride, int pad, int dil, int groups, int dg)
 {
-    dcn_shape s = {N, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg, 0, 0};
+    return dcn_oracle_forward_ex(x, offset, mask, weight, bias, out, N, C, H, W, Cout, kh, kw, stride,
+                                 stride, pad, pad, dil, dil, groups, dg);
+}
+
+/* grad_weight / grad_bias are ACCUMULATED into (caller zero-fills), like
+ * deform_conv_cuda.cpp:659-671; the other three grads are overwritten.
+ * mask == NULL: DCNv1 backward (deform_conv_cuda_kernel.cu:279-436, deform_conv_cuda.cpp:239-488);
+ * grad_mask is then ignored.  grad_weight contributions are multiplied by `scale`
+ * (deform_conv_backward_parameters, deform_conv_cuda.cpp:471-478). */
+int dcn_oracle_backward_ex(const float *x, const float *offset, const float *mask,
+                           const float *weight, const float *grad_out, float *grad_x,
+                           float *grad_offset, float *grad_mask, float *grad_weight,
+                           float *grad_bias /* may be NULL */, float scale, int N, int C, int H, int W,
+                           int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh_, int dw_,
+                           int groups, int dg)
+{
+    dcn_shape s = {N, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh_, dw_, groups, dg, 0, 0};
+    const int stride_h = sh, stride_w = sw, pad_h = ph, pad_w = pw, dil_h = dh_, dil_w = dw_;
     if (N < 0 || C <= 0 || Cout <= 0 || groups <= 0 || dg <= 0 || C % groups ||
-        Cout % groups || C % dg || stride <= 0)
+        Cout % groups || C % dg || sh <= 0 || sw <= 0)
         return -1;
     derive(&s);
     if (s.Ho <= 0 || s.Wo <= 0) return -2;
@@ -187,11 +201,11 @@ int dcn_oracle_backward(const float *x, const float *offset, const float *mask,
     for (int n = 0; n < N; ++n) {
         const float *xn = x + (size_t)n * C * H * W;
         const float *on = offset + (size_t)n * dg * 2 * K * HW;
-        const float *mn = mask + (size_t)n * dg * K * HW;
+        const float *mn = mask ? mask + (size_t)n * dg * K * HW : NULL;
         const float *gon = grad_out + (size_t)n * Cout * HW;
         float *gxn = grad_x + (size_t)n * C * H * W;
         float *goffn = grad_offset + (size_t)n * dg * 2 * K * HW;
-        float *gmn = grad_mask + (size_t)n * dg * K * HW;
+        float *gmn = (mask && grad_mask) ? grad_mask + (size_t)n * dg * K * HW : NULL;
 
         /* gcol = W^T · grad_out   (deform_conv_cuda.cpp:623-626) */
 #pragma omp parallel for schedule(static)
@@ -220,9 +234,9 @@ int dcn_oracle_backward(const float *x, const float *offset, const float *mask,
                     const int p = ho * s.Wo + wo;
                     const float dh = on[((size_t)g * 2 * K + 2 * k) * HW + p];
                     const float dw = on[((size_t)g * 2 * K + 2 * k + 1) * HW + p];
-                    const float m = mn[((size_t)g * K + k) * HW + p];
-                    float ih = ho * stride - pad + i * dil + dh;
-                    float iw = wo * stride - pad + j * dil + dw;
+                    const float m = mn ? mn[((size_t)g * K + k) * HW + p] : 1.0f;
+                    float ih = ho * stride_h - pad_h + i * dil_h + dh;
+                    float iw = wo * stride_w - pad_w + j * dil_w + dw;
                     const int outside = (ih <= -1 || iw <= -1 || ih >= H || iw >= W);
                     if (outside) ih = iw = -2; /* kernel.cu:747-750 sentinel */
                     double val = 0, mval = 0;
@@ -234,7 +248,7 @@ int dcn_oracle_backward(const float *x, const float *offset, const float *mask,
                         val += (double)coord_weight(ih, iw, H, W, im, dir) * gc * m;
                     }
                     goffn[(size_t)oc * HW + p] = (float)val;
-                    if (dir == 0) gmn[((size_t)g * K + k) * HW + p] = (float)mval;
+                    if (dir == 0 && gmn) gmn[((size_t)g * K + k) * HW + p] = (float)mval;
                 }
         }
 
@@ -250,9 +264,9 @@ int dcn_oracle_backward(const float *x, const float *offset, const float *mask,
                         const int p = ho * s.Wo + wo;
                         const float dh = on[((size_t)g * 2 * K + 2 * k) * HW + p];
                         const float dw = on[((size_t)g * 2 * K + 2 * k + 1) * HW + p];
-                        const float m = mn[((size_t)g * K + k) * HW + p];
-                        const float ih = ho * stride - pad + i * dil + dh;
-                        const float iw = wo * stride - pad + j * dil + dw;
+                        const float m = mn ? mn[((size_t)g * K + k) * HW + p] : 1.0f;
+                        const float ih = ho * stride_h - pad_h + i * dil_h + dh;
+                        const float iw = wo * stride_w - pad_w + j * dil_w + dw;
                         const float top = gcol[((size_t)c * K + k) * HW + p] * m;
                         const int ch = (int)ih, cw = (int)iw; /* truncation, :675-676 */
                         for (int dy = -2; dy <= 2; ++dy)
@@ -278,7 +292,7 @@ int dcn_oracle_backward(const float *x, const float *offset, const float *mask,
                 const float *crow = col + ((size_t)g * cg * K + r) * HW;
                 double acc = 0;
                 for (int p = 0; p < HW; ++p) acc += (double)grow[p] * crow[p];
-                grad_weight[(size_t)co * cg * K + r] += (float)acc;
+                grad_weight[(size_t)co * cg * K + r] += (float)(acc * scale);
             }
             if (grad_bias) {
                 double acc = 0;
@@ -290,4 +304,15 @@ int dcn_oracle_backward(const float *x, const float *offset, const float *mask,
     free(col);
     free(gcol);
     return 0;
+}
+
+int dcn_oracle_backward(const float *x, const float *offset, const float *mask,
+                        const float *weight, const float *grad_out, float *grad_x,
+                        float *grad_offset, float *grad_mask, float *grad_weight, float *grad_bias,
+                        int N, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad,
+                        int dil, int groups, int dg)
+{
+    return dcn_oracle_backward_ex(x, offset, mask, weight, grad_out, grad_x, grad_offset, grad_mask,
+                                  grad_weight, grad_bias, 1.0f, N, C, H, W, Cout, kh, kw, stride, stride,
+                                  pad, pad, dil, dil, groups, dg);
 }

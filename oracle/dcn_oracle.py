@@ -32,6 +32,10 @@ def _lib():
         _LIB.dcn_oracle_forward.restype = ctypes.c_int
         _LIB.dcn_oracle_backward.argtypes = [fp] * 10 + [ctypes.c_int] * 12
         _LIB.dcn_oracle_backward.restype = ctypes.c_int
+        _LIB.dcn_oracle_forward_ex.argtypes = [fp] * 6 + [ctypes.c_int] * 15
+        _LIB.dcn_oracle_forward_ex.restype = ctypes.c_int
+        _LIB.dcn_oracle_backward_ex.argtypes = [fp] * 10 + [ctypes.c_float] + [ctypes.c_int] * 15
+        _LIB.dcn_oracle_backward_ex.restype = ctypes.c_int
     return _LIB
 
 
@@ -83,3 +87,39 @@ def backward(x, offset, mask, weight, grad_out, with_bias=True, stride=1, paddin
     if rc != 0:
         raise ValueError(f"dcn_oracle_backward rc={rc}")
     return gx, goff, gmask, gw, gb
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def forward_v1(x, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1):
+    """DCNv1 (no modulation, no bias) — reference op ``deform_conv`` (deform_conv.py:12-57), per-axis parameters."""
+    x, offset, weight = map(_c, (x, offset, weight))
+    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
+    N, C, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    out = np.empty((N, Cout, Ho, Wo), np.float32)
+    rc = _lib().dcn_oracle_forward_ex(_p(x), _p(offset), _p(None), _p(weight), _p(None), _p(out), N, C, H, W, Cout,
+                                      kh, kw, sh, sw, ph, pw, dh, dw, groups, deformable_groups)
+    if rc != 0:
+        raise ValueError(f"dcn_oracle_forward_ex rc={rc}")
+    return out
+
+
+def backward_v1(x, offset, weight, grad_out, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
+                scale=1.0):
+    """Returns (grad_x, grad_offset, grad_weight) of DCNv1."""
+    x, offset, weight, grad_out = map(_c, (x, offset, weight, grad_out))
+    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
+    N, C, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    gx, goff, gw = np.zeros_like(x), np.zeros_like(offset), np.zeros_like(weight)
+    rc = _lib().dcn_oracle_backward_ex(_p(x), _p(offset), _p(None), _p(weight), _p(grad_out), _p(gx), _p(goff),
+                                       _p(None), _p(gw), _p(None), ctypes.c_float(scale), N, C, H, W, Cout, kh, kw,
+                                       sh, sw, ph, pw, dh, dw, groups, deformable_groups)
+    if rc != 0:
+        raise ValueError(f"dcn_oracle_backward_ex rc={rc}")
+    return gx, goff, gw

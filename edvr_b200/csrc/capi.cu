@@ -306,7 +306,8 @@ int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int
     memset(&P, 0, sizeof(P));
     P.x = static_cast<const __half*>(x); P.x_pix_stride = x_pix_stride; P.x_ch_off = x_ch_off;
     P.N = N; P.H = H; P.W = W; P.C = C; P.Ho = H; P.Wo = W;
-    P.kh = 3; P.kw = 3; P.stride = 1; P.pad = 1; P.dil = 1; P.dg = dg; P.cpg = C / dg;
+    P.kh = 3; P.kw = 3; P.stride = 1; P.pad = 1; P.dil = 1; P.stride_w = 1; P.pad_w = 1; P.dil_w = 1;
+    P.dg = dg; P.cpg = C / dg;
     P.off_mode = OFF_PACK_F16;
     P.offpack = static_cast<const __half*>(offpack); P.offpack_pix_stride = offpack_pix_stride;
     P.wpack = static_cast<const __half*>(wpack); P.BN = BN; P.n_tiles_n = n_tiles_n;
@@ -330,26 +331,27 @@ size_t eb_mdcn_forward_workspace(int N, int C, int H, int W, int Cout, int kh, i
            up256(static_cast<size_t>(BN) * nt * 4);
 }
 
-int eb_mdcn_forward(const float* x, const float* offset, const float* mask, const float* weight,
-                    const float* bias, float* out, int N, int C, int H, int W, int Cout, int kh, int kw,
-                    int stride, int pad, int dil, int groups, int dg, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+namespace {
+struct Geo2 { int sh, sw, ph, pw, dh, dw; };
+
+// Shared implementation of the reference-layout forward: mask == NULL and bias == NULL give DCNv1.
+int dcn_forward_impl(const char* who, const float* x, const float* offset, const float* mask, const float* weight,
+                     const float* bias, float* out, int N, int C, int H, int W, int Cout, int kh, int kw, Geo2 g,
+                     int groups, int dg, void* workspace, size_t workspace_bytes, void* stream, bool need_mask) {
     if (N == 0 && C > 0 && H > 0 && W > 0 && Cout > 0) return EB_OK;   // empty batch: nothing to do, pointers may be NULL
-    if (!x || !offset || !mask || !weight || !out) return fail(EB_ERR_NULLPTR, "mdcn_forward: null pointer");
-    if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || stride < 1 || pad < 0 || dil < 1 ||
-        groups < 1 || dg < 1 || C % dg || C % groups || Cout % groups)
-        return fail(EB_ERR_INVALID_SHAPE, "mdcn_forward: invalid shape");
-    if (groups != 1) return fail(EB_ERR_UNSUPPORTED, "mdcn_forward: groups=%d (only 1; EDVR uses 1)", groups);
-    if (C % 64 || (C / dg) % 8) return fail(EB_ERR_UNSUPPORTED, "mdcn_forward: C=%d dg=%d (C %% 64 == 0, (C/dg) %% 8 == 0)", C, dg);
-    if (Cout > DC_MAX_COUT) return fail(EB_ERR_UNSUPPORTED, "mdcn_forward: Cout=%d > %d", Cout, DC_MAX_COUT);
-    const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
-    const int Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
-    if (Ho < 1 || Wo < 1) return fail(EB_ERR_INVALID_SHAPE, "mdcn_forward: empty output");
-    if (workspace_bytes < eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw) || (!workspace && N > 0))
-        return fail(EB_ERR_WORKSPACE, "mdcn_forward: workspace %zu < %zu", workspace_bytes,
-                    eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw));
-    if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "mdcn_forward: workspace must be 16-byte aligned");
-    if (N == 0) return EB_OK;
+    if (!x || !offset || (need_mask && !mask) || !weight || !out) return fail(EB_ERR_NULLPTR, "%s: null pointer", who);
+    if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || g.sh < 1 || g.sw < 1 || g.ph < 0 || g.pw < 0 ||
+        g.dh < 1 || g.dw < 1 || groups < 1 || dg < 1 || C % dg || C % groups || Cout % groups)
+        return fail(EB_ERR_INVALID_SHAPE, "%s: invalid shape", who);
+    if (groups != 1) return fail(EB_ERR_UNSUPPORTED, "%s: groups=%d (only 1; EDVR uses 1)", who, groups);
+    if (C % 64 || (C / dg) % 8) return fail(EB_ERR_UNSUPPORTED, "%s: C=%d dg=%d (C %% 64 == 0, (C/dg) %% 8 == 0)", who, C, dg);
+    if (Cout > DC_MAX_COUT) return fail(EB_ERR_UNSUPPORTED, "%s: Cout=%d > %d", who, Cout, DC_MAX_COUT);
+    const int Ho = (H + 2 * g.ph - (g.dh * (kh - 1) + 1)) / g.sh + 1;
+    const int Wo = (W + 2 * g.pw - (g.dw * (kw - 1) + 1)) / g.sw + 1;
+    if (Ho < 1 || Wo < 1) return fail(EB_ERR_INVALID_SHAPE, "%s: empty output", who);
+    const size_t need = eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw);
+    if (workspace_bytes < need || !workspace) return fail(EB_ERR_WORKSPACE, "%s: workspace %zu < %zu", who, workspace_bytes, need);
+    if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "%s: workspace must be 16-byte aligned", who);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int BN;
     const int nt = cout_tiles(Cout, &BN);
@@ -359,7 +361,6 @@ int eb_mdcn_forward(const float* x, const float* offset, const float* mask, cons
     __half* wpack = reinterpret_cast<__half*>(ws);
     ws += up256(eb_packed_weight_bytes(C, kh * kw, BN, nt));
     float* bpack = reinterpret_cast<float*>(ws);
-
     {
         dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
         nchw_f32_to_nhwc_f16_kernel<<<grid, block, 0, st>>>(x, x16, C, H * W, C, 0);
@@ -373,12 +374,31 @@ int eb_mdcn_forward(const float* x, const float* offset, const float* mask, cons
     memset(&P, 0, sizeof(P));
     P.x = x16; P.x_pix_stride = C; P.x_ch_off = 0;
     P.N = N; P.H = H; P.W = W; P.C = C; P.Ho = Ho; P.Wo = Wo;
-    P.kh = kh; P.kw = kw; P.stride = stride; P.pad = pad; P.dil = dil; P.dg = dg; P.cpg = C / dg;
+    P.kh = kh; P.kw = kw; P.stride = g.sh; P.pad = g.ph; P.dil = g.dh; P.stride_w = g.sw; P.pad_w = g.pw; P.dil_w = g.dw;
+    P.dg = dg; P.cpg = C / dg;
     P.off_mode = OFF_NCHW_F32; P.offset = offset; P.mask = mask;
     P.wpack = wpack; P.BN = BN; P.n_tiles_n = nt;
-    P.epi.bias = bpack; P.epi.act = ACT_NONE; P.epi.H = Ho; P.epi.W = Wo;
+    P.epi.bias = bias ? bpack : nullptr; P.epi.act = ACT_NONE; P.epi.H = Ho; P.epi.W = Wo;
     P.epi.out_nchw = out; P.epi.nchw_C = Cout; P.epi.out_mode = OUT_SAME;
     return launch_dcn(P, st);
+}
+}  // namespace
+
+int eb_mdcn_forward(const float* x, const float* offset, const float* mask, const float* weight,
+                    const float* bias, float* out, int N, int C, int H, int W, int Cout, int kh, int kw,
+                    int stride, int pad, int dil, int groups, int dg, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    return dcn_forward_impl("mdcn_forward", x, offset, mask, weight, bias, out, N, C, H, W, Cout, kh, kw,
+                            Geo2{stride, stride, pad, pad, dil, dil}, groups, dg, workspace, workspace_bytes, stream, true);
+}
+
+/* DCNv1: deform_conv_forward of the reference extension (deform_conv_ext.cpp:51-67, deform_conv_cuda.cpp:152-237) */
+int eb_dcn1_forward(const float* x, const float* offset, const float* weight, float* out, int N, int C, int H, int W,
+                    int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                    int groups, int dg, void* workspace, size_t workspace_bytes, void* stream) {
+    return dcn_forward_impl("dcn1_forward", x, offset, nullptr, weight, nullptr, out, N, C, H, W, Cout, kh, kw,
+                            Geo2{stride_h, stride_w, pad_h, pad_w, dil_h, dil_w}, groups, dg, workspace, workspace_bytes,
+                            stream, false);
 }
 
 namespace {
@@ -407,36 +427,47 @@ BwdWs bwd_ws(int N, int C, int H, int W, int Cout, int K, int Ho, int Wo) {
 }
 }  // namespace
 
-size_t eb_mdcn_backward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int stride,
-                                  int pad, int dil) {
-    const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
-    const int Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
+static size_t bwd_workspace2(int N, int C, int H, int W, int Cout, int kh, int kw, Geo2 g) {
+    const int Ho = (H + 2 * g.ph - (g.dh * (kh - 1) + 1)) / g.sh + 1;
+    const int Wo = (W + 2 * g.pw - (g.dw * (kw - 1) + 1)) / g.sw + 1;
     if (Ho < 1 || Wo < 1 || N < 1) return 256;
     return bwd_ws(N, C, H, W, Cout, kh * kw, Ho, Wo).total;
 }
 
-int eb_mdcn_backward(const float* x, const float* offset, const float* mask, const float* weight,
-                     const float* grad_out, float* grad_x, float* grad_offset, float* grad_mask,
-                     float* grad_weight, float* grad_bias, int N, int C, int H, int W, int Cout, int kh,
-                     int kw, int stride, int pad, int dil, int groups, int dg, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+size_t eb_mdcn_backward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int stride,
+                                  int pad, int dil) {
+    return bwd_workspace2(N, C, H, W, Cout, kh, kw, Geo2{stride, stride, pad, pad, dil, dil});
+}
+
+size_t eb_dcn1_backward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w,
+                                  int pad_h, int pad_w, int dil_h, int dil_w) {
+    return bwd_workspace2(N, C, H, W, Cout, kh, kw, Geo2{stride_h, stride_w, pad_h, pad_w, dil_h, dil_w});
+}
+
+namespace {
+// Shared backward: `want_input` -> grad_x, grad_offset (and grad_mask when mask != NULL); `want_param` ->
+// grad_weight += scale * (...), grad_bias += (...).  mask == NULL gives DCNv1.
+int dcn_backward_impl(const char* who, const float* x, const float* offset, const float* mask, const float* weight,
+                      const float* grad_out, float* grad_x, float* grad_offset, float* grad_mask, float* grad_weight,
+                      float* grad_bias, float scale, bool want_input, bool want_param, int N, int C, int H, int W,
+                      int Cout, int kh, int kw, Geo2 g, int groups, int dg, void* workspace, size_t workspace_bytes,
+                      void* stream) {
     if (N == 0 && C > 0 && H > 0 && W > 0 && Cout > 0) return EB_OK;   // empty batch
-    if (!x || !offset || !mask || !weight || !grad_out || !grad_x || !grad_offset || !grad_mask || !grad_weight)
-        return fail(EB_ERR_NULLPTR, "mdcn_backward: null pointer");
-    if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || stride < 1 || pad < 0 || dil < 1 ||
-        groups < 1 || dg < 1 || C % dg || C % groups || Cout % groups)
-        return fail(EB_ERR_INVALID_SHAPE, "mdcn_backward: invalid shape");
-    if (groups != 1) return fail(EB_ERR_UNSUPPORTED, "mdcn_backward: groups=%d (only 1; EDVR uses 1)", groups);
-    if (C % 64 || (C / dg) % 8) return fail(EB_ERR_UNSUPPORTED, "mdcn_backward: C=%d dg=%d (C %% 64 == 0, (C/dg) %% 8 == 0)", C, dg);
-    const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
-    const int Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
-    if (Ho < 1 || Wo < 1) return fail(EB_ERR_INVALID_SHAPE, "mdcn_backward: empty output");
-    if (N == 0) return EB_OK;
+    if (!x || !offset || !grad_out || (want_input && (!weight || !grad_x || !grad_offset)) || (want_param && !grad_weight))
+        return fail(EB_ERR_NULLPTR, "%s: null pointer", who);
+    if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || g.sh < 1 || g.sw < 1 || g.ph < 0 || g.pw < 0 ||
+        g.dh < 1 || g.dw < 1 || groups < 1 || dg < 1 || C % dg || C % groups || Cout % groups)
+        return fail(EB_ERR_INVALID_SHAPE, "%s: invalid shape", who);
+    if (groups != 1) return fail(EB_ERR_UNSUPPORTED, "%s: groups=%d (only 1; EDVR uses 1)", who, groups);
+    if (C % 64 || (C / dg) % 8) return fail(EB_ERR_UNSUPPORTED, "%s: C=%d dg=%d (C %% 64 == 0, (C/dg) %% 8 == 0)", who, C, dg);
+    const int Ho = (H + 2 * g.ph - (g.dh * (kh - 1) + 1)) / g.sh + 1;
+    const int Wo = (W + 2 * g.pw - (g.dw * (kw - 1) + 1)) / g.sw + 1;
+    if (Ho < 1 || Wo < 1) return fail(EB_ERR_INVALID_SHAPE, "%s: empty output", who);
     const int K = kh * kw;
     const BwdWs ws = bwd_ws(N, C, H, W, Cout, K, Ho, Wo);
     if (!workspace || workspace_bytes < ws.total)
-        return fail(EB_ERR_WORKSPACE, "mdcn_backward: workspace %zu < %zu", workspace_bytes, ws.total);
-    if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "mdcn_backward: workspace must be 16-byte aligned");
+        return fail(EB_ERR_WORKSPACE, "%s: workspace %zu < %zu", who, workspace_bytes, ws.total);
+    if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "%s: workspace must be 16-byte aligned", who);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t* base = static_cast<uint8_t*>(workspace);
     __half* x16 = reinterpret_cast<__half*>(base + ws.x16);
@@ -446,19 +477,19 @@ int eb_mdcn_backward(const float* x, const float* offset, const float* mask, con
     float* gx32 = reinterpret_cast<float*>(base + ws.gx32);
     __half* colT = reinterpret_cast<__half*>(base + ws.colT);
     __half* goT = reinterpret_cast<__half*>(base + ws.goT);
-    const DcnBwdGeom G{N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, Ho, Wo};
+    DcnBwdGeom G{N, C, H, W, Cout, kh, kw, g.sh, g.ph, g.dh, dg, Ho, Wo, g.sw, g.pw, g.dw};
     const int HWo = Ho * Wo;
 
-    // layouts
-    {
+    {   // layouts
         dim3 block(32, 8);
         nchw_f32_to_nhwc_f16_kernel<<<dim3((H * W + 31) / 32, (C + 31) / 32, N), block, 0, st>>>(x, x16, C, H * W, C, 0);
-        if (ws.Cout64 != Cout) cudaMemsetAsync(go16, 0, static_cast<size_t>(ws.P) * ws.Cout64 * 2, st);
-        nchw_f32_to_nhwc_f16_kernel<<<dim3((HWo + 31) / 32, (Cout + 31) / 32, N), block, 0, st>>>(grad_out, go16, Cout, HWo, ws.Cout64, 0);
         if (int rc = check_launch("bwd layouts")) return rc;
     }
-    // stage 1: gcol = W^T . gO as a 1x1 conv with K*C output channels
-    {
+    if (want_input) {
+        // stage 1: gcol = W^T . gO as a 1x1 conv with K*C output channels
+        dim3 block(32, 8);
+        if (ws.Cout64 != Cout) cudaMemsetAsync(go16, 0, static_cast<size_t>(ws.P) * ws.Cout64 * 2, st);
+        nchw_f32_to_nhwc_f16_kernel<<<dim3((HWo + 31) / 32, (Cout + 31) / 32, N), block, 0, st>>>(grad_out, go16, Cout, HWo, ws.Cout64, 0);
         const long long groups16 = static_cast<long long>(K) * C * (ws.Cout64 / 8);
         pack_wT_kernel<<<grid_1d(groups16, 256), 256, 0, st>>>(weight, Cout, C, K, ws.Cout64, ws.BN, wT);
         ConvParams P;
@@ -470,17 +501,16 @@ int eb_mdcn_backward(const float* x, const float* offset, const float* mask, con
         P.epi.act = ACT_NONE; P.epi.H = Ho; P.epi.W = Wo; P.epi.out16 = gcol16; P.epi.out16_pix_stride = K * C;
         P.epi.out_mode = OUT_SAME;
         if (int rc = launch_conv(P, st)) return rc;
-    }
-    // stage 2: grad_offset, grad_mask, grad_input
-    {
+        // stage 2: grad_offset, grad_mask, grad_input
         cudaMemsetAsync(gx32, 0, static_cast<size_t>(N) * H * W * C * 4, st);
         const long long items = static_cast<long long>(N) * dg * K * HWo;
-        dcn_bwd_coord_scatter_kernel<<<grid_1d(items, 256), 256, 0, st>>>(G, x16, offset, mask, gcol16, gx32, grad_offset, grad_mask);
+        dcn_bwd_coord_scatter_kernel<<<grid_1d(items, 256), 256, 0, st>>>(G, x16, offset, mask, gcol16, gx32, grad_offset,
+                                                                          mask ? grad_mask : nullptr);
         nhwc_f32_to_nchw_f32_kernel<<<dim3((H * W + 31) / 32, (C + 31) / 32, N), dim3(32, 8), 0, st>>>(gx32, grad_x, C, H * W);
         if (int rc = check_launch("bwd coord/scatter")) return rc;
     }
-    // stage 3: grad_weight (+= over the batch), grad_bias
-    {
+    if (want_param) {
+        // stage 3: grad_weight (+= over the batch), grad_bias
         cudaMemsetAsync(goT, 0, static_cast<size_t>(ws.mt) * 128 * ws.Ppad * 2, st);
         if (ws.Ppad != ws.P) cudaMemsetAsync(colT, 0, static_cast<size_t>(K) * C * ws.Ppad * 2, st);
         dcn_bwd_goT_kernel<<<grid_1d(static_cast<long long>(N) * Cout * HWo, 256), 256, 0, st>>>(grad_out, goT, N, Cout, HWo, ws.Ppad);
@@ -493,11 +523,43 @@ int eb_mdcn_backward(const float* x, const float* offset, const float* mask, con
         const int sps = static_cast<int>((steps + want - 1) / want);
         const int splits = static_cast<int>((steps + sps - 1) / sps);
         if (int rc = set_smem(dcn_bwd_wgrad_kernel, WG_SMEM_BYTES)) return rc;
-        dcn_bwd_wgrad_kernel<<<dim3(ntn, ws.mt, splits), 128, WG_SMEM_BYTES, st>>>(goT, colT, grad_weight, Cout, C, K, ws.Ppad, ws.BN, sps);
+        dcn_bwd_wgrad_kernel<<<dim3(ntn, ws.mt, splits), 128, WG_SMEM_BYTES, st>>>(goT, colT, grad_weight, Cout, C, K, ws.Ppad, ws.BN, sps, scale);
         if (grad_bias) dcn_bwd_bias_kernel<<<Cout, 256, 0, st>>>(grad_out, grad_bias, N, Cout, HWo);
         if (int rc = check_launch("bwd wgrad")) return rc;
     }
     return EB_OK;
+}
+}  // namespace
+
+int eb_mdcn_backward(const float* x, const float* offset, const float* mask, const float* weight,
+                     const float* grad_out, float* grad_x, float* grad_offset, float* grad_mask,
+                     float* grad_weight, float* grad_bias, int N, int C, int H, int W, int Cout, int kh,
+                     int kw, int stride, int pad, int dil, int groups, int dg, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (!(N == 0) && (!mask || !grad_mask)) return fail(EB_ERR_NULLPTR, "mdcn_backward: null pointer");
+    return dcn_backward_impl("mdcn_backward", x, offset, mask, weight, grad_out, grad_x, grad_offset, grad_mask, grad_weight,
+                             grad_bias, 1.0f, true, true, N, C, H, W, Cout, kh, kw, Geo2{stride, stride, pad, pad, dil, dil},
+                             groups, dg, workspace, workspace_bytes, stream);
+}
+
+/* DCNv1: deform_conv_backward_input (deform_conv_ext.cpp:69-86, deform_conv_cuda.cpp:239-351): grad_x, grad_offset */
+int eb_dcn1_backward_input(const float* x, const float* offset, const float* weight, const float* grad_out, float* grad_x,
+                           float* grad_offset, int N, int C, int H, int W, int Cout, int kh, int kw, int stride_h,
+                           int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups, int dg, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    return dcn_backward_impl("dcn1_backward_input", x, offset, nullptr, weight, grad_out, grad_x, grad_offset, nullptr, nullptr,
+                             nullptr, 1.0f, true, false, N, C, H, W, Cout, kh, kw,
+                             Geo2{stride_h, stride_w, pad_h, pad_w, dil_h, dil_w}, groups, dg, workspace, workspace_bytes, stream);
+}
+
+/* DCNv1: deform_conv_backward_parameters (deform_conv_ext.cpp:88-104, deform_conv_cuda.cpp:353-488): grad_weight += scale * dW */
+int eb_dcn1_backward_parameters(const float* x, const float* offset, const float* grad_out, float* grad_weight, float scale,
+                                int N, int C, int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                                int pad_w, int dil_h, int dil_w, int groups, int dg, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    return dcn_backward_impl("dcn1_backward_parameters", x, offset, nullptr, nullptr, grad_out, nullptr, nullptr, nullptr,
+                             grad_weight, nullptr, scale, false, true, N, C, H, W, Cout, kh, kw,
+                             Geo2{stride_h, stride_w, pad_h, pad_w, dil_h, dil_w}, groups, dg, workspace, workspace_bytes, stream);
 }
 
 // ---- layout / elementwise ---------------------------------------------------------------------

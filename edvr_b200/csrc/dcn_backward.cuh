@@ -18,7 +18,8 @@
 namespace eb {
 
 struct DcnBwdGeom {
-    int N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, Ho, Wo;
+    int N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, Ho, Wo;   // stride / pad / dil along H
+    int stride_w, pad_w, dil_w;                                  // along W
 };
 
 // ---- W^T packed as the weight of a 1x1 conv with Cin = Cout64 and packed rows r = k*C + c
@@ -67,10 +68,10 @@ __global__ void dcn_bwd_coord_scatter_kernel(const DcnBwdGeom G, const __half* _
         const float dh = __ldg(offset + ob + static_cast<size_t>(2 * k) * HW);
         const float dw = __ldg(offset + ob + static_cast<size_t>(2 * k + 1) * HW);
         const size_t mb = ((static_cast<size_t>(n) * G.dg + g) * K + k) * HW + p;
-        const float mk = __ldg(mask + mb);
+        const float mk = mask ? __ldg(mask + mb) : 1.f;
         const int ki = k / G.kw, kj = k - ki * G.kw;
         const float h_im = static_cast<float>(ho * G.stride - G.pad + ki * G.dil) + dh;
-        const float w_im = static_cast<float>(wo * G.stride - G.pad + kj * G.dil) + dw;
+        const float w_im = static_cast<float>(wo * G.stride_w - G.pad_w + kj * G.dil_w) + dw;
         float goh = 0.f, gow = 0.f, gm = 0.f;
         if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(G.H) && w_im < static_cast<float>(G.W)) {
             const float hf = floorf(h_im), wf = floorf(w_im);
@@ -110,7 +111,7 @@ __global__ void dcn_bwd_coord_scatter_kernel(const DcnBwdGeom G, const __half* _
         }
         grad_offset[ob + static_cast<size_t>(2 * k) * HW] = goh;
         grad_offset[ob + static_cast<size_t>(2 * k + 1) * HW] = gow;
-        grad_mask[mb] = gm;
+        if (grad_mask != nullptr) grad_mask[mb] = gm;
     }
 }
 
@@ -146,10 +147,10 @@ __global__ void dcn_bwd_colT_kernel(const DcnBwdGeom G, const __half* __restrict
         const size_t ob = (static_cast<size_t>(n) * G.dg + g) * 2 * K * HW + p;
         const float dh = __ldg(offset + ob + static_cast<size_t>(2 * k) * HW);
         const float dw = __ldg(offset + ob + static_cast<size_t>(2 * k + 1) * HW);
-        const float mk = __ldg(mask + ((static_cast<size_t>(n) * G.dg + g) * K + k) * HW + p);
+        const float mk = mask ? __ldg(mask + ((static_cast<size_t>(n) * G.dg + g) * K + k) * HW + p) : 1.f;
         const int ki = k / G.kw, kj = k - ki * G.kw;
         const float h_im = static_cast<float>(ho * G.stride - G.pad + ki * G.dil) + dh;
-        const float w_im = static_cast<float>(wo * G.stride - G.pad + kj * G.dil) + dw;
+        const float w_im = static_cast<float>(wo * G.stride_w - G.pad_w + kj * G.dil_w) + dw;
         float val[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(G.H) && w_im < static_cast<float>(G.W)) {
             const float hf = floorf(h_im), wf = floorf(w_im);
@@ -194,7 +195,7 @@ constexpr int WG_SMEM_BYTES = WG_STAGES * (128 * 128 + 128 * 128);
 
 __global__ void __launch_bounds__(128, 1)
 dcn_bwd_wgrad_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ gW,
-                     int Cout, int C, int K, long long Ppad, int BN, int steps_per_split) {
+                     int Cout, int C, int K, long long Ppad, int BN, int steps_per_split, float scale) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t stage_free[WG_STAGES];
     __shared__ uint64_t done_bar;
@@ -265,7 +266,7 @@ dcn_bwd_wgrad_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
                 for (int j = 0; j < 32; ++j) {
                     const int n = nt * BN + cc + j;
                     const int k = n / C, c = n - k * C;
-                    atomicAdd(gW + (static_cast<size_t>(co) * C + c) * K + k, v[j]);
+                    atomicAdd(gW + (static_cast<size_t>(co) * C + c) * K + k, v[j] * scale);
                 }
             }
         }

@@ -42,11 +42,12 @@ struct DcnParams {
     int x_pix_stride, x_ch_off;
     int N, H, W, C;
     int Ho, Wo;
-    int kh, kw, stride, pad, dil;
+    int kh, kw, stride, pad, dil;   // along H
+    int stride_w, pad_w, dil_w;     // along W (DCNv1 passes independent pairs; v2 passes equal values)
     int dg, cpg;              // deformable groups, channels per group (multiple of 8)
     int off_mode;
     const float* offset;      // OFF_NCHW_F32: [N][dg*2*K][Ho][Wo]   (reference layout)
-    const float* mask;        //               [N][dg*K][Ho][Wo]
+    const float* mask;        //               [N][dg*K][Ho][Wo]; NULL = no modulation (DCNv1)
     const __half* offpack;    // OFF_PACK_F16: [N][Ho][Wo][dg*32]: per group 18 offsets, 9 masks, 5 pad
     int offpack_pix_stride;
     const __half* wpack;      // [n_tile][chunk][tap][kc=8][BN][8] fp16
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
         const int gw = warp - 6;                      // 0..7
         const int kc0 = (lane & 3) * 2;
         const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo, strd = P.stride, pad = P.pad, dil = P.dil;
+        const int strd_w = P.stride_w, pad_w = P.pad_w, dil_w = P.dil_w;
         const int kw = P.kw, cpg = P.cpg, dg = P.dg;
         const float fH = static_cast<float>(H), fW = static_cast<float>(W);
         const long long xps = P.x_pix_stride, xrow = static_cast<long long>(W) * xps;
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                     const float* ob = px.ob + (static_cast<long long>(g) * 2 * K + 2 * tap) * plane;
                     o.dh = __ldg(ob);
                     o.dw = __ldg(ob + plane);
-                    o.mk = __ldg(px.mb + (static_cast<long long>(g) * K + tap) * plane);
+                    o.mk = msk_f ? __ldg(px.mb + (static_cast<long long>(g) * K + tap) * plane) : 1.f;
                 } else {
                     const __half* rec = px.rec + g * 32;
                     const __half2 hw2 = *reinterpret_cast<const __half2*>(rec + 2 * tap);
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             c.dH = static_cast<int>(xrow);
             c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0.f;
             const float h_im = static_cast<float>(px.hb + ki * dil) + o.dh;
-            const float w_im = static_cast<float>(px.wb + kj * dil) + o.dw;
+            const float w_im = static_cast<float>(px.wb + kj * dil_w) + o.dw;
             if (px.ok && h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW) {
                 const float hf = floorf(h_im), wf = floorf(w_im);
                 const int hl = static_cast<int>(hf), wl = static_cast<int>(wf);
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                 const int ho = ty * DC_TILE_H + (px[i].m >> 3), wo = tx * DC_TILE_W + (px[i].m & 7);
                 px[i].ok = (ho < Ho) && (wo < Wo);
                 px[i].hb = ho * strd - pad;
-                px[i].wb = wo * strd - pad;
+                px[i].wb = wo * strd_w - pad_w;
                 const long long pix = static_cast<long long>(ho) * Wo + wo;
                 px[i].rec = (OFFMODE == OFF_PACK_F16) ? off_h + (static_cast<long long>(img) * plane + pix) * ops : nullptr;
                 px[i].ob = (OFFMODE == OFF_NCHW_F32) ? off_f + static_cast<long long>(img) * dg * 2 * K * plane + pix : nullptr;

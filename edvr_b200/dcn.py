@@ -6,8 +6,8 @@ Same public names, argument meaning, parameter names/shapes/initialisation and e
   ModulatedDeformConv ................................. :295-342
   ModulatedDeformConvPack ............................. :345-390
 and DCNv2Pack of /root/reference/basicsr/models/archs/arch_util.py:232-257.
-The v1 names (DeformConv, DeformConvPack, deform_conv) are exported for import compatibility and
-raise NotImplementedError when called: EDVR never reaches them.
+  DeformConvFunction / deform_conv (DCNv1) ............. :12-108
+  DeformConv / DeformConvPack ......................... :186-292
 
 There is no CPU path and no fallback: CPU tensors raise NotImplementedError exactly like the
 reference (deform_conv.py:133-134), and a missing libedvr_b200.so raises RuntimeError.
@@ -85,8 +85,64 @@ def mdcn_backward(x, offset, mask, weight, grad_out, with_bias, stride, padding,
 modulated_deform_conv = ModulatedDeformConvFunction.apply
 
 
-def deform_conv(*args, **kwargs):
-    raise NotImplementedError("DCNv1 (deform_conv) is not on the EDVR hot path; see DESIGN.md (row f3)")
+class DeformConvFunction(Function):
+    """DCNv1 through the three eb_dcn1_* entry points (per-axis stride / padding / dilation)."""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
+                im2col_step=64):
+        if input is not None and input.dim() != 4:
+            raise ValueError(f"Expected 4D tensor as input, got {input.dim()}D tensor instead.")
+        ctx.stride, ctx.padding, ctx.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        ctx.groups, ctx.deformable_groups, ctx.im2col_step = groups, deformable_groups, im2col_step
+        ctx.save_for_backward(input, offset, weight)
+        out_shape = DeformConvFunction._output_size(input, weight, ctx.padding, ctx.dilation, ctx.stride)
+        if not input.is_cuda:
+            raise NotImplementedError
+        step = min(ctx.im2col_step, input.shape[0])
+        assert (input.shape[0] % step) == 0, "im2col step must divide batchsize"
+        output = torch.empty(out_shape, dtype=torch.float32, device=input.device)
+        from . import deform_conv_ext as ext
+        ext.deform_conv_forward(_f32c(input), _f32c(weight), _f32c(offset), output, None, None, weight.size(3),
+                                weight.size(2), ctx.stride[1], ctx.stride[0], ctx.padding[1], ctx.padding[0],
+                                ctx.dilation[1], ctx.dilation[0], ctx.groups, ctx.deformable_groups, step)
+        return output.to(input.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        input, offset, weight = ctx.saved_tensors
+        grad_input = grad_offset = grad_weight = None
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        step = min(ctx.im2col_step, input.shape[0])
+        assert (input.shape[0] % step) == 0, "im2col step must divide batchsize"
+        from . import deform_conv_ext as ext
+        geom = (weight.size(3), weight.size(2), ctx.stride[1], ctx.stride[0], ctx.padding[1], ctx.padding[0],
+                ctx.dilation[1], ctx.dilation[0], ctx.groups, ctx.deformable_groups)
+        x, off, go = _f32c(input), _f32c(offset), _f32c(grad_output)
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gx, goff = torch.empty_like(x), torch.empty_like(off)
+            ext.deform_conv_backward_input(x, off, go, gx, goff, _f32c(weight), None, *geom, step)
+            grad_input, grad_offset = gx.to(input.dtype), goff.to(offset.dtype)
+        if ctx.needs_input_grad[2]:
+            gw = torch.zeros(weight.shape, dtype=torch.float32, device=weight.device)
+            ext.deform_conv_backward_parameters(x, off, go, gw, None, None, *geom, 1, step)
+            grad_weight = gw.to(weight.dtype)
+        return grad_input, grad_offset, grad_weight, None, None, None, None, None, None
+
+    @staticmethod
+    def _output_size(input, weight, padding, dilation, stride):
+        size = (input.size(0), weight.size(0))
+        for d in range(input.dim() - 2):
+            kernel = dilation[d] * (weight.size(d + 2) - 1) + 1
+            size += ((input.size(d + 2) + 2 * padding[d] - kernel) // stride[d] + 1,)
+        if not all(s > 0 for s in size):
+            raise ValueError(f"convolution input is too small (output would be {'x'.join(map(str, size))})")
+        return size
+
+
+deform_conv = DeformConvFunction.apply
 
 
 class ModulatedDeformConv(nn.Module):
@@ -214,13 +270,62 @@ class DCNv2Pack(ModulatedDeformConvPack):
 
 
 class DeformConv(nn.Module):
-    def __init__(self, *args, **kwargs):
+    """DCNv1 layer with external offsets; parameters and init as deform_conv.py:186-247 (bias is not supported there)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=False):
         super().__init__()
-        raise NotImplementedError("DCNv1 is not on the EDVR hot path; see DESIGN.md (row f3)")
+        assert not bias
+        assert in_channels % groups == 0, f"in_channels {in_channels} is not divisible by groups {groups}"
+        assert out_channels % groups == 0, f"out_channels {out_channels} is not divisible by groups {groups}"
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride = _pair(kernel_size), _pair(stride)
+        self.padding, self.dilation = _pair(padding), _pair(dilation)
+        self.groups, self.deformable_groups = groups, deformable_groups
+        self.transposed, self.output_padding = False, _single(0)     # nn.Conv2d look-alike attributes
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1.0 / math.sqrt(self.in_channels * self.kernel_size[0] * self.kernel_size[1])
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def forward(self, x, offset):
+        # inputs smaller than the kernel are zero-padded on the bottom/right and the output cropped back
+        # (deform_conv.py:232-247)
+        pad_h = max(self.kernel_size[0] - x.size(2), 0)
+        pad_w = max(self.kernel_size[1] - x.size(3), 0)
+        if pad_h or pad_w:
+            x = nn.functional.pad(x, (0, pad_w, 0, pad_h), "constant", 0).contiguous()
+            offset = nn.functional.pad(offset, (0, pad_w, 0, pad_h), "constant", 0).contiguous()
+        out = deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                          self.deformable_groups)
+        if pad_h or pad_w:
+            out = out[:, :, :out.size(2) - pad_h, :out.size(3) - pad_w].contiguous()
+        return out
 
 
 class DeformConvPack(DeformConv):
-    pass
+    """DCNv1 layer that predicts its own offsets with a zero-initialised conv (deform_conv.py:250-292)."""
+
+    _version = 2
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.conv_offset = nn.Conv2d(self.in_channels,
+                                     self.deformable_groups * 2 * self.kernel_size[0] * self.kernel_size[1],
+                                     kernel_size=self.kernel_size, stride=_pair(self.stride),
+                                     padding=_pair(self.padding), dilation=_pair(self.dilation), bias=True)
+        self.init_offset()
+
+    def init_offset(self):
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+
+    def forward(self, x):
+        offset = self.conv_offset(x)
+        return deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                           self.deformable_groups)
 
 
 __all__ = ["DeformConv", "DeformConvPack", "ModulatedDeformConv", "ModulatedDeformConvPack", "deform_conv",

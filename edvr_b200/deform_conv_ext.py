@@ -1,6 +1,6 @@
 """B1 boundary: a drop-in for the compiled module ``basicsr.models.ops.dcn.deform_conv_ext``.
 
-Exposes the five pybind11 names of /root/reference/basicsr/models/ops/dcn/src/deform_conv_ext.cpp:149-163 with the
+Exposes all five pybind11 names (DCNv2 forward/backward, DCNv1 forward/backward_input/backward_parameters) of /root/reference/basicsr/models/ops/dcn/src/deform_conv_ext.cpp:149-163 with the
 same positional signatures and in-place ownership rules (caller allocates every output; grad_weight / grad_bias are
 accumulated into; `ones` / `columns` are legacy scratch handles and are ignored), implemented over the C ABI of
 libedvr_b200.so.  Register it BEFORE importing basicsr and the unmodified reference tree runs on the B200 kernels:
@@ -92,10 +92,141 @@ def modulated_deform_conv_backward(input, weight, bias, ones, offset, mask, colu
         dst.copy_(src)
 
 
-def _v1(*args, **kwargs):
-    raise NotImplementedError("DCNv1 entry points are not on the EDVR hot path (DESIGN.md §7, SURVEY §8 row f3)")
+def _v1_shape_check(input, offset, grad_output, weight, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group,
+                    deformable_group):
+    """Host-side restatement of the argument checks the reference runs before a v1 launch (deform_conv_cuda.cpp:62-149);
+    returns (batched input, batched offset, batched grad_output, Ho, Wo)."""
+    if weight.dim() != 4:
+        raise RuntimeError(f"4D weight tensor (nOutputPlane,nInputPlane,kH,kW) expected, but got: {weight.dim()}")
+    if not weight.is_contiguous():
+        raise RuntimeError("weight tensor has to be contiguous")
+    if kW <= 0 or kH <= 0:
+        raise RuntimeError(f"kernel size should be greater than zero, but got kH: {kH} kW: {kW}")
+    if (weight.size(2), weight.size(3)) != (kH, kW):
+        raise RuntimeError(f"kernel size should be consistent with weight, but got kH: {kH} kW: {kW} "
+                           f"weight.size(2): {weight.size(2)}, weight.size(3): {weight.size(3)}")
+    if dW <= 0 or dH <= 0:
+        raise RuntimeError(f"stride should be greater than zero, but got dH: {dH} dW: {dW}")
+    if dilationW <= 0 or dilationH <= 0:
+        raise RuntimeError(f"dilation should be greater than 0, but got dilationH: {dilationH} dilationW: {dilationW}")
+    if input.dim() not in (3, 4):
+        raise RuntimeError(f"3D or 4D input tensor expected but got: {input.dim()}")
+    if input.dim() == 3:                                    # unbatched call: deform_conv_cuda.cpp:176-183
+        input, offset = input.unsqueeze(0), offset.unsqueeze(0)
+        if grad_output is not None:
+            grad_output = grad_output.unsqueeze(0)
+    n_in, n_out = weight.size(1) * group, weight.size(0)
+    H, W = input.size(2), input.size(3)
+    Ho = (H + 2 * padH - (dilationH * (kH - 1) + 1)) // dH + 1
+    Wo = (W + 2 * padW - (dilationW * (kW - 1) + 1)) // dW + 1
+    if n_in % deformable_group:
+        raise RuntimeError("input channels must divide deformable group size")
+    if Wo < 1 or Ho < 1:
+        raise RuntimeError(f"Given input size: ({n_in} x {H} x {W}). Calculated output size: ({n_out} x {Ho} x {Wo}). "
+                           "Output size is too small")
+    if input.size(1) != n_in:
+        raise RuntimeError(f"invalid number of input planes, expected: {n_in}, but got: {input.size(1)}")
+    if H < kH or W < kW:
+        raise RuntimeError("input image is smaller than kernel")
+    if (offset.size(2), offset.size(3)) != (Ho, Wo):
+        raise RuntimeError(f"invalid spatial size of offset, expected height: {Ho} width: {Wo}, but got height: "
+                           f"{offset.size(2)} width: {offset.size(3)}")
+    if offset.size(1) != deformable_group * 2 * kH * kW:
+        raise RuntimeError("invalid number of channels of offset")
+    if offset.size(0) != input.size(0):
+        raise RuntimeError("invalid batch size of offset")                       # deform_conv_cuda.cpp:190
+    if grad_output is not None:
+        if grad_output.size(1) != n_out:
+            raise RuntimeError(f"invalid number of gradOutput planes, expected: {n_out}, but got: {grad_output.size(1)}")
+        if (grad_output.size(2), grad_output.size(3)) != (Ho, Wo):
+            raise RuntimeError(f"invalid size of gradOutput, expected height: {Ho} width: {Wo} , but got height: "
+                               f"{grad_output.size(2)} width: {grad_output.size(3)}")
+    return input, offset, grad_output, Ho, Wo
 
 
-deform_conv_forward = _v1
-deform_conv_backward_input = _v1
-deform_conv_backward_parameters = _v1
+def _out_buf(t, accumulate=False):
+    """fp32 contiguous view of a caller-owned output (itself when it already is one) and whether to copy back."""
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t, False
+    return (t.float().contiguous() if accumulate else torch.empty(t.shape, dtype=torch.float32, device=t.device)), True
+
+
+def deform_conv_forward(input, weight, offset, output, columns, ones, kW, kH, dW, dH, padW, padH, dilationW, dilationH,
+                        group, deformable_group, im2col_step):
+    """deform_conv_ext.cpp:51-67 -> deform_conv_forward_cuda (deform_conv_cuda.cpp:152-237).  `columns` / `ones` are the
+    reference's scratch handles (ignored); `im2col_step` only has to divide the batch (no effect on the result).
+    Resizes `output` to [N, Cout, Ho, Wo] like the reference's view/resize dance and returns 1."""
+    _check_cuda(input, "deform conv")
+    input4, offset4, _, Ho, Wo = _v1_shape_check(input, offset, None, weight, kH, kW, dH, dW, padH, padW, dilationH,
+                                                 dilationW, group, deformable_group)
+    N, C, H, W = input4.shape
+    if N % im2col_step:
+        raise RuntimeError("im2col step must divide batchsize")                  # deform_conv_cuda.cpp:189
+    Cout = weight.shape[0]
+    x, w, off = _f32(input4), _f32(weight), _f32(offset4)
+    shape = (N, Cout, Ho, Wo) if input.dim() == 4 else (Cout, Ho, Wo)
+    if tuple(output.shape) != shape:
+        output.resize_(shape)
+    out32, copy_back = _out_buf(output)
+    need = L.lib().eb_mdcn_forward_workspace(N, C, H, W, Cout, kH, kW)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
+    with torch.cuda.device(input.device):
+        L.check(L.lib().eb_dcn1_forward(L.ptr(x), L.ptr(off), L.ptr(w), L.ptr(out32), N, C, H, W, Cout, kH, kW, dH, dW,
+                                        padH, padW, dilationH, dilationW, group, deformable_group, L.ptr(ws), ws.numel(),
+                                        L.stream_ptr()), "eb_dcn1_forward")
+    if copy_back:
+        output.copy_(out32)
+    return 1
+
+
+def deform_conv_backward_input(input, offset, gradOutput, gradInput, gradOffset, weight, columns, kW, kH, dW, dH, padW,
+                               padH, dilationW, dilationH, group, deformable_group, im2col_step):
+    """deform_conv_ext.cpp:69-86 -> deform_conv_backward_input_cuda (deform_conv_cuda.cpp:239-351): OVERWRITES the caller's
+    gradInput and gradOffset; returns 1."""
+    _check_cuda(input, "deform conv")
+    input4, offset4, go4, Ho, Wo = _v1_shape_check(input, offset, gradOutput, weight, kH, kW, dH, dW, padH, padW,
+                                                   dilationH, dilationW, group, deformable_group)
+    N, C, H, W = input4.shape
+    if N % im2col_step:
+        raise RuntimeError("im2col step must divide batchsize")
+    Cout = weight.shape[0]
+    x, w, off, go = _f32(input4), _f32(weight), _f32(offset4), _f32(go4)
+    gx, gx_back = _out_buf(gradInput)
+    goff, goff_back = _out_buf(gradOffset)
+    need = L.lib().eb_dcn1_backward_workspace(N, C, H, W, Cout, kH, kW, dH, dW, padH, padW, dilationH, dilationW)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
+    with torch.cuda.device(input.device):
+        L.check(L.lib().eb_dcn1_backward_input(L.ptr(x), L.ptr(off), L.ptr(w), L.ptr(go), L.ptr(gx), L.ptr(goff), N, C, H, W,
+                                               Cout, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group,
+                                               deformable_group, L.ptr(ws), ws.numel(), L.stream_ptr()),
+                "eb_dcn1_backward_input")
+    if gx_back:
+        gradInput.copy_(gx)
+    if goff_back:
+        gradOffset.copy_(goff)
+    return 1
+
+
+def deform_conv_backward_parameters(input, offset, gradOutput, gradWeight, columns, ones, kW, kH, dW, dH, padW, padH,
+                                    dilationW, dilationH, group, deformable_group, scale, im2col_step):
+    """deform_conv_ext.cpp:88-104 -> deform_conv_backward_parameters_cuda (deform_conv_cuda.cpp:353-488):
+    gradWeight += scale * dL/dW (accumulated into the caller's tensor); returns 1."""
+    _check_cuda(input, "deform conv")
+    input4, offset4, go4, Ho, Wo = _v1_shape_check(input, offset, gradOutput, gradWeight, kH, kW, dH, dW, padH, padW,
+                                                   dilationH, dilationW, group, deformable_group)
+    N, C, H, W = input4.shape
+    if N % im2col_step:
+        raise RuntimeError("im2col step must divide batchsize")
+    Cout = gradWeight.shape[0]
+    x, off, go = _f32(input4), _f32(offset4), _f32(go4)
+    gw, gw_back = _out_buf(gradWeight, accumulate=True)
+    need = L.lib().eb_dcn1_backward_workspace(N, C, H, W, Cout, kH, kW, dH, dW, padH, padW, dilationH, dilationW)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
+    with torch.cuda.device(input.device):
+        L.check(L.lib().eb_dcn1_backward_parameters(L.ptr(x), L.ptr(off), L.ptr(go), L.ptr(gw), float(scale), N, C, H, W,
+                                                    Cout, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group,
+                                                    deformable_group, L.ptr(ws), ws.numel(), L.stream_ptr()),
+                "eb_dcn1_backward_parameters")
+    if gw_back:
+        gradWeight.copy_(gw)
+    return 1

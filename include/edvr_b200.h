@@ -117,6 +117,25 @@ int eb_mdcn_backward(const float* x, const float* offset, const float* mask, con
                      int W, int Cout, int kh, int kw, int stride, int pad, int dil, int groups, int dg,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- DCNv1 (deformable conv without modulation): the other three entry points of the reference extension
+ * (deform_conv_ext.cpp:51-104; deform_conv_cuda.cpp:152-488), per-axis stride / pad / dilation like its Python
+ * wrapper passes them (deform_conv.py:44-49).  Same NCHW fp32 layouts, offset [N, dg*2*kh*kw, Ho, Wo], no bias.
+ * `im2col_step` of the reference is a batching detail with no effect on results and has no equivalent here.
+ * Workspace: eb_mdcn_forward_workspace / eb_dcn1_backward_workspace. */
+int eb_dcn1_forward(const float* x, const float* offset, const float* weight, float* out, int N, int C, int H, int W,
+                    int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                    int groups, int dg, void* workspace, size_t workspace_bytes, void* stream);
+size_t eb_dcn1_backward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w,
+                                  int pad_h, int pad_w, int dil_h, int dil_w);
+int eb_dcn1_backward_input(const float* x, const float* offset, const float* weight, const float* grad_out, float* grad_x,
+                           float* grad_offset, int N, int C, int H, int W, int Cout, int kh, int kw, int stride_h,
+                           int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups, int dg, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int eb_dcn1_backward_parameters(const float* x, const float* offset, const float* grad_out, float* grad_weight, float scale,
+                                int N, int C, int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                                int pad_w, int dil_h, int dil_w, int groups, int dg, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
 /* ---- layout / elementwise stages of the EDVR graph (all NHWC fp16 unless noted) --------- */
 int eb_nchw_f32_to_nhwc_f16(const float* src, void* dst, int N, int C, int H, int W,
                             int dst_pix_stride, int dst_ch_off, void* stream);

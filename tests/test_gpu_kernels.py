@@ -269,6 +269,111 @@ def test_autograd_function_matches_oracle(ops):
         modulated_deform_conv(x, off, mask, w, b, 1, 1, 1, 1, 8)
 
 
+# ---- DCNv1: deform_conv_forward / backward_input / backward_parameters -------------------------
+V1_GPU_CASES = {  # N, C, H, W, Cout, dg, (kh, kw), stride, padding, dilation, offset scale
+    "iso_dg8": (2, 64, 12, 14, 64, 8, (3, 3), (1, 1), (1, 1), (1, 1), 2.0),
+    "aniso_dg1": (2, 64, 15, 13, 32, 1, (3, 3), (2, 1), (1, 2), (1, 2), 3.0),
+    "k1x3_c128": (1, 128, 9, 11, 128, 4, (1, 3), (1, 1), (0, 1), (1, 1), 1.5),
+    "ragged_big_offsets": (3, 64, 21, 37, 64, 8, (3, 3), (1, 1), (1, 1), (1, 1), 25.0),
+}
+
+
+def _v1_case(N, C, H, W, Cout, dg, k, s, p, d, osc, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    Ho = (H + 2 * p[0] - (d[0] * (k[0] - 1) + 1)) // s[0] + 1
+    Wo = (W + 2 * p[1] - (d[1] * (k[1] - 1) + 1)) // s[1] + 1
+    x = torch.randn(N, C, H, W, generator=g)
+    off = torch.randn(N, dg * 2 * k[0] * k[1], Ho, Wo, generator=g) * osc
+    w = (torch.rand(Cout, C, *k, generator=g) * 2 - 1) / (C * k[0] * k[1]) ** 0.5
+    go = torch.randn(N, Cout, Ho, Wo, generator=g)
+    return x, off, w, go
+
+
+@pytest.mark.parametrize("name", list(V1_GPU_CASES))
+def test_dcn1_autograd_vs_oracle(ops, name):
+    """deform_conv (autograd Function over the three eb_dcn1_* entry points) vs the C oracle; tolerance 1e-3."""
+    from oracle import dcn_oracle
+    from edvr_b200.dcn import deform_conv
+    N, C, H, W, Cout, dg, k, s, p, d, osc = V1_GPU_CASES[name]
+    x, off, w, go = _v1_case(*V1_GPU_CASES[name])
+    ts = [t.cuda().requires_grad_(True) for t in (x, off, w)]
+    y = deform_conv(*ts, s, p, d, 1, dg)
+    ref = dcn_oracle.forward_v1(x.numpy(), off.numpy(), w.numpy(), s, p, d, 1, dg)
+    e = rel_err(y.detach().cpu(), ref)
+    assert y.shape == ref.shape and e[0] < TOL and e[1] < TOL, e
+    y.backward(go.cuda())
+    grads = dcn_oracle.backward_v1(x.numpy(), off.numpy(), w.numpy(), go.numpy(), s, p, d, 1, dg)
+    for nm, t, r in zip(("gx", "goff", "gw"), ts, grads):
+        e = rel_err(t.grad.cpu(), r)
+        assert e[0] < TOL and e[1] < TOL, (nm, e)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "dcn1_ref_cuda_*.npz"))))
+def test_dcn1_ext_vs_reference_cuda_golden(ops, path):
+    """The B1 shim's three v1 functions, called with the reference's argument order (kW before kH ...), against
+    outputs recorded from the unmodified reference CUDA extension; grad_weight accumulates scale * dW."""
+    from edvr_b200 import deform_conv_ext as ext
+    z = np.load(path)
+    N, C, H, W, Cout, dg, kh, kw, sh, sw, ph, pw, dh, dw = (int(v) for v in z["meta"])
+    scale = float(z["scale"])
+    x, off, w, go = (torch.from_numpy(z[k]).cuda() for k in ("x", "offset", "weight", "grad_out"))
+    geom = (kw, kh, sw, sh, pw, ph, dw, dh, 1, dg)
+    out = x.new_empty(0)
+    assert ext.deform_conv_forward(x, w, off, out, x.new_empty(0), x.new_empty(0), *geom, N) == 1
+    e = rel_err(out.cpu(), z["out"])
+    assert out.shape == z["out"].shape and e[0] < TOL and e[1] < TOL, ("out", e)
+    gx, goff = torch.full_like(x, 7.0), torch.full_like(off, 7.0)        # overwritten, not accumulated
+    ext.deform_conv_backward_input(x, off, go, gx, goff, w, x.new_empty(0), *geom, N)
+    gw = torch.ones_like(w)                                              # accumulated into
+    ext.deform_conv_backward_parameters(x, off, go, gw, x.new_empty(0), x.new_empty(0), *geom, scale, N)
+    for nm, got, ref in (("grad_x", gx, z["grad_x"]), ("grad_offset", goff, z["grad_offset"]),
+                         ("grad_weight", gw - 1.0, z["grad_weight"])):
+        e = rel_err(got.cpu(), ref)
+        assert e[0] < TOL and e[1] < TOL, (nm, e)
+
+
+def test_dcn1_modules_and_error_behaviour(ops):
+    """DeformConvPack: zero-initialised conv_offset => equals a plain convolution; DeformConv pads inputs smaller than
+    the kernel (deform_conv.py:232-247); reference error behaviour for bad arguments."""
+    from edvr_b200 import deform_conv_ext as ext
+    from edvr_b200.dcn import DeformConv, DeformConvPack, deform_conv
+    torch.manual_seed(0)
+    m = DeformConvPack(64, 64, 3, stride=1, padding=1, deformable_groups=8).cuda()
+    assert sorted(k for k, _ in m.named_parameters()) == ["conv_offset.bias", "conv_offset.weight", "weight"]
+    x = torch.randn(2, 64, 10, 13, device="cuda")
+    e = rel_err(m(x).detach().cpu(), F.conv2d(x, m.weight, None, padding=1).detach().cpu())
+    assert e[0] < TOL and e[1] < TOL, e
+    m(x).sum().backward()
+    assert m.weight.grad is not None and m.conv_offset.weight.grad is not None
+    small = DeformConv(64, 64, 3, padding=1, deformable_groups=1).cuda()
+    y = small(torch.randn(1, 64, 2, 2, device="cuda"), torch.zeros(1, 18, 2, 2, device="cuda"))
+    assert y.shape == (1, 64, 2, 2)
+    with pytest.raises(NotImplementedError):                             # CPU tensors (deform_conv.py:43-44)
+        deform_conv(torch.zeros(1, 64, 4, 4), torch.zeros(1, 18, 4, 4), torch.zeros(64, 64, 3, 3), 1, 1, 1, 1, 1)
+    with pytest.raises(ValueError, match="Expected 4D tensor"):
+        deform_conv(torch.zeros(64, 4, 4, device="cuda"), torch.zeros(1, 18, 4, 4, device="cuda"),
+                    torch.zeros(64, 64, 3, 3, device="cuda"))
+    with pytest.raises(AssertionError, match="im2col step must divide batchsize"):
+        deform_conv(torch.zeros(3, 64, 4, 4, device="cuda"), torch.zeros(3, 18, 4, 4, device="cuda"),
+                    torch.zeros(64, 64, 3, 3, device="cuda"), 1, 1, 1, 1, 1, 2)
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    with pytest.raises(RuntimeError, match="invalid number of channels of offset"):
+        ext.deform_conv_forward(z(1, 64, 4, 4), z(64, 64, 3, 3), z(1, 20, 4, 4), z(0), z(0), z(0), 3, 3, 1, 1, 1, 1, 1, 1,
+                                1, 1, 1)
+    with pytest.raises(RuntimeError, match="invalid spatial size of offset"):
+        ext.deform_conv_forward(z(1, 64, 4, 4), z(64, 64, 3, 3), z(1, 18, 5, 4), z(0), z(0), z(0), 3, 3, 1, 1, 1, 1, 1, 1,
+                                1, 1, 1)
+    with pytest.raises(RuntimeError, match="not implemented on CPU"):
+        ext.deform_conv_forward(torch.zeros(1, 64, 4, 4), torch.zeros(64, 64, 3, 3), torch.zeros(1, 18, 4, 4),
+                                torch.zeros(0), torch.zeros(0), torch.zeros(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1)
+    # unbatched (3-D) call, deform_conv_cuda.cpp:176-183,230-234
+    x3, w3, o3 = torch.randn(64, 6, 7, device="cuda"), torch.randn(64, 64, 3, 3, device="cuda") / 24, z(18, 6, 7)
+    out3 = z(0)
+    ext.deform_conv_forward(x3, w3, o3, out3, z(0), z(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1)
+    e = rel_err(out3.cpu(), F.conv2d(x3[None], w3, None, padding=1)[0].cpu())
+    assert out3.shape == (64, 6, 7) and e[0] < TOL, e
+
+
 def test_error_codes_not_printf(ops):
     from edvr_b200 import _lib as L
     x = torch.zeros(1, 60, 8, 8, device="cuda")          # C % 64 != 0 -> unsupported, reported loudly
@@ -396,8 +501,8 @@ def test_b1_extension_shim_signature_and_inplace_semantics(ops, golden_dir):
     with pytest.raises(RuntimeError, match="not implemented on CPU"):
         ext.modulated_deform_conv_forward(t["x"].cpu(), t["weight"].cpu(), t["bias"].cpu(), e, t["offset"].cpu(),
                                           t["mask"].cpu(), out.cpu(), e, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, True)
-    with pytest.raises(NotImplementedError):
-        ext.deform_conv_forward()
+    assert all(callable(getattr(ext, n)) for n in ("deform_conv_forward", "deform_conv_backward_input",
+                                                    "deform_conv_backward_parameters"))   # deform_conv_ext.cpp:149-163
 
 
 # ---------------------------------------------------------------- full-size, size-independent properties

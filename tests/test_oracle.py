@@ -104,6 +104,48 @@ def test_oracle_vs_reference_cuda_golden(path):
         assert rel_err(got, z[name])[0] < 5e-6, name
 
 
+V1_CASES = [  # N, C, H, W, Cout, dg, (kh, kw), stride, padding, dilation
+    (2, 8, 9, 11, 6, 2, (3, 3), (1, 1), (1, 1), (1, 1)),
+    (1, 8, 12, 10, 4, 1, (3, 3), (2, 1), (1, 2), (1, 2)),
+    (1, 16, 7, 9, 8, 4, (1, 3), (1, 2), (0, 1), (1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", V1_CASES)
+def test_oracle_v1_forward_backward_vs_torchvision(case):
+    """DCNv1 (mask-less, bias-less, per-axis geometry, `scale` on grad_weight) against torchvision's autograd."""
+    from torchvision.ops import deform_conv2d
+    N, C, H, W, Cout, dg, k, s, p, d = case
+    g = torch.Generator().manual_seed(13)
+    Ho, Wo = ((sz + 2 * p[i] - (d[i] * (k[i] - 1) + 1)) // s[i] + 1 for i, sz in enumerate((H, W)))
+    x = torch.randn(N, C, H, W, generator=g, requires_grad=True)
+    off = (torch.randn(N, dg * 2 * k[0] * k[1], Ho, Wo, generator=g) * 2).requires_grad_(True)
+    w = (torch.randn(Cout, C, *k, generator=g) * 0.1).requires_grad_(True)
+    y = deform_conv2d(x, off, w, None, stride=s, padding=p, dilation=d)
+    go = torch.randn(y.shape, generator=g)
+    y.backward(go)
+    dn = lambda t: t.detach().numpy()
+    yo = dcn_oracle.forward_v1(dn(x), dn(off), dn(w), s, p, d, 1, dg)
+    assert yo.shape == tuple(y.shape) and rel_err(yo, y.detach())[0] < 1e-5
+    gx, goff, gw = dcn_oracle.backward_v1(dn(x), dn(off), dn(w), go.numpy(), s, p, d, 1, dg, scale=0.25)
+    assert rel_err(gx, x.grad)[0] < 2e-5 and rel_err(goff, off.grad)[0] < 2e-5
+    assert rel_err(gw, 0.25 * w.grad)[0] < 2e-5
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "dcn1_ref_cuda_*.npz"))))
+def test_oracle_v1_vs_reference_cuda_golden(path):
+    """Pins the DCNv1 oracle on outputs of the unmodified reference CUDA extension (tools/first_light.py refext_v1)."""
+    z = np.load(path)
+    N, C, H, W, Cout, dg, kh, kw, sh, sw, ph, pw, dh, dw = (int(v) for v in z["meta"])
+    s, p, d = (sh, sw), (ph, pw), (dh, dw)
+    yo = dcn_oracle.forward_v1(z["x"], z["offset"], z["weight"], s, p, d, 1, dg)
+    assert rel_err(yo, z["out"])[0] < 1e-5
+    gx, goff, gw = dcn_oracle.backward_v1(z["x"], z["offset"], z["weight"], z["grad_out"], s, p, d, 1, dg,
+                                          scale=float(z["scale"]))
+    for name, got in (("grad_x", gx), ("grad_offset", goff), ("grad_weight", gw)):
+        assert rel_err(got, z[name])[0] < 2e-5, name
+
+
 def test_oracle_rejects_bad_shapes():
     x = np.zeros((1, 6, 4, 4), np.float32)
     with pytest.raises(ValueError):

@@ -210,6 +210,93 @@ def sec_refext():
     return res
 
 
+V1_CASES = {  # name: N, C, H, W, Cout, dg, (kh, kw), stride, padding, dilation, offset scale
+    "v1_c64_dg8": (2, 64, 12, 14, 64, 8, (3, 3), (1, 1), (1, 1), (1, 1), 2.0),
+    "v1_c64_dg1_aniso": (2, 64, 15, 13, 32, 1, (3, 3), (2, 1), (1, 2), (1, 2), 3.0),
+    "v1_c128_dg4_k1x3": (1, 128, 9, 11, 128, 4, (1, 3), (1, 1), (0, 1), (1, 1), 1.5),
+}
+
+
+def _v1_inputs(N, C, H, W, Cout, dg, k, stride, pad, dil, osc, seed=11):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    Ho = (H + 2 * pad[0] - (dil[0] * (k[0] - 1) + 1)) // stride[0] + 1
+    Wo = (W + 2 * pad[1] - (dil[1] * (k[1] - 1) + 1)) // stride[1] + 1
+    x = torch.randn(N, C, H, W, generator=g)
+    off = torch.randn(N, dg * 2 * k[0] * k[1], Ho, Wo, generator=g) * osc
+    w = (torch.rand(Cout, C, *k, generator=g) * 2 - 1) / (C * k[0] * k[1]) ** 0.5
+    go = torch.randn(N, Cout, Ho, Wo, generator=g)
+    return x, off, w, go
+
+
+def sec_refext_v1():
+    """DCNv1 entry points of the reference CUDA ext: compare with the C oracle and our kernels, emit golden vectors."""
+    import numpy as np
+    import torch
+    from edvr_b200 import deform_conv_ext as ours
+    from oracle import build_ref, dcn_oracle
+    ext = build_ref.load_ref()
+    res = {}
+    gold_dir = os.path.join(OUT, "golden")
+    os.makedirs(gold_dir, exist_ok=True)
+
+    def run(mod, x, off, w, go, k, s, p, d, dg, scale, is_ref=False):
+        # On current torch the reference's v1 host code only runs for some im2col_step values: forward re-views `columns`
+        # inside its batch loop (needs a single iteration, step == N; deform_conv_cuda.cpp:222-226), backward_parameters
+        # views a zeros_like() of a transposed tensor (needs step == 1; :425-434).  The result does not depend on the
+        # step, so the reference is called with whichever step it accepts.
+        N = x.shape[0]
+        geom = (k[1], k[0], s[1], s[0], p[1], p[0], d[1], d[0], 1, dg)
+        e = lambda: x.new_empty(0)
+
+        def call(fn, *args):
+            steps = (N, 1) if is_ref else (N,)
+            for i, st in enumerate(steps):
+                try:
+                    return fn(*args, st)
+                except RuntimeError:
+                    if i == len(steps) - 1:
+                        raise
+
+        out = x.new_empty(go.shape)
+        call(mod.deform_conv_forward, x, w, off, out, e(), e(), *geom)
+        gx, goff, gw = torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(w)
+        call(mod.deform_conv_backward_input, x, off, go, gx, goff, w, e(), *geom)
+        try:
+            mod.deform_conv_backward_parameters(x, off, go, gw, e(), e(), *geom, scale, N)
+        except RuntimeError:
+            if not is_ref:
+                raise
+            gw.zero_()
+            mod.deform_conv_backward_parameters(x, off, go, gw, e(), e(), *geom, scale, 1)
+        torch.cuda.synchronize()
+        return out, gx, goff, gw
+
+    for name, (N, C, H, W, Cout, dg, k, s, p, d, osc) in V1_CASES.items():
+        x, off, w, go = _v1_inputs(N, C, H, W, Cout, dg, k, s, p, d, osc)
+        cu = [t.cuda() for t in (x, off, w, go)]
+        ref = run(ext, *cu, k, s, p, d, dg, 0.5, is_ref=True)
+        yo = dcn_oracle.forward_v1(x.numpy(), off.numpy(), w.numpy(), s, p, d, 1, dg)
+        go_ = dcn_oracle.backward_v1(x.numpy(), off.numpy(), w.numpy(), go.numpy(), s, p, d, 1, dg, scale=0.5)
+        r = {"fwd_oracle_vs_ref": rel(torch.from_numpy(yo), ref[0].cpu())}
+        for nm, a, bb in zip(("gx", "goff", "gw"), go_, ref[1:]):
+            r[f"{nm}_oracle_vs_ref"] = rel(torch.from_numpy(a), bb.cpu())
+        try:
+            mine = run(ours, *cu, k, s, p, d, dg, 0.5)
+            for nm, a, bb in zip(("fwd", "gx", "goff", "gw"), mine, ref):
+                r[f"{nm}_ours_vs_ref"] = rel(a.cpu(), bb.cpu())
+        except Exception as exc:   # keep the golden vectors even if our path is not up yet
+            r["ours_error"] = repr(exc)[:300]
+        res[name] = r
+        print(f"refext_v1 {name}: {json.dumps(r)}", flush=True)
+        np.savez_compressed(os.path.join(gold_dir, f"dcn1_ref_cuda_{name}.npz"),
+                            x=x.numpy(), offset=off.numpy(), weight=w.numpy(), grad_out=go.numpy(),
+                            out=ref[0].cpu().numpy(), grad_x=ref[1].cpu().numpy(), grad_offset=ref[2].cpu().numpy(),
+                            grad_weight=ref[3].cpu().numpy(),
+                            meta=np.array([N, C, H, W, Cout, dg, *k, *s, *p, *d]), scale=np.float32(0.5))
+    return res
+
+
 def sec_refbench():
     """Time the reference CUDA path (reference dcn ext + cuDNN convs) on EDVR-L cfg 3 and EDVR-M cfg 2."""
     import torch
@@ -254,7 +341,7 @@ def sec_refbench():
 
 
 SECTIONS = {"selftest": sec_selftest, "conv": sec_conv, "dcn": sec_dcn, "refext": sec_refext,
-            "refbench": sec_refbench}
+            "refext_v1": sec_refext_v1, "refbench": sec_refbench}
 
 
 def main():

@@ -288,7 +288,7 @@ def profile_step(eng, x):
     torch.cuda.synchronize()
     recs, ops.PROFILE = ops.PROFILE, None
     agg, total = {}, 0.0
-    for name, flops, e0, e1 in recs:
+    for name, flops, e0, e1, _detail in recs:
         ms = e0.elapsed_time(e1)
         a = agg.setdefault(name, [0.0, 0.0, 0])
         a[0] += ms; a[1] += flops; a[2] += 1

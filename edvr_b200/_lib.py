@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libedvr_b200.so")
+LIB_PATH = os.environ.get("EDVR_B200_LIB", os.path.join(_HERE, "libedvr_b200.so"))   # override: A/B-test a build
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_DCN_PACK, ACT_SIGMOID = 0, 1, 2, 3, 4
 OUT_SAME, OUT_PIXSHUF2, OUT_STRIDE2 = 0, 1, 2
@@ -46,6 +46,7 @@ _SIGS = {
     "eb_mdcn_forward": (c_int, [c_void_p] * 6 + [c_int] * 12 + [c_void_p, c_size_t, c_void_p]),
     "eb_mdcn_backward_workspace": (c_size_t, [c_int] * 10),
     "eb_mdcn_backward": (c_int, [c_void_p] * 10 + [c_int] * 12 + [c_void_p, c_size_t, c_void_p]),
+    "eb_selftest_mma_rate": (c_int, [c_int] * 10 + [c_void_p, c_void_p, c_void_p]),
     "eb_dcn1_forward": (c_int, [c_void_p] * 4 + [c_int] * 15 + [c_void_p, c_size_t, c_void_p]),
     "eb_dcn1_backward_workspace": (c_size_t, [c_int] * 13),
     "eb_dcn1_backward_input": (c_int, [c_void_p] * 6 + [c_int] * 15 + [c_void_p, c_size_t, c_void_p]),

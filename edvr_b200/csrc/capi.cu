@@ -124,6 +124,34 @@ int eb_selftest_umma(const void* A, const void* B, float* D, int N, int K, int v
     return check_launch("selftest_umma");
 }
 
+int eb_selftest_mma_rate(int cta_group, int M, int N, int layout, int a_lbo, int a_sbo, int b_lbo, int b_sbo,
+                         int kstep_bytes, int reps, unsigned long long* cycles, int* n_ctas, void* stream) {
+    if (!cycles || !n_ctas) return fail(EB_ERR_NULLPTR, "mma_rate: null pointer");
+    if ((cta_group != 1 && cta_group != 2) || reps < 1) return fail(EB_ERR_INVALID_SHAPE, "mma_rate: cta_group=%d", cta_group);
+    MmaRateParams P{M, N, layout, reps, a_lbo, a_sbo, b_lbo, b_sbo, kstep_bytes, cycles};
+    const int smem = 96 * 1024;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() / cta_group * cta_group);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cta_group; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    *n_ctas = static_cast<int>(cfg.gridDim.x);
+    cudaError_t e;
+    if (cta_group == 2) {
+        if (int rc = set_smem(mma_rate_kernel<2>, smem)) return rc;
+        e = cudaLaunchKernelEx(&cfg, mma_rate_kernel<2>, P);
+    } else {
+        if (int rc = set_smem(mma_rate_kernel<1>, smem)) return rc;
+        e = cudaLaunchKernelEx(&cfg, mma_rate_kernel<1>, P);
+    }
+    if (e != cudaSuccess) return fail(EB_ERR_LAUNCH, "mma_rate: %s", cudaGetErrorString(e));
+    return check_launch("mma_rate");
+}
+
 size_t eb_packed_weight_bytes(int cin, int ktaps, int BN, int n_tiles_n) {
     return static_cast<size_t>(n_tiles_n) * BN * cin * ktaps * 2;
 }
@@ -265,7 +293,7 @@ int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksi
     P.wpack = static_cast<const __half*>(wpack);
     if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
     P.stats = stats;
-    { const char* e = getenv("EDVR_B200_DBG"); P.dbg = (stats != nullptr && e != nullptr) ? atoi(e) : 0; }
+    { const char* e = getenv("EDVR_B200_DBG"); P.dbg = e != nullptr ? atoi(e) : 0; }   // profiling switches (wrong results)
     return launch_conv(P, static_cast<cudaStream_t>(stream));
 }
 

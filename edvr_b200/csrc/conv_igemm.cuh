@@ -11,9 +11,10 @@
 //             per chunk instead of nine times.
 // B operand : weights pre-packed on the host in consumption order
 //             [n_tile][chunk][tap][kc=8][BN][8] fp16, streamed by 1-D bulk async copies.
-// Pipeline  : warp 0 B-producer | warp 1 MMA issuer | warps 2-5 A-producers |
-//             warps 6-9 epilogue; mbarrier rings; 2 x 256 TMEM columns so that the
-//             epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs.
+// Pipeline  : warp 0 B-producer | warp 1 MMA issuer | warps 2-5 A-producers (cp.async with zero-fill,
+//             completion tracked by the mbarrier, so a whole chunk is in flight per SM) |
+//             warps 6-13 epilogue (one 16x8 half of the tile each); mbarrier rings; 2 x 256 TMEM columns so
+//             that the epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs.
 #pragma once
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -21,13 +22,13 @@
 namespace eb {
 
 constexpr int CV_TILE = 16;
-constexpr int CV_A_BUFS = 2;
-constexpr int CV_B_STAGES = 6;
+constexpr int CV_A_BUFS = 3;
+constexpr int CV_B_STAGES = 5;
 constexpr int CV_PLANE_BYTES = 325 * 16;              // >= 18*18*16, odd # of 16B units
 constexpr int CV_A_BUF_BYTES = 8 * CV_PLANE_BYTES;    // 41600
 constexpr int CV_B_STAGE_BYTES = 128 * 128;           // BN(<=128) rows x 64 ch x 2 B
 constexpr int CV_MAX_COUT = 512;
-constexpr int CV_THREADS = 320;
+constexpr int CV_THREADS = 448;
 constexpr int CV_SMEM_BYTES = CV_A_BUFS * CV_A_BUF_BYTES + CV_B_STAGES * CV_B_STAGE_BYTES +
                               CV_MAX_COUT * 4 + 256;
 
@@ -50,42 +51,36 @@ struct ConvParams {
     const __half* wpack;
     EpiParams epi;
     unsigned long long* stats;   // optional [gridDim.x][16] cycle counters (profiling builds of the call only)
-    int dbg;                     // profiling only: bit0 skip epilogue global memory, bit1 skip phase 2, bit2 skip tmem loads
+    int dbg;                     // profiling only (results become wrong): 1 no epilogue global memory, 4 no epilogue at all,
+                                 // 8 no weight copies after the first ring fill, 16 same for activations, 32 no MMAs
 };
 
 template <int HALO>
 __device__ __forceinline__ void conv_load_halo(const ConvParams& P, int chunk, int img, int ty,
                                                int tx, uint32_t abuf_saddr, int tid) {
     constexpr int RP = CV_TILE + 2 * HALO;
-    constexpr int NITEM = RP * RP * 8;
-    constexpr int U = HALO ? 7 : 8;
+    constexpr int NPIX = RP * RP;
     // which source does this 64-channel chunk come from?
     int s = 0, ch = chunk * 64;
     if (P.nsrc > 1 && ch >= P.src[0].C) { s = 1; ch -= P.src[0].C; }
     const ConvSrc& S = P.src[s];
     const int simg = (img / S.div) * S.mul + (img % S.div) * S.keep + S.add;
-    const __half* base = S.ptr + S.ch_off + ch;
+    const int kc = tid & 7;                       // 16-byte K atom of this thread; 8 lanes = 128 contiguous bytes
+    const __half* base = S.ptr + S.ch_off + ch + kc * 8;
+    const __half* img_base = base + static_cast<size_t>(simg) * P.H * P.W * S.pix_stride;
     const int y0 = ty * CV_TILE - HALO, x0 = tx * CV_TILE - HALO;
-    for (int b = 0; b < NITEM; b += 128 * U) {
-        uint4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int idx = b + u * 128 + tid;
-            v[u] = make_uint4(0, 0, 0, 0);
-            if (idx < NITEM) {
-                const int p = idx >> 3, kc = idx & 7;
-                const int y = p / RP, x = p - y * RP;
-                const int gy = y0 + y, gx = x0 + x;
-                if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W)
-                    v[u] = ldg_nc_v4(base + ((static_cast<size_t>(simg) * P.H + gy) * P.W + gx) *
-                                                S.pix_stride + kc * 8);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int idx = b + u * 128 + tid;
-            if (idx < NITEM) sts_v4(abuf_saddr + (idx & 7) * CV_PLANE_BYTES + (idx >> 3) * 16, v[u]);
-        }
+    const int H = P.H, W = P.W, ps = S.pix_stride;
+    uint32_t dst = abuf_saddr + kc * CV_PLANE_BYTES + (tid >> 3) * 16;
+    int y = (tid >> 3) / RP, x = (tid >> 3) - y * RP;       // 16 pixels per step of the 128 threads
+#pragma unroll 4
+    for (int p = tid >> 3; p < NPIX; p += 16) {
+        const int gy = y0 + y, gx = x0 + x;
+        const bool in = (gy >= 0) & (gy < H) & (gx >= 0) & (gx < W);
+        const __half* g = in ? img_base + (static_cast<size_t>(gy) * W + gx) * ps : base;
+        cp_async16_zfill(dst, g, in ? 16u : 0u);
+        dst += 16 * 16;
+        x += 16;
+        if (x >= RP) { x -= RP; ++y; }
     }
 }
 
@@ -96,11 +91,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
     uint8_t* b_smem = smem + CV_A_BUFS * CV_A_BUF_BYTES;
     float* bias_s = reinterpret_cast<float*>(b_smem + CV_B_STAGES * CV_B_STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + CV_MAX_COUT);
-    uint64_t* a_full = bars;                    // [2]
-    uint64_t* a_empty = bars + 2;               // [2]
-    uint64_t* b_full = bars + 4;                // [6]
-    uint64_t* b_empty = bars + 4 + CV_B_STAGES; // [6]
-    uint64_t* acc_full = bars + 4 + 2 * CV_B_STAGES;   // [2]
+    uint64_t* a_full = bars;                                 // [CV_A_BUFS]
+    uint64_t* a_empty = bars + CV_A_BUFS;                    // [CV_A_BUFS]
+    uint64_t* b_full = bars + 2 * CV_A_BUFS;                 // [CV_B_STAGES]
+    uint64_t* b_empty = b_full + CV_B_STAGES;                // [CV_B_STAGES]
+    uint64_t* acc_full = b_empty + CV_B_STAGES;              // [2]
     uint64_t* acc_empty = acc_full + 2;                // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -121,9 +116,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
     if (has_bias)
         for (int i = threadIdx.x; i < cout_packed; i += blockDim.x) bias_s[i] = P.epi.bias[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < CV_A_BUFS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < CV_A_BUFS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < CV_B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -143,6 +138,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
                 for (int st = 0; st < nchunks * P.taps; ++st, ++it) {
                     const uint32_t s = it % CV_B_STAGES, ph = (it / CV_B_STAGES) & 1u;
                     mbar_wait(&b_empty[s], ph ^ 1u);
+                    if ((P.dbg & 8) && it >= CV_B_STAGES) { mbar_arrive(&b_full[s]); continue; }
                     mbar_arrive_expect_tx(&b_full[s], b_bytes);
                     bulk_g2s(b_smem + s * CV_B_STAGE_BYTES, w + static_cast<size_t>(st) * b_bytes,
                              b_bytes, &b_full[s]);
@@ -162,6 +158,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
                 for (int c = 0; c < nchunks; ++c, ++a_it) {
                     const uint32_t as = a_it % CV_A_BUFS, aph = (a_it / CV_A_BUFS) & 1u;
                     mbar_wait(&a_full[as], aph);
+                    fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
                     tc_fence_after_sync();
                     const uint32_t a_base = smem_u32(a_smem + as * CV_A_BUF_BYTES);
                     for (int t = 0; t < P.taps; ++t, ++b_it) {
@@ -179,7 +176,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
                                 const uint64_t ad = umma_desc_nosw(a_tap + k16 * 2 * CV_PLANE_BYTES,
                                                                    CV_PLANE_BYTES, RP * 16);
                                 const uint64_t bd = umma_desc_nosw(b_base + k16 * 2 * lbo_b, lbo_b, 128);
-                                umma_f16(d, ad, bd, idesc, (c | t | k16) != 0 ? 1u : 0u);
+                                if (!(P.dbg & 32)) umma_f16(d, ad, bd, idesc, (c | t | k16) != 0 ? 1u : 0u);
                             }
                         }
                         umma_commit(&b_empty[bs]);
@@ -199,15 +196,16 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
             for (int c = 0; c < nchunks; ++c, ++a_it) {
                 const uint32_t as = a_it % CV_A_BUFS, aph = (a_it / CV_A_BUFS) & 1u;
                 mbar_wait_warp(&a_empty[as], aph ^ 1u);
+                if ((P.dbg & 16) && a_it >= CV_A_BUFS) { mbar_arrive(&a_full[as]); continue; }
                 conv_load_halo<HALO>(P, c, img, ty, tx, smem_u32(a_smem + as * CV_A_BUF_BYTES), tid);
-                fence_proxy_async_smem();   // generic-proxy stores -> visible to the MMA (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[as]);
+                cp_async_mbar_arrive_noinc(&a_full[as]);   // arrives when this thread's copies have landed
             }
         }
     } else {
-        // ================= epilogue (128 threads == 128 TMEM lanes)
+        // ================= epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., warps 6-9 take the left 16x8 half
+        // of the tile (sub 0), warps 10-13 the right one
         const int q = warp & 3;
+        const int sub = (warp - 6) >> 2;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
             const int nt = tile % P.n_tiles_n, pt = tile / P.n_tiles_n;
@@ -216,17 +214,14 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
             mbar_wait_warp(&acc_full[ab], (acc_it >> 1) & 1u);
             tc_fence_after_sync();
             const int y = ty * CV_TILE + 4 * q + (lane >> 3);
+            const int x = tx * CV_TILE + 8 * sub + (lane & 7);
+            const bool valid = (y < P.H) && (x < P.W) && !(P.dbg & 1);
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 256u + sub * 128u;
 #pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-                const int x = tx * CV_TILE + 8 * sub + (lane & 7);
-                const bool valid = (y < P.H) && (x < P.W);
-                const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 256u + sub * 128u;
-#pragma unroll 1
-                for (int cc = 0; cc < P.BN; cc += 32) {
-                    float v[32];
-                    tmem_ld32(t0 + cc, v);
-                    epi_store32<EK>(P.epi, has_bias ? bias_s : nullptr, v, img, y, x, nt * P.BN + cc, valid);
-                }
+            for (int cc = 0; cc < ((P.dbg & 4) ? 0 : P.BN); cc += 32) {
+                float v[32];
+                tmem_ld32(t0 + cc, v);
+                epi_store32<EK>(P.epi, has_bias ? bias_s : nullptr, v, img, y, x, nt * P.BN + cc, valid);
             }
             tc_fence_before_sync();
             __syncwarp();

@@ -13,14 +13,14 @@ from ._lib import (ACT_DCN_PACK, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, OUT
 
 
 LAUNCHES = [0]      # number of libedvr_b200 kernel launches issued through this module (bench.py: gpu_launches)
-PROFILE = None      # when a list: (kernel name, algorithmic FLOPs, start event, end event) per call (bench.py)
+PROFILE = None      # when a list: (kernel name, algorithmic FLOPs, start event, end event, detail) per call (bench.py)
 
 
 class _Rec:
     """Counts launches and, when PROFILE is a list, brackets the call with CUDA events on the current stream."""
 
-    def __init__(self, name, kernels=1, flops=0.0):
-        self.name, self.kernels, self.flops = name, kernels, flops
+    def __init__(self, name, kernels=1, flops=0.0, detail=""):
+        self.name, self.kernels, self.flops, self.detail = name, kernels, flops, detail
 
     def __enter__(self):
         LAUNCHES[0] += self.kernels
@@ -33,7 +33,7 @@ class _Rec:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.append((self.name, self.flops, self.e0, self.e1))
+            PROFILE.append((self.name, self.flops, self.e0, self.e1, self.detail))
         return False
 
 
@@ -190,14 +190,19 @@ def conv2d(pc, srcs, out16=None, act=ACT_NONE, res16=None, res32=None, out32=Non
     assert sum(v.C for v in srcs) == pc.cin, (sum(v.C for v in srcs), pc.cin)
     e = _epi(pc.b, act, out16, out32, res16, res32, out_mode=out_mode, absmean=absmean)
     opix = N * v0.H * v0.W if out_mode != OUT_STRIDE2 else N * ((v0.H + 1) // 2) * ((v0.W + 1) // 2)
-    with _Rec(f"conv_igemm_{pc.ksize}x{pc.ksize}", 1, 2.0 * opix * pc.cout * pc.cin * pc.ksize * pc.ksize):
+    detail = ""
+    if PROFILE is not None:
+        detail = (f"{pc.cin}->{pc.cout} {N}x{v0.H}x{v0.W} act{act} mode{out_mode}"
+                  f"{' res16' if res16 is not None else ''}{' res32' if res32 is not None else ''}"
+                  f"{' out32' if out32 is not None else ''}{' pack' if absmean is not None else ''}")
+    with _Rec(f"conv_igemm_{pc.ksize}x{pc.ksize}", 1, 2.0 * opix * pc.cout * pc.cin * pc.ksize * pc.ksize, detail):
         L.check(L.lib().eb_conv2d(arr, len(srcs), N, v0.H, v0.W, pc.ksize, L.ptr(pc.w), pc.BN, pc.n_tiles,
                                   ctypes.byref(e), L.stream_ptr()), "eb_conv2d")
 
 
 def dcn_nhwc(pc, x, offpack, dg, out16=None, act=ACT_NONE, out_nchw=None, nchw_C=0):
     e = _epi(pc.b, act, out16, out_nchw=out_nchw, nchw_C=nchw_C)
-    with _Rec("dcn_fused", 1, 2.0 * x.N * x.H * x.W * pc.cout * pc.cin * 9):
+    with _Rec("dcn_fused", 1, 2.0 * x.N * x.H * x.W * pc.cout * pc.cin * 9, f"{x.N}x{x.H}x{x.W} C{x.C}"):
         L.check(L.lib().eb_dcn_nhwc(L.ptr(x.t), x.pix_stride, x.ch_off, x.N, x.H, x.W, x.C, dg, L.ptr(offpack.t),
                                     offpack.pix_stride, L.ptr(pc.w), pc.BN, pc.n_tiles, ctypes.byref(e),
                                     L.stream_ptr()), "eb_dcn_nhwc")

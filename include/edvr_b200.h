@@ -77,6 +77,11 @@ const char* eb_last_error(void);      /* thread-local text of the last non-zero 
 /* ---- hardware self-test: D[128,N] = A[128,K] * B[N,K]^T through tcgen05 (fp16 in, fp32 out).
  * variant 0 is the production descriptor convention; other values probe alternatives. */
 int eb_selftest_umma(const void* A, const void* B, float* D, int N, int K, int variant, void* stream);
+/* Hardware probe (no reference counterpart): cycles per tcgen05.mma for a shape / shared-memory layout / CTA-group
+ * choice, `reps` back-to-back MMAs on zeroed operands on every SM; cycles[i] = total cycles seen by CTA i's issuer
+ * (0 for non-issuing CTAs of a pair).  layout: 0 no-swizzle planes, 2/4/6 = 128/64/32-byte swizzle. */
+int eb_selftest_mma_rate(int cta_group, int M, int N, int layout, int a_lbo, int a_sbo, int b_lbo, int b_sbo,
+                         int kstep_bytes, int reps, unsigned long long* cycles, int* n_ctas, void* stream);
 
 /* ---- weight packing (device side; fp32 OIHW -> fp16 MMA-ready stages) ------------------
  * layout [n_tile][s1][s2][kc=8][BN][8]; tap_major=1: s1=tap,s2=chunk (DCN); 0: s1=chunk,s2=tap.

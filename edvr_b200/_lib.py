@@ -40,6 +40,10 @@ _SIGS = {
                           ctypes.POINTER(Epilogue), c_void_p]),
     "eb_conv2d_stats": (c_int, [ctypes.POINTER(Src), c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                 ctypes.POINTER(Epilogue), c_void_p, c_void_p]),
+    "eb_conv2d_pair_supported": (c_int, [c_int] * 4),
+    "eb_pack_weight_pair": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "eb_conv2d_pair": (c_int, [ctypes.POINTER(Src), c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                               ctypes.POINTER(Epilogue), c_void_p]),
     "eb_dcn_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                             c_void_p, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
     "eb_mdcn_forward_workspace": (c_size_t, [c_int] * 7),

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "conv_igemm.cuh"
 #include "conv_igemm2.cuh"
+#include "conv_pair.cuh"
 #include "dcn_backward.cuh"
 #include "dcn_fused.cuh"
 #include "elementwise.cuh"
@@ -168,6 +169,59 @@ int eb_pack_weight(const float* w, int cout, int cin, int ktaps, const int* row_
     return check_launch("pack_weight");
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*eb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static eb_encode_tiled_fn tensor_map_encoder() {
+    static eb_encode_tiled_fn fn = []() -> eb_encode_tiled_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<eb_encode_tiled_fn>(p);
+    }();
+    return fn;
+}
+
+// NHWC fp16 view as a 5-D tensor {8 channels, W, H, pix_stride / 8 K-atoms, images}; box = halo tile of 4 K-atoms
+static int encode_halo_map(const ConvSrc& S, int H, int W, int n_images, CUtensorMap* out) {
+    eb_encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return fail(EB_ERR_UNSUPPORTED, "conv2d_pair: cuTensorMapEncodeTiled unavailable");
+    const cuuint64_t ps = static_cast<cuuint64_t>(S.pix_stride);
+    const cuuint64_t dims[5] = {8, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), ps / 8, static_cast<cuuint64_t>(n_images)};
+    const cuuint64_t strides[4] = {ps * 2, static_cast<cuuint64_t>(W) * ps * 2, 16, static_cast<cuuint64_t>(H) * W * ps * 2};
+    const cuuint32_t box[5] = {8, CP_RP, CP_RP, 4, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(S.ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "conv2d_pair: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+    return EB_OK;
+}
+
+int eb_pack_weight_pair(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN, int n_tiles_n,
+                        void* wpack, void* stream) {
+    if (!w || !wpack) return fail(EB_ERR_NULLPTR, "pack_weight_pair: null pointer");
+    if (cin % 64 || BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || ktaps < 1 || cout < 1)
+        return fail(EB_ERR_INVALID_SHAPE, "pack_weight_pair: cin=%d BN=%d tiles=%d taps=%d", cin, BN, n_tiles_n, ktaps);
+    if (!row_map && cout > BN * n_tiles_n) return fail(EB_ERR_INVALID_SHAPE, "pack_weight_pair: cout exceeds packed rows");
+    const long long groups = static_cast<long long>(n_tiles_n) * BN * (cin / 8) * ktaps;
+    pack_weight_pair_kernel<<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, cout, cin, ktaps, row_map, BN, n_tiles_n, static_cast<__half*>(wpack));
+    return check_launch("pack_weight_pair");
+}
+
+int eb_conv2d_pair_supported(int cin, int ksize, int BN, int n_tiles_n) {
+    // 1x1 layers have too little work per 32-channel stage for this pipeline (measured slower than conv_igemm)
+    if (cin < 64 || cin % 64 || ksize != 3 || BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1) return 0;
+    if (static_cast<long long>(cin) * ksize * ksize * (BN / 2) * 2 > CP_W_BYTES) return 0;
+    return (n_tiles_n <= num_sms() / 2 && tensor_map_encoder() != nullptr) ? 1 : 0;
+}
+
 static bool conv_force_v1() {
     const char* e = getenv("EDVR_B200_CONV_V1");     // A/B switch for profiling; read-only, no mutable state
     return e != nullptr && e[0] == '1';
@@ -262,29 +316,26 @@ static int launch_conv(const ConvParams& P, cudaStream_t st) {
     return check_launch("conv_igemm");
 }
 
-int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack, int BN,
-              int n_tiles_n, const eb_epilogue_t* epi, void* stream) {
-    return eb_conv2d_stats(srcs, nsrc, N, H, W, ksize, wpack, BN, n_tiles_n, epi, nullptr, stream);
-}
-
-int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack, int BN,
-                    int n_tiles_n, const eb_epilogue_t* epi, unsigned long long* stats, void* stream) {
-    if (!srcs || !wpack) return fail(EB_ERR_NULLPTR, "conv2d: null pointer");
-    if (nsrc < 1 || nsrc > 2) return fail(EB_ERR_UNSUPPORTED, "conv2d: nsrc=%d", nsrc);
-    if (ksize != 1 && ksize != 3) return fail(EB_ERR_UNSUPPORTED, "conv2d: ksize=%d", ksize);
-    if (N < 0 || H < 1 || W < 1) return fail(EB_ERR_INVALID_SHAPE, "conv2d: N=%d H=%d W=%d", N, H, W);
-    if (BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || (epi && epi->bias && BN * n_tiles_n > CV_MAX_COUT))
-        return fail(EB_ERR_INVALID_SHAPE, "conv2d: BN=%d n_tiles_n=%d", BN, n_tiles_n);
-    if (!al16(wpack)) return fail(EB_ERR_ALIGNMENT, "conv2d: wpack must be 16-byte aligned");
-    ConvParams P;
+static int build_conv_params(const char* who, const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize,
+                             const void* wpack, int BN, int n_tiles_n, const eb_epilogue_t* epi, bool bias_in_smem_table,
+                             ConvParams* out) {
+    if (!srcs || !wpack) return fail(EB_ERR_NULLPTR, "%s: null pointer", who);
+    if (nsrc < 1 || nsrc > 2) return fail(EB_ERR_UNSUPPORTED, "%s: nsrc=%d", who, nsrc);
+    if (ksize != 1 && ksize != 3) return fail(EB_ERR_UNSUPPORTED, "%s: ksize=%d", who, ksize);
+    if (N < 0 || H < 1 || W < 1) return fail(EB_ERR_INVALID_SHAPE, "%s: N=%d H=%d W=%d", who, N, H, W);
+    if (BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 ||
+        (bias_in_smem_table && epi && epi->bias && BN * n_tiles_n > CV_MAX_COUT))
+        return fail(EB_ERR_INVALID_SHAPE, "%s: BN=%d n_tiles_n=%d", who, BN, n_tiles_n);
+    if (!al16(wpack)) return fail(EB_ERR_ALIGNMENT, "%s: wpack must be 16-byte aligned", who);
+    ConvParams& P = *out;
     memset(&P, 0, sizeof(P));
     for (int i = 0; i < nsrc; ++i) {
         const eb_src_t& s = srcs[i];
-        if (!s.ptr) return fail(EB_ERR_NULLPTR, "conv2d: src %d null", i);
-        if (s.C < 64 || s.C % 64) return fail(EB_ERR_INVALID_SHAPE, "conv2d: src %d C=%d (multiple of 64)", i, s.C);
+        if (!s.ptr) return fail(EB_ERR_NULLPTR, "%s: src %d null", who, i);
+        if (s.C < 64 || s.C % 64) return fail(EB_ERR_INVALID_SHAPE, "%s: src %d C=%d (multiple of 64)", who, i, s.C);
         if (!al16(s.ptr) || s.pix_stride % 8 || s.ch_off % 8 || s.pix_stride < s.C + s.ch_off)
-            return fail(EB_ERR_ALIGNMENT, "conv2d: src %d view (stride %d, off %d)", i, s.pix_stride, s.ch_off);
-        if (s.div < 1) return fail(EB_ERR_INVALID_SHAPE, "conv2d: src %d div=%d", i, s.div);
+            return fail(EB_ERR_ALIGNMENT, "%s: src %d view (stride %d, off %d)", who, i, s.pix_stride, s.ch_off);
+        if (s.div < 1) return fail(EB_ERR_INVALID_SHAPE, "%s: src %d div=%d", who, i, s.div);
         P.src[i].ptr = static_cast<const __half*>(s.ptr);
         P.src[i].C = s.C; P.src[i].pix_stride = s.pix_stride; P.src[i].ch_off = s.ch_off;
         P.src[i].div = s.div; P.src[i].mul = s.mul; P.src[i].keep = s.keep; P.src[i].add = s.add;
@@ -292,9 +343,101 @@ int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksi
     P.nsrc = nsrc; P.N = N; P.H = H; P.W = W; P.taps = ksize * ksize; P.BN = BN; P.n_tiles_n = n_tiles_n;
     P.wpack = static_cast<const __half*>(wpack);
     if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
-    P.stats = stats;
     { const char* e = getenv("EDVR_B200_DBG"); P.dbg = e != nullptr ? atoi(e) : 0; }   // profiling switches (wrong results)
+    return EB_OK;
+}
+
+int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack, int BN,
+              int n_tiles_n, const eb_epilogue_t* epi, void* stream) {
+    return eb_conv2d_stats(srcs, nsrc, N, H, W, ksize, wpack, BN, n_tiles_n, epi, nullptr, stream);
+}
+
+int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack, int BN,
+                    int n_tiles_n, const eb_epilogue_t* epi, unsigned long long* stats, void* stream) {
+    ConvParams P;
+    if (int rc = build_conv_params("conv2d", srcs, nsrc, N, H, W, ksize, wpack, BN, n_tiles_n, epi, true, &P)) return rc;
+    P.stats = stats;
     return launch_conv(P, static_cast<cudaStream_t>(stream));
+}
+
+// CTA-pair kernel with shared-memory-resident weights (conv_pair.cuh); `wpair` comes from eb_pack_weight_pair.
+int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpair, int BN,
+                   int n_tiles_n, const eb_epilogue_t* epi, void* stream) {
+    ConvParams P;
+    if (int rc = build_conv_params("conv2d_pair", srcs, nsrc, N, H, W, ksize, wpair, BN, n_tiles_n, epi, false, &P)) return rc;
+    const int cin = P.src[0].C + (nsrc > 1 ? P.src[1].C : 0);
+    if (!eb_conv2d_pair_supported(cin, ksize, BN, n_tiles_n))
+        return fail(EB_ERR_UNSUPPORTED, "conv2d_pair: cin=%d k=%d BN=%d tiles=%d (weights must fit %d bytes per CTA)", cin, ksize,
+                    BN, n_tiles_n, CP_W_BYTES);
+    if (N == 0) return EB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long pair_tiles = static_cast<long long>(N) * ((H + 15) / 16) * (((W + 15) / 16 + 1) / 2);
+    long long want = pair_tiles * n_tiles_n;
+    const int max_clusters = num_sms() / 2;
+    int nclusters = static_cast<int>(want < max_clusters ? want : max_clusters);
+    nclusters = nclusters / n_tiles_n * n_tiles_n;
+    if (nclusters < n_tiles_n) nclusters = n_tiles_n;
+    int ek1 = EK_GENERIC;
+    {
+        const EpiParams& e = P.epi;
+        const bool plain_out = e.out16 && !e.out32 && !e.res32 && !e.out_nchw;
+        if (e.out_mode == OUT_PIXSHUF2) ek1 = EK_PIXSHUF;
+        else if (e.out_mode == OUT_STRIDE2) ek1 = EK_STRIDE2;
+        else if (e.act == ACT_DCN_PACK) { if (plain_out && !e.res16) ek1 = EK_PACK; }
+        else if (plain_out) ek1 = EK_PLAIN;
+        else if ((e.out32 || e.res32) && !e.res16 && !e.out_nchw) ek1 = EK_F32;
+    }
+    PairParams PP;
+    PP.c = P;
+    for (int i = 0; i < nsrc; ++i) {
+        const ConvSrc& S = P.src[i];
+        const int last = N - 1;       // largest source image index the kernel can ask for
+        const int n_images = (last / S.div) * S.mul + ((last < S.div ? last : S.div - 1)) * (S.keep > 0 ? S.keep : 0) + S.add + 1;
+        if (int rc = encode_halo_map(S, H, W, n_images < 1 ? 1 : n_images, &PP.tmap[i])) return rc;
+    }
+    if (nsrc == 1) PP.tmap[1] = PP.tmap[0];
+    // fp16 NHWC output through TMA when the epilogue writes it pixel-for-pixel (plain / fp32-stream / DCN-record kinds)
+    PP.tma_out = 0;
+    PP.tmap_out = PP.tmap[0];
+    if ((ek1 == EK_PLAIN || ek1 == EK_F32 || ek1 == EK_PACK) && P.epi.out16 != nullptr && !(P.dbg & 64)) {
+        eb_encode_tiled_fn enc = tensor_map_encoder();
+        const cuuint64_t ps = static_cast<cuuint64_t>(P.epi.out16_pix_stride);
+        const cuuint64_t dims[4] = {ps, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+        const cuuint64_t strides[3] = {ps * 2, static_cast<cuuint64_t>(W) * ps * 2, static_cast<cuuint64_t>(H) * W * ps * 2};
+        const cuuint32_t box[4] = {32, 8, 4, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = enc(&PP.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, P.epi.out16, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "conv2d_pair: output tensor map failed (%d)", static_cast<int>(r));
+        PP.tma_out = 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * nclusters);
+    cfg.blockDim = dim3(CP_THREADS);
+    cfg.dynamicSmemBytes = CP_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t err = cudaSuccess;
+#define EB_LAUNCH_CP(EK_, TO_)                                                                         \
+    do {                                                                                               \
+        if (int rc = set_smem(conv_pair_kernel<EK_, TO_>, CP_SMEM_BYTES)) return rc;                   \
+        err = cudaLaunchKernelEx(&cfg, conv_pair_kernel<EK_, TO_>, PP);                                \
+    } while (0)
+    switch (ek1) {
+        case EK_PLAIN: if (PP.tma_out) EB_LAUNCH_CP(EK_PLAIN, true); else EB_LAUNCH_CP(EK_PLAIN, false); break;
+        case EK_F32: if (PP.tma_out) EB_LAUNCH_CP(EK_F32, true); else EB_LAUNCH_CP(EK_F32, false); break;
+        case EK_PACK: if (PP.tma_out) EB_LAUNCH_CP(EK_PACK, true); else EB_LAUNCH_CP(EK_PACK, false); break;
+        case EK_PIXSHUF: EB_LAUNCH_CP(EK_PIXSHUF, false); break;
+        case EK_STRIDE2: EB_LAUNCH_CP(EK_STRIDE2, false); break;
+        default: EB_LAUNCH_CP(EK_GENERIC, false); break;
+    }
+#undef EB_LAUNCH_CP
+    if (err != cudaSuccess) return fail(EB_ERR_LAUNCH, "conv2d_pair: %s", cudaGetErrorString(err));
+    return check_launch("conv_pair");
 }
 
 static int launch_dcn(DcnParams& P, cudaStream_t st) {

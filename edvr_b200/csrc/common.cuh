@@ -76,6 +76,25 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_t<0>(bar, parity); }
 
+// Same, observing arrivals made by the other CTA of the cluster (acquire at cluster scope).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (spin == 64) t0 = clock64();
+        if (spin > 64 && (spin & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
 // Whole-warp wait.  Every lane polls: electing one lane + __syncwarp (and try_wait suspend-time hints) measured
 // 20-50 % SLOWER on B200 (profiles/r01_conv_stats_warp_elected.log) - the wake-up latency dominates.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
@@ -188,6 +207,75 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t targe
         ::"r"(smem_u32(bar)), "r"(target)
         : "memory");
 }
+// ---- lean issue path.  The MMA warp runs its loops with all 32 lanes converged and elects ONE lane per instruction:
+// written like this the compiler keeps descriptors in uniform registers.  Issued from inside an `if (lane == 0)` region
+// every MMA was wrapped in an election loop with 2-3 R2UR transfers (~15 dependent instructions, ~130 cycles per MMA
+// for a 64-cycle MMA: the tensor pipe starved on issue, not on data; profiles/r01_one_conv_dbg.log).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// descriptor = {lo: start address >> 4 | LBO >> 4 << 16, hi: SBO >> 4 | version 1 << 14 | layout << 29}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+template <int CG>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+    if (CG == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+
+// ---- TMA (tensor-map bulk copies), CTA-pair flavour: the copy lands in THIS CTA's shared memory, its bytes are
+// counted on the mbarrier at the same offset in the EVEN CTA of the pair (the one that issues the MMAs).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address
+__device__ __forceinline__ void tma_load_5d_pair(void* dst_smem, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask),
+          "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+// arrive + expect `bytes` on the mbarrier at the same offset in CTA `target` of the cluster
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint64_t* bar, uint32_t bytes, uint32_t target) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(target), "r"(bytes)
+        : "memory");
+}
+// shared -> global tile store (bulk async group of the issuing thread); out-of-range parts of the box are clipped
+__device__ __forceinline__ void tma_store_4d(const void* tmap, const void* src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
 // Shared-memory matrix descriptor with a swizzled K-major layout (rows of 32/64/128 bytes, 8-row groups SBO apart):
 // layout type 2 = 128 B, 4 = 64 B, 6 = 32 B swizzle.
 __device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {

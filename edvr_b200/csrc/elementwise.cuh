@@ -82,6 +82,35 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
         h8_store(out + i * 8, v);
     }
 }
+// CTA-pair kernel (conv_pair.cuh): [nt][rank 2][chunk of 32 ch][tap][k16 step 2][plane 2][BN/2 rows][8] fp16 - each
+// CTA of a pair keeps its half of the output channels resident, K steps in consumption order.
+__global__ void pack_weight_pair_kernel(const float* __restrict__ w, int cout, int cin, int ktaps,
+                                        const int* __restrict__ row_map, int BN, int n_tiles_n,
+                                        __half* __restrict__ out) {
+    const int nchunks = cin / 32, half = BN / 2;
+    const long long total = static_cast<long long>(n_tiles_n) * 2 * nchunks * ktaps * 4 * half;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int row = r % half; r /= half;
+        const int plane = r % 2; r /= 2;
+        const int h = r % 2; r /= 2;
+        const int tap = r % ktaps; r /= ktaps;
+        const int chunk = r % nchunks; r /= nchunks;
+        const int rank = r % 2; r /= 2;
+        const int nt = static_cast<int>(r);
+        const int prow = nt * BN + rank * half + row;
+        int srow = row_map ? row_map[prow] : prow;
+        if (srow >= cout) srow = -1;
+        H8 v;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ci = chunk * 32 + h * 16 + plane * 8 + e;
+            v.v[e] = srow >= 0 ? w[(static_cast<size_t>(srow) * cin + ci) * ktaps + tap] : 0.f;
+        }
+        h8_store(out + i * 8, v);
+    }
+}
 __global__ void pack_bias_kernel(const float* __restrict__ b, int cout, const int* __restrict__ row_map,
                                  int n_packed, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -49,7 +49,8 @@ __host__ __device__ __forceinline__ long long blocked32_block(int img, int y, in
 
 // v: 32 consecutive accumulator channels [c0, c0+32) of output pixel (img, y, x).
 // Every lane of the warp must call this (shuffles inside); `valid` masks the memory traffic.
-template <int EK = EK_GENERIC>
+// EXT16: the caller stores the fp16 NHWC copy itself (TMA store in conv_pair.cuh); v[] holds the final values on return.
+template <int EK = EK_GENERIC, bool EXT16 = false>
 __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __restrict__ bias_s,
                                             float (&v)[32], int img, int y, int x, int c0,
                                             bool valid) {
@@ -102,7 +103,7 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
     }
 
     if ((G && p.out_mode == OUT_SAME) || EK == EK_PLAIN || EK == EK_F32 || EK == EK_PACK || EK == EK_NCHW) {
-        if (EK != EK_NCHW && p.out16 != nullptr) {
+        if (!EXT16 && EK != EK_NCHW && p.out16 != nullptr) {
             uint4* o = reinterpret_cast<uint4*>(p.out16 + pix * p.out16_pix_stride + p.out16_ch_off + c0);
 #pragma unroll
             for (int q = 0; q < 4; ++q)

@@ -4,6 +4,7 @@ PyTorch is used only for device memory and the current CUDA stream; every comput
 through libedvr_b200.so (edvr_b200/_lib.py) with raw pointers.
 """
 import ctypes
+import os
 
 import torch
 
@@ -13,6 +14,7 @@ from ._lib import (ACT_DCN_PACK, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, OUT
 
 
 LAUNCHES = [0]      # number of libedvr_b200 kernel launches issued through this module (bench.py: gpu_launches)
+USE_PAIR = True     # route eligible convolutions to the CTA-pair kernel (conv_pair.cuh)
 PROFILE = None      # when a list: (kernel name, algorithmic FLOPs, start event, end event, detail) per call (bench.py)
 
 
@@ -68,7 +70,7 @@ def new_act(N, H, W, C, device="cuda"):
 class PackedConv:
     """MMA-ready fp16 weights + fp32 bias of one convolution (see eb_pack_weight)."""
 
-    __slots__ = ("w", "b", "BN", "n_tiles", "cin", "ksize", "cout")
+    __slots__ = ("w", "b", "BN", "n_tiles", "cin", "ksize", "cout", "wpair")
 
 
 def _choose_bn(cout_packed):
@@ -100,6 +102,13 @@ def pack_conv(weight, bias=None, row_map=None, tap_major=False, cout_packed=None
     with _Rec("pack_weight", 1):
         L.check(L.lib().eb_pack_weight(L.ptr(weight), cout, cin, k * k, L.ptr(rm), p.BN, p.n_tiles,
                                        1 if tap_major else 0, L.ptr(p.w), L.stream_ptr()), "eb_pack_weight")
+    p.wpair = None
+    if not tap_major and L.lib().eb_conv2d_pair_supported(cin, k, p.BN, p.n_tiles):
+        # second packing for the CTA-pair kernel (weights resident in shared memory), see conv_pair.cuh
+        p.wpair = torch.empty(nbytes // 2, dtype=torch.float16, device=weight.device)
+        with _Rec("pack_weight", 1):
+            L.check(L.lib().eb_pack_weight_pair(L.ptr(weight), cout, cin, k * k, L.ptr(rm), p.BN, p.n_tiles,
+                                                L.ptr(p.wpair), L.stream_ptr()), "eb_pack_weight_pair")
     b = torch.zeros(cout_packed, dtype=torch.float32, device=weight.device)
     if bias is not None:
         if rm is None:
@@ -196,8 +205,12 @@ def conv2d(pc, srcs, out16=None, act=ACT_NONE, res16=None, res32=None, out32=Non
                   f"{' res16' if res16 is not None else ''}{' res32' if res32 is not None else ''}"
                   f"{' out32' if out32 is not None else ''}{' pack' if absmean is not None else ''}")
     with _Rec(f"conv_igemm_{pc.ksize}x{pc.ksize}", 1, 2.0 * opix * pc.cout * pc.cin * pc.ksize * pc.ksize, detail):
-        L.check(L.lib().eb_conv2d(arr, len(srcs), N, v0.H, v0.W, pc.ksize, L.ptr(pc.w), pc.BN, pc.n_tiles,
-                                  ctypes.byref(e), L.stream_ptr()), "eb_conv2d")
+        if pc.wpair is not None and USE_PAIR and os.environ.get("EDVR_B200_CONV_PAIR", "1") != "0":
+            L.check(L.lib().eb_conv2d_pair(arr, len(srcs), N, v0.H, v0.W, pc.ksize, L.ptr(pc.wpair), pc.BN, pc.n_tiles,
+                                           ctypes.byref(e), L.stream_ptr()), "eb_conv2d_pair")
+        else:
+            L.check(L.lib().eb_conv2d(arr, len(srcs), N, v0.H, v0.W, pc.ksize, L.ptr(pc.w), pc.BN, pc.n_tiles,
+                                      ctypes.byref(e), L.stream_ptr()), "eb_conv2d")
 
 
 def dcn_nhwc(pc, x, offpack, dg, out16=None, act=ACT_NONE, out_nchw=None, nchw_C=0):

@@ -97,6 +97,15 @@ int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, co
 int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack,
                     int BN, int n_tiles_n, const eb_epilogue_t* epi, unsigned long long* stats, void* stream);
 
+/* Same convolution on CTA pairs (tcgen05 cta_group::2) with the weights resident in shared memory: available when
+ * eb_conv2d_pair_supported() returns 1 (Cin * ksize^2 * BN <= 147456, e.g. 128 -> 128 3x3).  `wpair` is produced by
+ * eb_pack_weight_pair (same size as eb_packed_weight_bytes); sources, epilogue and results as eb_conv2d. */
+int eb_conv2d_pair_supported(int cin, int ksize, int BN, int n_tiles_n);
+int eb_pack_weight_pair(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN, int n_tiles_n,
+                        void* wpair, void* stream);
+int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpair, int BN,
+                   int n_tiles_n, const eb_epilogue_t* epi, void* stream);
+
 /* Tile-blocked fp32 layout of the trunk's residual stream (private to this library: written by eb_tsa_modulate or a
  * conv epilogue, read/updated in place by eb_conv2d epilogues).  Pixels are grouped exactly as the pixel-major conv
  * epilogue owns them (16x16 tiles -> two 16x8 halves -> four 32-pixel quarters -> 32-channel chunks), so that every

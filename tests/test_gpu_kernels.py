@@ -69,13 +69,15 @@ CONV_CASES = [
 ]
 
 
-@pytest.fixture(params=["v2_transposed", "v1_pixel_major"])
+@pytest.fixture(params=["v2_transposed", "v1_pixel_major", "cta_pair"])
 def conv_variant(request, monkeypatch):
-    """Cout tiles of 128 may run conv_igemm2 (channel-major accumulator; picked automatically for long K loops and
-    PixelShuffle stores, forced here with EDVR_B200_CONV_V2=1) or the pixel-major kernel (EDVR_B200_CONV_V1=1), which
-    also serves every other tile width.  Both must pass the same cases."""
+    """Three kernels serve the dense convolutions and must pass the same cases: conv_igemm2 (channel-major accumulator,
+    Cout tiles of 128; forced with EDVR_B200_CONV_V2=1), the pixel-major kernel (EDVR_B200_CONV_V1=1, every tile width)
+    and the CTA-pair kernel with resident weights (conv_pair.cuh; default whenever the weights fit in shared memory,
+    switched off with EDVR_B200_CONV_PAIR=0 - shapes it does not cover fall through to the automatic choice)."""
+    monkeypatch.setenv("EDVR_B200_CONV_PAIR", "1" if request.param == "cta_pair" else "0")
     monkeypatch.setenv("EDVR_B200_CONV_V1", "1" if request.param == "v1_pixel_major" else "0")
-    monkeypatch.setenv("EDVR_B200_CONV_V2", "0" if request.param == "v1_pixel_major" else "1")
+    monkeypatch.setenv("EDVR_B200_CONV_V2", "1" if request.param == "v2_transposed" else "0")
     return request.param
 
 

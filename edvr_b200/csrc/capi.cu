@@ -441,6 +441,8 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
 }
 
 static int launch_dcn(DcnParams& P, cudaStream_t st) {
+    P.x_wide = (P.cpg % 16 == 0 && P.x_pix_stride % 16 == 0 && P.x_ch_off % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(P.x) % 32 == 0 && getenv("EDVR_B200_DCN_NARROW") == nullptr) ? 1 : 0;
     const long long tiles = static_cast<long long>(P.N) * ((P.Ho + DC_TILE_H - 1) / DC_TILE_H) *
                             ((P.Wo + DC_TILE_W - 1) / DC_TILE_W) * P.n_tiles_n;
     if (tiles == 0) return EB_OK;

@@ -334,6 +334,12 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t saddr, const void* g, 
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// 32-byte read-only load (sm_100: LDG.256); p must be 32-byte aligned
+__device__ __forceinline__ void ldg_nc_v8(const void* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
 __device__ __forceinline__ void sts_v4(uint32_t saddr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y),
                  "r"(v.z), "r"(v.w)

@@ -40,6 +40,7 @@ enum : int { OFF_NCHW_F32 = 0, OFF_PACK_F16 = 1 };
 struct DcnParams {
     const __half* x;          // NHWC fp16 [N][H][W][C] view
     int x_pix_stride, x_ch_off;
+    int x_wide;               // 1: every (pixel, 16-channel group) of the view is 32-byte aligned -> one LDG.256 per corner
     int N, H, W, C;
     int Ho, Wo;
     int kh, kw, stride, pad, dil;   // along H
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
         const float* const msk_f = P.mask;
         const __half* const off_h = P.offpack;
         const long long ops = P.offpack_pix_stride;
+        const bool wide = P.x_wide != 0;
 
         struct Pix { int m, hb, wb; bool ok; const __half* rec; const float* ob; const float* mb; };
         auto fetch = [&](const Pix& px, int g, int tap) -> DcnOff {
@@ -302,6 +304,21 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                     }
                     // all 16 corner loads in flight before anything is consumed
                     uint4 u[2][2][4];
+                    if (wide && !two) {
+                        // the lane's two K atoms (one deformable group, 32 contiguous bytes) in ONE load per corner: the four
+                        // lanes of a pixel fetch a full 128-byte line per instruction (half the L1 wavefronts of 2 x LDG.128)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const DcnCorner& c = cn[i][0];
+                            const __half* b = c.base + ch;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) u[i][0][k] = u[i][1][k] = make_uint4(0, 0, 0, 0);
+                            if (c.valid & 1u) ldg_nc_v8(b, u[i][0][0], u[i][1][0]);
+                            if (c.valid & 2u) ldg_nc_v8(b + c.dW, u[i][0][1], u[i][1][1]);
+                            if (c.valid & 4u) ldg_nc_v8(b + c.dH, u[i][0][2], u[i][1][2]);
+                            if (c.valid & 8u) ldg_nc_v8(b + c.dH + c.dW, u[i][0][3], u[i][1][3]);
+                        }
+                    } else
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
 #pragma unroll

@@ -154,47 +154,64 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                 const uint32_t w_lo0 = umma_desc_lo(smem_u32(w_smem), lbo_b);
                 const uint32_t a_hi = umma_desc_hi(RP * 16), b_hi = umma_desc_hi(128);
                 const uint32_t b_step = (2u * lbo_b) >> 4;                 // one K16 step of the resident weights
+                // Waits are software-pipelined: everything stage n+1 needs (its TMA boxes; at a tile boundary the drained
+                // accumulator; on the first tile the weight group) is awaited in the MIDDLE of issuing stage n, while ~20 MMAs
+                // are still queued - the barrier round trip no longer leaves the tensor pipe idle between stages.
                 uint32_t a_it = 0, acc_it = 0;
-                bool first = true;
+                auto wait_stage = [&](int c, uint32_t ait, uint32_t accit, bool first_tile) {
+                    if (c == 0) mbar_wait_cluster(&acc_empty[accit & 1u], ((accit >> 1) & 1u) ^ 1u);
+                    if (first_tile && c % cpg == 0) mbar_wait_cluster(&w_full[c / cpg], 0);
+                    mbar_wait_cluster(&a_full[ait % CP_A_STAGES], (ait / CP_A_STAGES) & 1u);
+                };
+                if (ci < total_pt) wait_stage(0, 0, 0, true);
                 for (int t = ci; t < total_pt; t += cpn, ++acc_it) {
                     const uint32_t ab = acc_it & 1u;
-                    mbar_wait_cluster(&acc_empty[ab], ((acc_it >> 1) & 1u) ^ 1u);
-                    tc_fence_after_sync();
+                    const bool first = t == ci;
                     const uint32_t d0 = tmem_base + ab * 256u;
-                    uint32_t b_lo = w_lo0;
                     for (int c = 0; c < nchunks; ++c, ++a_it) {
-                        if (first && c % cpg == 0) mbar_wait_cluster(&w_full[c / cpg], 0);
-                        const uint32_t as = a_it % CP_A_STAGES, aph = (a_it / CP_A_STAGES) & 1u;
-                        mbar_wait_cluster(&a_full[as], aph);
+                        const uint32_t as = a_it % CP_A_STAGES;
                         tc_fence_after_sync();
                         const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_smem + as * CP_A_STAGE_BYTES), CP_PLANE_BYTES);
-                        if (P.dbg & 32) {
-                            if (elect_one()) {
-                                umma_commit_pair(&a_empty[as], 3);
-                                if (c == nchunks - 1) umma_commit_pair(&acc_full[ab], 3);
-                            }
-                        } else if (elect_one()) {
+                        const uint32_t b_lo0 = w_lo0 + static_cast<uint32_t>(c) * 18u * b_step;
+                        const bool skip = (P.dbg & 32) != 0;
+                        if (!skip && elect_one()) {
                             uint32_t acc = c != 0 ? 1u : 0u;
 #pragma unroll
-                            for (int tp = 0; tp < 9; ++tp) {
+                            for (int tp = 0; tp < 5; ++tp) {
                                 const int ki = tp / 3, kj = tp % 3;
 #pragma unroll
                                 for (int h = 0; h < 2; ++h) {
                                     const uint32_t a_lo = a_lo0 + (ki * RP + kj) + h * (2 * CP_PLANE_BYTES / 16);
+                                    const uint32_t b_lo = b_lo0 + (tp * 2 + h) * b_step;
                                     umma_f16_lohi<2>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc);
                                     umma_f16_lohi<2>(d0 + 128u, a_lo + 8, a_hi, b_lo, b_hi, idesc, acc);
                                     acc = 1u;
-                                    b_lo += b_step;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        // requirements of the next stage (possibly the first stage of the next tile)
+                        if (c + 1 < nchunks) wait_stage(c + 1, a_it + 1, acc_it, first);
+                        else if (t + cpn < total_pt) wait_stage(0, a_it + 1, acc_it + 1, false);
+                        if (elect_one()) {
+                            if (!skip) {
+#pragma unroll
+                                for (int tp = 5; tp < 9; ++tp) {
+                                    const int ki = tp / 3, kj = tp % 3;
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) {
+                                        const uint32_t a_lo = a_lo0 + (ki * RP + kj) + h * (2 * CP_PLANE_BYTES / 16);
+                                        const uint32_t b_lo = b_lo0 + (tp * 2 + h) * b_step;
+                                        umma_f16_lohi<2>(d0, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+                                        umma_f16_lohi<2>(d0 + 128u, a_lo + 8, a_hi, b_lo, b_hi, idesc, 1u);
+                                    }
                                 }
                             }
                             umma_commit_pair(&a_empty[as], 3);
                             if (c == nchunks - 1) umma_commit_pair(&acc_full[ab], 3);
-                        } else {
-                            b_lo += b_step * 18u;
                         }
                         __syncwarp();
                     }
-                    first = false;
                 }
             }
         } else {
@@ -206,6 +223,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
             const uint32_t st_row = smem_u32(stage) + lane * 64;
             const uint32_t st_x = ((lane >> 1) & 3) * 16;
             uint32_t acc_it = 0;
+            float abs_sum = 0.f;
+            float* const abs_ptr = (EK == EK_PACK && P.epi.absmean_acc != nullptr) ? &abs_sum : nullptr;
             for (int t = ci; t < total_pt; t += cpn, ++acc_it) {
                 const int tx = (t % tiles_x2) * 2 + static_cast<int>(rank), ty = (t / tiles_x2) % tiles_y;
                 const int img = t / (tiles_x2 * tiles_y);
@@ -222,7 +241,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                 for (int cc = 0; cc < ((P.dbg & 4) ? 0 : P.BN); cc += 32) {
                     float v[32];
                     tmem_ld32(t0 + cc, v);
-                    epi_store32<EK, TMA_OUT>(P.epi, has_bias ? bias_s - nt * P.BN : nullptr, v, img, y, x, nt * P.BN + cc, valid);
+                    epi_store32<EK, TMA_OUT>(P.epi, has_bias ? bias_s - nt * P.BN : nullptr, v, img, y, x, nt * P.BN + cc, valid, abs_ptr);
                     if (TMA_OUT) {
                         if (lane == 0) bulk_wait_group_read0();          // the previous box has been read out of the staging buffer
                         __syncwarp();
@@ -243,6 +262,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                 __syncwarp();
                 if (lane == 0) { if (leader) mbar_arrive(&acc_empty[ab]); else mbar_arrive_remote(&acc_empty[ab], 0); }
             }
+            if (abs_ptr != nullptr) epi_flush_abs_sum(P.epi, abs_sum);
             if (TMA_OUT && lane == 0) bulk_wait_group0();        // all output boxes written before the CTA retires
         }
     }

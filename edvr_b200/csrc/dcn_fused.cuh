@@ -4,7 +4,7 @@
 // per-sample addmm_ + the bias pass
 // (/root/reference/basicsr/models/ops/dcn/src/deform_conv_cuda.cpp:490-569,
 //  deform_conv_cuda_kernel.cu:467-497,570-633): the im2col "columns" matrix never exists in
-// HBM.  For each tile of 16x8 output pixels, eight gather warps bilinear-sample the NHWC fp16
+// HBM.  For each tile of 16x8 output pixels, the gather warps bilinear-sample the NHWC fp16
 // input (16 B = 8 channels per corner load), apply the modulation mask and write the result
 // straight into the shared-memory A operand (no-swizzle K-major planes, common.cuh); one
 // thread issues tcgen05.mma against the pre-packed weights (B operand, bulk async copies);
@@ -29,8 +29,10 @@ constexpr int DC_STAGES = 4;             // 4 x 32 KB: leaves ~90 KB of the SM's
 constexpr int DC_A_LBO = 128 * 16 + 16;  // plane pitch (+16 B: the 8 kc-lanes of a pixel hit 8 different bank groups)
 constexpr int DC_A_BYTES = 8 * DC_A_LBO; // 8 planes x 128 rows x 16 B (+ pad)
 constexpr int DC_B_BYTES = 128 * 128;    // BN(<=128) rows x 64 ch x 2 B
-constexpr int DC_THREADS = 448;          // 14 warps
-constexpr int DC_GATHER_THREADS = 256;
+constexpr int DC_NPX = 1;                // output pixels per gather thread and stage.  1 -> 16 gather warps (4 per scheduler):
+                                         // the gather is latency/issue bound, twice the warps hide more than 2-pixel ILP did
+constexpr int DC_GATHER_THREADS = 512 / DC_NPX;
+constexpr int DC_THREADS = 192 + DC_GATHER_THREADS;   // warps 0 B-producer, 1 MMA, 2-5 epilogue, 6.. gather
 constexpr int DC_MAX_COUT = 512;
 constexpr int DC_SMEM_BYTES = DC_STAGES * (DC_A_BYTES + DC_B_BYTES) + DC_MAX_COUT * 4 + 256;
 constexpr int DC_TILE_H = 16, DC_TILE_W = 8;
@@ -203,10 +205,10 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
     } else {
         // ================= gather warps (256 threads): build the A operand of each stage.
         // lane -> (pixel slot = lane/4, channel-atom pair kp = lane%4 -> atoms 2kp, 2kp+1 = 32 contiguous bytes);
-        // a thread owns 2 pixels per stage.  The 4 lanes of a pixel cover one full 128-byte line per corner.
+        // a thread owns DC_NPX pixels per stage.  The 4 lanes of a pixel cover one full 128-byte line per corner.
         // All kernel parameters used below are copied to registers first: with two gather warps per scheduler
         // every constant-bank load / integer division inside the stage loop is exposed latency.
-        const int gw = warp - 6;                      // 0..7
+        const int gw = warp - 6;                      // 0 .. DC_GATHER_THREADS/32 - 1
         const int kc0 = (lane & 3) * 2;
         const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo, strd = P.stride, pad = P.pad, dil = P.dil;
         const int strd_w = P.stride_w, pad_w = P.pad_w, dil_w = P.dil_w;
@@ -267,10 +269,10 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             const int pt = tile / P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
             const __half* const ximg = xview + static_cast<long long>(img) * H * xrow;
-            Pix px[2];
+            Pix px[DC_NPX];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                px[i].m = i * 64 + gw * 8 + (lane >> 2);
+            for (int i = 0; i < DC_NPX; ++i) {
+                px[i].m = i * (128 / DC_NPX) + gw * 8 + (lane >> 2);
                 const int ho = ty * DC_TILE_H + (px[i].m >> 3), wo = tx * DC_TILE_W + (px[i].m & 7);
                 px[i].ok = (ho < Ho) && (wo < Wo);
                 px[i].hb = ho * strd - pad;
@@ -282,9 +284,9 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             }
             // software pipeline: the (dh, dw, mask) triples of the NEXT stage are fetched while this one is gathered
             int g0 = (kc0 * 8) / cpg, g1 = (kc0 * 8 + 8) / cpg;
-            DcnOff nxt[2][2];
+            DcnOff nxt[DC_NPX][2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < DC_NPX; ++i) {
                 nxt[i][0] = fetch(px[i], g0, 0);
                 nxt[i][1] = (g1 != g0) ? fetch(px[i], g1, 0) : nxt[i][0];
             }
@@ -296,19 +298,19 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                 int ki = 0, kj = 0;
                 for (int tap = 0; tap < K; ++tap, ++it) {
                     const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
-                    DcnCorner cn[2][2];
+                    DcnCorner cn[DC_NPX][2];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
+                    for (int i = 0; i < DC_NPX; ++i) {
                         cn[i][0] = corner(px[i], ximg, ki, kj, nxt[i][0]);
                         cn[i][1] = two ? corner(px[i], ximg, ki, kj, nxt[i][1]) : cn[i][0];
                     }
                     // all 16 corner loads in flight before anything is consumed
-                    uint4 u[2][2][4];
+                    uint4 u[DC_NPX][2][4];
                     if (wide && !two) {
                         // the lane's two K atoms (one deformable group, 32 contiguous bytes) in ONE load per corner: the four
                         // lanes of a pixel fetch a full 128-byte line per instruction (half the L1 wavefronts of 2 x LDG.128)
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
+                        for (int i = 0; i < DC_NPX; ++i) {
                             const DcnCorner& c = cn[i][0];
                             const __half* b = c.base + ch;
 #pragma unroll
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                         }
                     } else
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
+                    for (int i = 0; i < DC_NPX; ++i)
 #pragma unroll
                         for (int a = 0; a < 2; ++a) {
                             const DcnCorner& c = cn[i][a];
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                         const int h0 = last_tap ? ng0 : g0, h1 = last_tap ? ng1 : g1;
                         if (!(last_tap && chunk + 1 == nchunks)) {
 #pragma unroll
-                            for (int i = 0; i < 2; ++i) {
+                            for (int i = 0; i < DC_NPX; ++i) {
                                 nxt[i][0] = fetch(px[i], h0, t1);
                                 nxt[i][1] = (h1 != h0) ? fetch(px[i], h1, t1) : nxt[i][0];
                             }
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                     mbar_wait_warp(&empty[s], ph ^ 1u);
                     const uint32_t dst = smem_u32(a_smem + s * DC_A_BYTES) + kc0 * DC_A_LBO;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
+                    for (int i = 0; i < DC_NPX; ++i)
 #pragma unroll
                         for (int a = 0; a < 2; ++a) {
                             uint4 r;

@@ -218,8 +218,9 @@ int eb_pack_weight_pair(const float* w, int cout, int cin, int ktaps, const int*
 int eb_conv2d_pair_supported(int cin, int ksize, int BN, int n_tiles_n) {
     // 1x1 layers have too little work per 32-channel stage for this pipeline (measured slower than conv_igemm)
     if (cin < 64 || cin % 64 || ksize != 3 || BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1) return 0;
-    if (static_cast<long long>(cin) * ksize * ksize * (BN / 2) * 2 > CP_W_BYTES) return 0;
-    return (n_tiles_n <= num_sms() / 2 && tensor_map_encoder() != nullptr) ? 1 : 0;
+    if (n_tiles_n > num_sms() / 2 || tensor_map_encoder() == nullptr) return 0;
+    // 1: each CTA keeps its half of the weights resident in shared memory; 2: weights stream with the activation stages
+    return static_cast<long long>(cin) * ksize * ksize * (BN / 2) * 2 <= CP_W_BYTES ? 1 : 2;
 }
 
 static bool conv_force_v1() {
@@ -366,9 +367,9 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
     ConvParams P;
     if (int rc = build_conv_params("conv2d_pair", srcs, nsrc, N, H, W, ksize, wpair, BN, n_tiles_n, epi, false, &P)) return rc;
     const int cin = P.src[0].C + (nsrc > 1 ? P.src[1].C : 0);
-    if (!eb_conv2d_pair_supported(cin, ksize, BN, n_tiles_n))
-        return fail(EB_ERR_UNSUPPORTED, "conv2d_pair: cin=%d k=%d BN=%d tiles=%d (weights must fit %d bytes per CTA)", cin, ksize,
-                    BN, n_tiles_n, CP_W_BYTES);
+    const int mode = eb_conv2d_pair_supported(cin, ksize, BN, n_tiles_n);
+    if (!mode) return fail(EB_ERR_UNSUPPORTED, "conv2d_pair: cin=%d k=%d BN=%d tiles=%d", cin, ksize, BN, n_tiles_n);
+    const bool resident = mode == 1 && !(P.dbg & 128);
     if (N == 0) return EB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long pair_tiles = static_cast<long long>(N) * ((H + 15) / 16) * (((W + 15) / 16 + 1) / 2);
@@ -396,6 +397,20 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
         if (int rc = encode_halo_map(S, H, W, n_images < 1 ? 1 : n_images, &PP.tmap[i])) return rc;
     }
     if (nsrc == 1) PP.tmap[1] = PP.tmap[0];
+    PP.tmap_w = PP.tmap[0];
+    if (!resident) {
+        // packed weights as rows of 256 fp16; one box = the (BN/2) x 9 x 32 slice one CTA needs for one 32-channel chunk
+        eb_encode_tiled_fn enc = tensor_map_encoder();
+        const cuuint64_t total = static_cast<cuuint64_t>(n_tiles_n) * BN * cin * 9;          // fp16 elements
+        const cuuint64_t dims[2] = {256, total / 256};
+        const cuuint64_t strides[1] = {512};
+        const cuuint32_t box[2] = {256, static_cast<cuuint32_t>(9 * 4 * (BN / 2) * 16 / 512)};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&PP.tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(P.wpack), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "conv2d_pair: weight tensor map failed (%d)", static_cast<int>(r));
+    }
     // fp16 NHWC output through TMA when the epilogue writes it pixel-for-pixel (plain / fp32-stream / DCN-record kinds)
     PP.tma_out = 0;
     PP.tmap_out = PP.tmap[0];
@@ -415,7 +430,7 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * nclusters);
     cfg.blockDim = dim3(CP_THREADS);
-    cfg.dynamicSmemBytes = CP_SMEM_BYTES;
+    cfg.dynamicSmemBytes = resident ? CP_SMEM_BYTES : CP_SMEM_BYTES_STREAM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -424,8 +439,13 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
     cudaError_t err = cudaSuccess;
 #define EB_LAUNCH_CP(EK_, TO_)                                                                         \
     do {                                                                                               \
-        if (int rc = set_smem(conv_pair_kernel<EK_, TO_>, CP_SMEM_BYTES)) return rc;                   \
-        err = cudaLaunchKernelEx(&cfg, conv_pair_kernel<EK_, TO_>, PP);                                \
+        if (resident) {                                                                                \
+            if (int rc = set_smem(conv_pair_kernel<EK_, TO_, true>, CP_SMEM_BYTES)) return rc;         \
+            err = cudaLaunchKernelEx(&cfg, conv_pair_kernel<EK_, TO_, true>, PP);                      \
+        } else {                                                                                       \
+            if (int rc = set_smem(conv_pair_kernel<EK_, TO_, false>, CP_SMEM_BYTES_STREAM)) return rc; \
+            err = cudaLaunchKernelEx(&cfg, conv_pair_kernel<EK_, TO_, false>, PP);                     \
+        }                                                                                              \
     } while (0)
     switch (ek1) {
         case EK_PLAIN: if (PP.tma_out) EB_LAUNCH_CP(EK_PLAIN, true); else EB_LAUNCH_CP(EK_PLAIN, false); break;
@@ -785,6 +805,16 @@ int eb_conv_last(const void* x, int x_pix_stride, const float* w, const float* b
     conv_last_kernel<<<grid_1d(items, 128), 128, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(x), x_pix_stride, w, bias, base, base_img_stride, scale, out, N, H, W, Cin);
     return check_launch("conv_last");
+}
+
+int eb_add_base(const float* base, long long base_img_stride, int scale, float* out, int N, int C, int H, int W, void* stream) {
+    if (!base || !out) return fail(EB_ERR_NULLPTR, "add_base: null pointer");
+    if (N < 0 || C < 1 || H < 1 || W < 1 || (scale != 1 && scale != 4) || H % scale || W % scale)
+        return fail(EB_ERR_INVALID_SHAPE, "add_base: shape");
+    if (N == 0) return EB_OK;
+    add_base_kernel<<<grid_1d(static_cast<long long>(N) * C * H * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        base, base_img_stride, scale, out, N, C, H, W);
+    return check_launch("add_base");
 }
 
 static bool view_ok(const void* p, int ps, int co, int C) {

@@ -254,6 +254,13 @@ __device__ __forceinline__ void tma_load_5d_pair(void* dst_smem, const void* tma
           "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_pair(void* dst_smem, const void* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
 // arrive + expect `bytes` on the mbarrier at the same offset in CTA `target` of the cluster
 __device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint64_t* bar, uint32_t bytes, uint32_t target) {
     asm volatile(

@@ -17,7 +17,9 @@
 //   * the fp16 NHWC output leaves through TMA as well: each epilogue warp stages its 32 pixels x 32 channels in a private
 //     2 KB buffer (64-byte swizzle, conflict-free) and one lane issues a box store - full 64-byte segments per pixel
 //     instead of 32 scattered 16-byte st.global per instruction (the epilogue's LSU wavefronts cost 4K cycles per tile);
-//   * the MMA warp runs converged and elects one lane per instruction, descriptors live in uniform registers.
+//   * the MMA warp runs converged and elects one lane per instruction, descriptors live in uniform registers;
+//   * layers whose weights do not fit (Cin = 256) use the same kernel with RESIDENT = false: each CTA's half of the weights
+//     of a 32-channel chunk (36 KB) travels with the activation stage as a second TMA box on the same mbarrier.
 // Only the even CTA issues MMAs; completion is multicast to both CTAs' mbarriers; the odd CTA's epilogue warps signal
 // "accumulator drained" to the even CTA through the cluster shared-memory window.
 #pragma once
@@ -38,23 +40,28 @@ constexpr int CP_W_BYTES = 147456;                          // resident weights 
 constexpr int CP_MAX_WGROUPS = 8;
 constexpr int CP_THREADS = 320;                             // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
 constexpr int CP_OUT_STAGE_BYTES = 32 * 64;                 // per epilogue warp: 32 pixels x 32 fp16 channels
+constexpr int CP_W_STAGE_BYTES = 9 * 4 * 64 * 16;           // streamed mode: weights of one chunk, BN/2 <= 64 rows
 constexpr int CP_SMEM_BYTES = CP_W_BYTES + 8 * CP_OUT_STAGE_BYTES + CP_A_STAGES * CP_A_STAGE_BYTES + 128 * 4 + 256;
+constexpr int CP_SMEM_BYTES_STREAM = 8 * CP_OUT_STAGE_BYTES + CP_A_STAGES * (CP_A_STAGE_BYTES + CP_W_STAGE_BYTES) + 128 * 4 + 256;
 
 struct PairParams {
     ConvParams c;
     CUtensorMap tmap[2];        // one per source: dims {8 ch, W, H, pix_stride/8 atoms, images}, box {8, 18, 18, 4, 1}
+    CUtensorMap tmap_w;         // streamed weights: packed array as rows of 256 fp16, box = one chunk stage of one CTA
     CUtensorMap tmap_out;       // fp16 NHWC output: dims {pix_stride, W, H, N}, box {32 ch, 8 x, 4 y, 1}, 64-byte swizzle
     int tma_out;                // 1: out16 leaves through tmap_out
 };
 
-template <int EK, bool TMA_OUT>
+template <int EK, bool TMA_OUT, bool RESIDENT>
 __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_constant__ PairParams PP) {
     const ConvParams& P = PP.c;
     extern __shared__ __align__(1024) uint8_t smem[];
+    // resident: [weights 144 KB][output staging 16 KB][3 activation stages]; streamed: [output staging][3 x (activations, weights)]
+    constexpr int STAGE_STRIDE = RESIDENT ? CP_A_STAGE_BYTES : CP_A_STAGE_BYTES + CP_W_STAGE_BYTES;
     uint8_t* w_smem = smem;
-    uint8_t* o_smem = smem + CP_W_BYTES;                     // 8 x 2 KB output staging (1024-byte aligned)
+    uint8_t* o_smem = smem + (RESIDENT ? CP_W_BYTES : 0);    // 8 x 2 KB output staging (1024-byte aligned)
     uint8_t* a_smem = o_smem + 8 * CP_OUT_STAGE_BYTES;
-    float* bias_s = reinterpret_cast<float*>(a_smem + CP_A_STAGES * CP_A_STAGE_BYTES);
+    float* bias_s = reinterpret_cast<float*>(a_smem + CP_A_STAGES * STAGE_STRIDE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 128);
     uint64_t* a_full = bars;                         // [CP_A_STAGES]  even CTA: both CTAs' TMA boxes (2 arrivals + bytes)
     uint64_t* a_empty = a_full + CP_A_STAGES;        // [CP_A_STAGES]  multicast commit
@@ -93,12 +100,13 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
     if (has_bias && threadIdx.x < P.BN) bias_s[threadIdx.x] = P.epi.bias[nt * P.BN + threadIdx.x];
     if (threadIdx.x == 0) {
         for (int i = 0; i < CP_A_STAGES; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < CP_MAX_WGROUPS; ++i) mbar_init(&w_full[i], leader ? 2 : 1);
+        for (int i = 0; i < CP_MAX_WGROUPS; ++i) mbar_init(&w_full[i], leader ? 2 : 1);     // resident mode only
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
         fence_barrier_init();
         tma_prefetch_desc(&PP.tmap[0]);
         if (P.nsrc > 1) tma_prefetch_desc(&PP.tmap[1]);
         if (TMA_OUT) tma_prefetch_desc(&PP.tmap_out);
+        if (!RESIDENT) tma_prefetch_desc(&PP.tmap_w);
     }
     if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
     tc_fence_before_sync();
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                 // ================= producer.  Weights: this CTA's half of n-tile nt, once, in consumption order.
                 const uint8_t* w = reinterpret_cast<const uint8_t*>(P.wpack) +
                                    (static_cast<size_t>(nt) * 2 + rank) * nchunks * stage_w_bytes;
-                for (int g = 0; g < wgroups; ++g) {
+                for (int g = 0; RESIDENT && g < wgroups; ++g) {
                     const int c0 = g * cpg, c1 = (c0 + cpg < nchunks) ? c0 + cpg : nchunks;
                     if (c1 <= c0) { mbar_arrive(&w_full[g]); continue; }
                     mbar_arrive_expect_tx(&w_full[g], static_cast<uint32_t>(c1 - c0) * stage_w_bytes);
@@ -123,7 +131,9 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                 }
                 // Activations: one TMA box per stage into this CTA, bytes counted on the even CTA's a_full.
                 uint32_t a_it = 0;
-                bool first = true;
+                bool first = RESIDENT;
+                const int w_rows = static_cast<int>(stage_w_bytes / 512u);           // streamed: rows of 256 fp16 per chunk stage
+                const int w_row0 = (nt * 2 + static_cast<int>(rank)) * nchunks * w_rows;
                 for (int t = ci; t < total_pt; t += cpn) {
                     const int tx = (t % tiles_x2) * 2 + static_cast<int>(rank), ty = (t / tiles_x2) % tiles_y;
                     const int img = t / (tiles_x2 * tiles_y);
@@ -136,12 +146,16 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                         const uint32_t as = a_it % CP_A_STAGES, aph = (a_it / CP_A_STAGES) & 1u;
                         mbar_wait(&a_empty[as], aph ^ 1u);
                         const bool skip = (P.dbg & 16) && a_it >= CP_A_STAGES;           // profiling: reuse stale stages
-                        const uint32_t bytes = skip ? 0u : static_cast<uint32_t>(CP_A_STAGE_BYTES);
+                        const uint32_t bytes = skip ? 0u : static_cast<uint32_t>(CP_A_STAGE_BYTES) + (RESIDENT ? 0u : stage_w_bytes);
                         if (leader) mbar_arrive_expect_tx(&a_full[as], bytes);
                         else mbar_arrive_expect_tx_remote(&a_full[as], bytes, 0);
-                        if (!skip)
-                            tma_load_5d_pair(a_smem + as * CP_A_STAGE_BYTES, &PP.tmap[s], &a_full[as], 0, tx * CV_TILE - 1,
+                        if (!skip) {
+                            tma_load_5d_pair(a_smem + as * STAGE_STRIDE, &PP.tmap[s], &a_full[as], 0, tx * CV_TILE - 1,
                                              ty * CV_TILE - 1, (S.ch_off + ch) >> 3, simg);
+                            if (!RESIDENT)
+                                tma_load_2d_pair(a_smem + as * STAGE_STRIDE + CP_A_STAGE_BYTES, &PP.tmap_w, &a_full[as], 0,
+                                                 w_row0 + c * w_rows);
+                        }
                     }
                     first = false;
                 }
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                 uint32_t a_it = 0, acc_it = 0;
                 auto wait_stage = [&](int c, uint32_t ait, uint32_t accit, bool first_tile) {
                     if (c == 0) mbar_wait_cluster(&acc_empty[accit & 1u], ((accit >> 1) & 1u) ^ 1u);
-                    if (first_tile && c % cpg == 0) mbar_wait_cluster(&w_full[c / cpg], 0);
+                    if (RESIDENT && first_tile && c % cpg == 0) mbar_wait_cluster(&w_full[c / cpg], 0);
                     mbar_wait_cluster(&a_full[ait % CP_A_STAGES], (ait / CP_A_STAGES) & 1u);
                 };
                 if (ci < total_pt) wait_stage(0, 0, 0, true);
@@ -171,8 +185,9 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                     for (int c = 0; c < nchunks; ++c, ++a_it) {
                         const uint32_t as = a_it % CP_A_STAGES;
                         tc_fence_after_sync();
-                        const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_smem + as * CP_A_STAGE_BYTES), CP_PLANE_BYTES);
-                        const uint32_t b_lo0 = w_lo0 + static_cast<uint32_t>(c) * 18u * b_step;
+                        const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_smem + as * STAGE_STRIDE), CP_PLANE_BYTES);
+                        const uint32_t b_lo0 = RESIDENT ? w_lo0 + static_cast<uint32_t>(c) * 18u * b_step
+                                                        : umma_desc_lo(smem_u32(a_smem + as * STAGE_STRIDE + CP_A_STAGE_BYTES), lbo_b);
                         const bool skip = (P.dbg & 32) != 0;
                         if (!skip && elect_one()) {
                             uint32_t acc = c != 0 ? 1u : 0u;

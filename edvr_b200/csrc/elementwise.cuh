@@ -265,6 +265,21 @@ __global__ void conv_last_kernel(const __half* __restrict__ x, int x_pix_stride,
     }
 }
 
+// out[n, c, y, x] += bilinear x`scale` of base[n, c] (scale 4) or base itself (scale 1): the `+ base` of edvr_arch.py:414-419
+// when conv_last runs on the tensor cores (its NCHW store leaves conv + bias in `out`)
+__global__ void add_base_kernel(const float* __restrict__ base, long long base_img_stride, int scale,
+                                float* __restrict__ out, int N, int C, int H, int W) {
+    const long long total = static_cast<long long>(N) * C * H * W;
+    const int bh = H / scale, bw = W / scale;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int x = i % W, y = (i / W) % H, c = (i / (static_cast<long long>(W) * H)) % C;
+        const long long n = i / (static_cast<long long>(W) * H * C);
+        const float* bc = base + n * base_img_stride + static_cast<size_t>(c) * bh * bw;
+        out[i] += scale == 1 ? bc[y * bw + x] : bilinear_up_sample(bc, bh, bw, y, x, scale);
+    }
+}
+
 // ------------------------------------------------------------------ bilinear x2 (align_corners=False)
 // out[2k] = .25 in[k-1] + .75 in[k]; out[2k+1] = .75 in[k] + .25 in[k+1]; edges replicate.
 __global__ void upsample2x_kernel(const __half* __restrict__ src, int sps, int sco,

@@ -234,6 +234,9 @@ class EDVREngine:
         conv("upconv2")
         conv("conv_hr")
         raw["last"] = (sd["conv_last.weight"], sd["conv_last.bias"])
+        # conv_last on the tensor cores: 3 output channels padded to one 32-wide tile, fp32 NCHW store (+ eb_add_base)
+        self.last_tc = ops.pack_conv(sd["conv_last.weight"].float(), sd["conv_last.bias"].float(), cout_packed=32) \
+            if sd["conv_last.weight"].shape[1] % 64 == 0 else None
         self.p, self.raw = p, raw
 
     # ------------------------------------------------------------------ helpers
@@ -315,7 +318,11 @@ class EDVREngine:
         ops.conv2d(p["conv_hr"], [u2], out16=hr, act=ACT_LRELU)
         out = torch.empty(B, 3, 4 * h, 4 * w, dtype=torch.float32, device=self.device)
         xc = x[:, self.center]          # [B,3,hin,win] view: image stride T*3*hin*win
-        ops.conv_last(hr, *self.raw["last"], xc, T * 3 * hin * win, 1 if self.hr_in else 4, out)
+        if self.last_tc is not None:
+            ops.conv2d(self.last_tc, [hr], act=ACT_NONE, out_nchw=out, nchw_C=3)
+            ops.add_base(xc, T * 3 * hin * win, 1 if self.hr_in else 4, out)
+        else:
+            ops.conv_last(hr, *self.raw["last"], xc, T * 3 * hin * win, 1 if self.hr_in else 4, out)
         return out
 
     # ------------------------------------------------------------------ PredeblurModule (edvr_arch.py:250-269)

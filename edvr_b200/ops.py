@@ -188,7 +188,7 @@ def _epi(pc_bias, act, out16=None, out32=None, res16=None, res32=None, out_nchw=
 
 
 def conv2d(pc, srcs, out16=None, act=ACT_NONE, res16=None, res32=None, out32=None, out_mode=OUT_SAME,
-           absmean=None, src_maps=None, N=None):
+           absmean=None, src_maps=None, N=None, out_nchw=None, nchw_C=0):
     """srcs: list of 1-2 Views (channel-concatenated input). src_maps: per-source (div, mul, keep, add)."""
     v0 = srcs[0]
     N = v0.N if N is None else N
@@ -197,7 +197,7 @@ def conv2d(pc, srcs, out16=None, act=ACT_NONE, res16=None, res32=None, out32=Non
         m = (1, 1, 0, 0) if src_maps is None or src_maps[i] is None else src_maps[i]
         arr[i] = _src(v, *m)
     assert sum(v.C for v in srcs) == pc.cin, (sum(v.C for v in srcs), pc.cin)
-    e = _epi(pc.b, act, out16, out32, res16, res32, out_mode=out_mode, absmean=absmean)
+    e = _epi(pc.b, act, out16, out32, res16, res32, out_nchw=out_nchw, nchw_C=nchw_C, out_mode=out_mode, absmean=absmean)
     opix = N * v0.H * v0.W if out_mode != OUT_STRIDE2 else N * ((v0.H + 1) // 2) * ((v0.W + 1) // 2)
     detail = ""
     if PROFILE is not None:
@@ -244,6 +244,14 @@ def conv_first(x_nchw, w, b, out, act=ACT_LRELU):
     with _Rec("conv_first", 1):
         L.check(L.lib().eb_conv_first(L.ptr(x_nchw), L.ptr(w), L.ptr(b), L.ptr(out.t), N, H, W, w.shape[0],
                                       out.pix_stride, act, L.stream_ptr()), "eb_conv_first")
+
+
+def add_base(base, base_img_stride, scale, out_nchw):
+    """out_nchw (fp32 [N,C,H,W]) += bilinear x4 of base (scale 4) or base (scale 1)."""
+    N, C, H, W = out_nchw.shape
+    with _Rec("add_base", 1):
+        L.check(L.lib().eb_add_base(L.ptr(base), base_img_stride, scale, L.ptr(out_nchw), N, C, H, W, L.stream_ptr()),
+                "eb_add_base")
 
 
 def conv_last(x, w, b, base, base_img_stride, scale, out_nchw):

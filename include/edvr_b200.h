@@ -97,8 +97,9 @@ int eb_conv2d(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, co
 int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpack,
                     int BN, int n_tiles_n, const eb_epilogue_t* epi, unsigned long long* stats, void* stream);
 
-/* Same convolution on CTA pairs (tcgen05 cta_group::2) with the weights resident in shared memory: available when
- * eb_conv2d_pair_supported() returns 1 (Cin * ksize^2 * BN <= 147456, e.g. 128 -> 128 3x3).  `wpair` is produced by
+/* Same convolution on CTA pairs (tcgen05 cta_group::2), TMA in and out: available when eb_conv2d_pair_supported() is
+ * non-zero (3x3 layers; 1 = each CTA keeps its half of the weights resident in shared memory, Cin * 9 * BN <= 147456,
+ * e.g. 128 -> 128; 2 = weights stream with the activation stages, e.g. 256 -> 128).  `wpair` is produced by
  * eb_pack_weight_pair (same size as eb_packed_weight_bytes); sources, epilogue and results as eb_conv2d. */
 int eb_conv2d_pair_supported(int cin, int ksize, int BN, int n_tiles_n);
 int eb_pack_weight_pair(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN, int n_tiles_n,
@@ -163,6 +164,9 @@ int eb_conv_first(const float* x_nchw, const float* w_oihw, const float* bias, v
 int eb_conv_last(const void* x, int x_pix_stride, const float* w_oihw, const float* bias,
                  const float* base_nchw, long long base_img_stride, int scale, float* out_nchw, int N,
                  int H, int W, int Cin, void* stream);
+/* out[N, C, H, W] (fp32 NCHW) += bilinear x4 (align_corners = False) of base[N, C, H/4, W/4], or += base when scale == 1:
+ * the second half of eb_conv_last for callers that run the 64 -> 3 convolution through eb_conv2d(_pair) with an NCHW store. */
+int eb_add_base(const float* base, long long base_img_stride, int scale, float* out, int N, int C, int H, int W, void* stream);
 /* bilinear x2, align_corners=False, times `mul` (edvr_arch.py:68-69,109-110), channel-slice I/O */
 int eb_upsample2x(const void* src, int src_pix_stride, int src_ch_off, void* dst, int dst_pix_stride,
                   int dst_ch_off, int N, int H, int W, int C, float mul, const void* add,

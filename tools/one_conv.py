@@ -60,6 +60,15 @@ def run(N, H, W, cin, cout, k, dbgs, f32=False, pair_dbgs=(0,)):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ncu":       # ncu target: the trunk convolution on the CTA-pair kernel only
+        os.environ["EDVR_B200_CONV_PAIR"] = "1"
+        x = ops.nchw_to_nhwc(torch.randn(4, 128, 180, 320, device="cuda"))
+        pc = ops.pack_conv(torch.randn(128, 128, 3, 3, device="cuda") / 34, torch.zeros(128, device="cuda"))
+        out = ops.new_act(4, 180, 320, 128)
+        for _ in range(4):
+            ops.conv2d(pc, [x], out16=out, act=ops.ACT_RELU)
+        torch.cuda.synchronize()
+        sys.exit(0)
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     DBGS = [0] if quick else [0, 1, 4, 8, 16, 24, 28, 60, 32]
     run(28, 180, 320, 128, 128, 3, DBGS, pair_dbgs=(0, 1, 4, 16, 20, 32, 52))

@@ -432,10 +432,12 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
     cfg.blockDim = dim3(CP_THREADS);
     cfg.dynamicSmemBytes = resident ? CP_SMEM_BYTES : CP_SMEM_BYTES_STREAM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see pdl_wait() in conv_pair.cuh
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = getenv("EDVR_B200_NO_PDL") ? 1 : 2;
     cudaError_t err = cudaSuccess;
 #define EB_LAUNCH_CP(EK_, TO_)                                                                         \
     do {                                                                                               \

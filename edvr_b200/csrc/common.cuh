@@ -283,6 +283,12 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 
+// ---- programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running (once every CTA of the predecessor has triggered or exited); it must
+// not touch memory the predecessor reads or writes before pdl_wait() returns (= predecessor complete and flushed).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Shared-memory matrix descriptor with a swizzled K-major layout (rows of 32/64/128 bytes, 8-row groups SBO apart):
 // layout type 2 = 128 B, 4 = 64 B, 6 = 32 B swizzle.
 __device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {

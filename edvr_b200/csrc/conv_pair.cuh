@@ -115,6 +115,12 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Programmatic dependent launch: the next kernel of the stream may begin its prologue (barriers, TMEM, weights) on SMs
+    // this grid has already left - the tail of a 6.5-round launch leaves half of them idle.  Everything above and the weight
+    // copies below touch only constants; activations, residuals and outputs wait for the predecessor (pdl_wait).
+    pdl_trigger();
+    if (!(active && warp == 0 && lane == 0)) pdl_wait();
+
     if (active) {
         if (warp == 0) {
             if (lane == 0) {
@@ -129,6 +135,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                         bulk_g2s(w_smem + static_cast<size_t>(c) * stage_w_bytes, w + static_cast<size_t>(c) * stage_w_bytes,
                                  stage_w_bytes, &w_full[g]);
                 }
+                pdl_wait();
                 // Activations: one TMA box per stage into this CTA, bytes counted on the even CTA's a_full.
                 uint32_t a_it = 0;
                 bool first = RESIDENT;

@@ -32,7 +32,7 @@ constexpr int DC_B_BYTES = 128 * 128;    // BN(<=128) rows x 64 ch x 2 B
 constexpr int DC_NPX = 1;                // output pixels per gather thread and stage.  1 -> 16 gather warps (4 per scheduler):
                                          // the gather is latency/issue bound, twice the warps hide more than 2-pixel ILP did
 constexpr int DC_GATHER_THREADS = 512 / DC_NPX;
-constexpr int DC_THREADS = 192 + DC_GATHER_THREADS;   // warps 0 B-producer, 1 MMA, 2-5 epilogue, 6.. gather
+constexpr int DC_THREADS = 192 + DC_GATHER_THREADS + 32;   // warps 0 B-producer, 1 MMA, 2-5 epilogue, 6.. gather, last: forwarder
 constexpr int DC_MAX_COUT = 512;
 constexpr int DC_SMEM_BYTES = DC_STAGES * (DC_A_BYTES + DC_B_BYTES) + DC_MAX_COUT * 4 + 256;
 constexpr int DC_TILE_H = 16, DC_TILE_W = 8;
@@ -104,9 +104,10 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
     uint8_t* b_smem = smem + DC_STAGES * DC_A_BYTES;
     float* bias_s = reinterpret_cast<float*>(b_smem + DC_STAGES * DC_B_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + DC_MAX_COUT);
-    uint64_t* full = bars;                       // [S]  8 gather-warp arrivals + 1 expect_tx
+    uint64_t* full = bars;                       // [S]  forwarder arrival + 1 expect_tx (weights)
     uint64_t* empty = bars + DC_STAGES;          // [S]
-    uint64_t* acc_full = bars + 2 * DC_STAGES;   // [2]
+    uint64_t* gathered = bars + 2 * DC_STAGES;   // [S]  one arrival per gather warp
+    uint64_t* acc_full = bars + 3 * DC_STAGES;   // [2]
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
     if (has_bias)
         for (int i = threadIdx.x; i < cout_packed; i += blockDim.x) bias_s[i] = P.epi.bias[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < DC_STAGES; ++i) { mbar_init(&full[i], DC_GATHER_THREADS / 32 + 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < DC_STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); mbar_init(&gathered[i], DC_GATHER_THREADS / 32); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_barrier_init();
     }
@@ -201,6 +202,20 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        }
+    } else if (warp == DC_THREADS / 32 - 1) {
+        // ================= forwarder: "all gather warps have written stage s" -> generic->async proxy fence -> full[s].
+        // The fence used to sit in every gather thread (MEMBAR.ALL.CTA), where it also waited for the thread's prefetched
+        // offset loads of the NEXT stage, i.e. it undid the software pipelining of the gather.
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+                for (int st = 0; st < nstages; ++st, ++it) {
+                    const uint32_t s = it % DC_STAGES, ph = (it / DC_STAGES) & 1u;
+                    mbar_wait(&gathered[s], ph);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&full[s]);
+                }
         }
     } else {
         // ================= gather warps (256 threads): build the A operand of each stage.
@@ -368,9 +383,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                             }
                             sts_v4(dst + a * DC_A_LBO + px[i].m * 16, r);
                         }
-                    fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[s]);
+                    if (lane == 0) mbar_arrive(&gathered[s]);
                 }
                 g0 = ng0;
                 g1 = ng1;

@@ -162,6 +162,64 @@ def test_blocked_fp32_stream_roundtrip(ops):
     assert rel_err(ops.nhwc_to_nchw(out16).cpu(), want.cpu())[0] < TOL
 
 
+def test_conv_pair_resident_and_streamed_weights_agree(ops, monkeypatch):
+    """The CTA-pair kernel keeps the weights resident in shared memory when they fit and streams them with the activation
+    stages otherwise; EDVR_B200_DBG=128 forces the streamed mode on a layer that fits, so both modes run the SAME layer:
+    identical MMA order => bit-identical outputs; both within 1e-3 of an fp64 convolution on the fp16-rounded operands.
+    Also covers a tile count that is not a multiple of the cluster count and an odd number of 16-pixel tile columns."""
+    from edvr_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, C, H, W = 3, 128, 50, 41
+    x = torch.randn(N, C, H, W, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, device="cuda", generator=g) / 34
+    b = torch.randn(C, device="cuda", generator=g) * 0.1
+    pc = ops.pack_conv(w, b)
+    assert L.lib().eb_conv2d_pair_supported(C, 3, pc.BN, pc.n_tiles) == 1 and pc.wpair is not None
+    assert L.lib().eb_conv2d_pair_supported(256, 3, 128, 1) == 2 and L.lib().eb_conv2d_pair_supported(896, 1, 128, 2) == 0
+    want = F.relu(F.conv2d(x.half().double(), w.half().double(), b.double(), 1, 1)).float()
+    outs = []
+    for dbg in ("0", "128"):
+        monkeypatch.setenv("EDVR_B200_DBG", dbg)
+        out = ops.new_act(N, H, W, C)
+        out.t.fill_(float("nan"))
+        ops.conv2d(pc, [ops.nchw_to_nhwc(x)], out16=out, act=ops.ACT_RELU)
+        torch.cuda.synchronize()
+        outs.append(out.t.clone())
+        e = rel_err(ops.nhwc_to_nchw(out).cpu(), want.cpu())
+        assert e[0] < TOL and e[1] < TOL, (dbg, e)
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_add_base_matches_torch_bilinear(ops):
+    """eb_add_base = the `out + F.interpolate(x_center, scale_factor=4, mode='bilinear', align_corners=False)` of
+    edvr_arch.py:414-419 (and `+ x_center` for hr_in), applied after the tensor-core conv_last."""
+    base = torch.rand(2, 5, 3, 9, 13, device="cuda")[:, 2]            # strided centre-frame view, like the engine passes it
+    out = torch.randn(2, 3, 36, 52, device="cuda")
+    want = out + F.interpolate(base.contiguous(), scale_factor=4, mode="bilinear", align_corners=False)
+    ops.add_base(base, 5 * 3 * 9 * 13, 4, out)
+    assert rel_err(out.cpu(), want.cpu())[0] < 1e-6
+    out1 = torch.randn(2, 3, 9, 13, device="cuda")
+    want1 = out1 + base
+    ops.add_base(base, 5 * 3 * 9 * 13, 1, out1)
+    assert torch.equal(out1, want1)
+
+
+def test_mma_rate_probe_reaches_the_tensor_pipe_floor(ops):
+    """Hardware probe used for the design decisions in DESIGN.md: a 128x128x16 MMA (and the 256x128x16 CTA-pair MMA) issue
+    back to back at 64 cycles each in the kernels' no-swizzle operand layout."""
+    import ctypes
+    from edvr_b200 import _lib as L
+    for cg, M in ((1, 128), (2, 256)):
+        cyc = torch.zeros(160, dtype=torch.int64, device="cuda")
+        n = ctypes.c_int(0)
+        L.check(L.lib().eb_selftest_mma_rate(cg, M, 128, 0, 2048, 128, 2048 // cg, 128, 4096, 2048, L.ptr(cyc), ctypes.byref(n),
+                                             L.stream_ptr()))
+        torch.cuda.synchronize()
+        c = cyc[:n.value].double()
+        per_mma = float(c[c > 0].mean()) / 2048
+        assert 60.0 < per_mma < 80.0, (cg, per_mma)
+
+
 def test_stride2_conv_matches_torch_stride2(ops):
     """OUT_STRIDE2 must equal a real stride-2/pad-1 conv (edvr_arch.py:329,331)."""
     x = torch.randn(2, 64, 26, 34, device="cuda")

@@ -79,6 +79,8 @@ int fill_epi(const eb_epilogue_t* e, int H, int W, int cout_packed, EpiParams* o
     o->out_mode = e->out_mode;
     o->absmean_acc = e->absmean_acc;
     o->f32_blocked = e->f32_blocked;
+    o->res16_wide = (e->res16 && reinterpret_cast<uintptr_t>(e->res16) % 32 == 0 && e->res_pix_stride % 16 == 0 &&
+                     e->res_ch_off % 16 == 0) ? 1 : 0;
     if (e->f32_blocked && (e->out_mode != EB_OUT_SAME || (e->out32 && (e->out32_pix_stride % 32 || e->out32_ch_off % 32)) ||
                            (e->res32 && (e->res_pix_stride % 32 || e->res_ch_off % 32)) || e->res16))
         return fail(EB_ERR_UNSUPPORTED, "f32_blocked needs OUT_SAME, C %% 32 == 0, and no fp16 residual");

@@ -36,6 +36,7 @@ struct EpiParams {
     int out_mode;             // OUT_*
     float* absmean_acc;       // ACT_DCN_PACK: sum |offset| accumulator (optional)
     int f32_blocked;          // res32 / out32 in the tile-blocked layout (blocked32_offset)
+    int res16_wide;           // res16 view is 32-byte aligned per 16 channels: 2 x LDG.256 instead of 4 x LDG.128
 };
 
 // Tile-blocked fp32 layout: float index of (pixel (img,y,x), channel c) for an [N,H,W,C] tensor, C % 32 == 0.
@@ -84,9 +85,17 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
     const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
     if ((G || EK == EK_PLAIN) && p.res16 != nullptr) {
         const __half* r = p.res16 + pix * p.res_pix_stride + p.res_ch_off + c0;
+        uint4 ru[4];
+        if (p.res16_wide) {     // lanes read different pixels: a 32-byte load halves the L1 wavefronts per byte
+            ldg_nc_v8(r, ru[0], ru[1]);
+            ldg_nc_v8(r + 16, ru[2], ru[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ru[q] = ldg_nc_v4(r + q * 8);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            uint4 u = ldg_nc_v4(r + q * 8);
+            const uint4 u = ru[q];
             float2 f0 = unpack_h2(u.x), f1 = unpack_h2(u.y), f2 = unpack_h2(u.z), f3 = unpack_h2(u.w);
             v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
             v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;

@@ -28,11 +28,11 @@ class _Arena:
         self.device = device
         self.bufs = {}
 
-    def act(self, name, N, H, W, C):
+    def act(self, name, N, H, W, C, zero=False):
         key = (name, N, H, W, C)
         t = self.bufs.get(key)
         if t is None:
-            t = torch.empty(N, H, W, C, dtype=torch.float16, device=self.device)
+            t = (torch.zeros if zero else torch.empty)(N, H, W, C, dtype=torch.float16, device=self.device)
             self.bufs[key] = t
         return View(t)
 
@@ -237,7 +237,24 @@ class EDVREngine:
         # conv_last on the tensor cores: 3 output channels padded to one 32-wide tile, fp32 NCHW store (+ eb_add_base)
         self.last_tc = ops.pack_conv(sd["conv_last.weight"].float(), sd["conv_last.bias"].float(), cout_packed=32) \
             if sd["conv_last.weight"].shape[1] % 64 == 0 else None
+        # conv_first (3 -> C) on the tensor cores: the image goes into channels 0-2 of a zero-filled 64-channel NHWC buffer and
+        # the weights are zero-padded to 64 input channels (exact: the extra products are 0); the CUDA-core kernel it replaces
+        # was FMA-issue bound at ~3x this time
+        wf, bf = raw["first"]
+        wpad = torch.zeros(wf.shape[0], 64, 3, 3, dtype=torch.float32, device=wf.device)
+        wpad[:, :3] = wf
+        self.first_tc = ops.pack_conv(wpad, bf) if wf.shape[0] % 32 == 0 else None
         self.p, self.raw = p, raw
+
+    def _first(self, x, out):
+        """conv_first + lrelu of an fp32 NCHW image batch into the NHWC fp16 view `out` (edvr_arch.py:371-376,254)."""
+        if self.first_tc is None or self.first_tc.wpair is None:
+            ops.conv_first(x, *self.raw["first"], out, act=ACT_LRELU)
+            return
+        N, _, H, W = x.shape
+        pad = self.arena.act("first_in", N, H, W, 64, zero=True)
+        ops.nchw_to_nhwc(x, out=View(pad.t, 0, 3))
+        ops.conv2d(self.first_tc, [pad], out16=out, act=ACT_LRELU)
 
     # ------------------------------------------------------------------ helpers
     def _resblock16(self, key, x, tmp, out):
@@ -271,7 +288,7 @@ class EDVREngine:
         else:
             h, w = hin, win
             l1 = a.act("l1a", N, h, w, C)
-            ops.conv_first(x.view(N, 3, h, w), *self.raw["first"], l1, act=ACT_LRELU)
+            self._first(x.view(N, 3, h, w), l1)
         tmp, alt = a.act("l1t", N, h, w, C), a.act("l1b", N, h, w, C)
         for i in range(self.n_extract):
             self._resblock16(f"feature_extraction.{i}", l1, tmp, alt)
@@ -331,7 +348,7 @@ class EDVREngine:
         N, _, H, W = x.shape
         pre = "predeblur."
         f = a.act("pd_first", N, H, W, C)
-        ops.conv_first(x, *self.raw["first"], f, act=ACT_LRELU)
+        self._first(x, f)
         if self.hr_in:
             f1 = a.act("pd_hr1", N, H // 2, W // 2, C)
             ops.conv2d(p[pre + "stride_conv_hr1"], [f], out16=f1, act=ACT_LRELU, out_mode=OUT_STRIDE2)

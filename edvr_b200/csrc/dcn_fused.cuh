@@ -60,11 +60,11 @@ struct DcnParams {
 
 struct DcnCorner {
     float w[4];
-    const __half* base;   // address of (h_low, w_low), channel 0 of the view
-    int dW;               // element offsets of the 4 corners: 0, dx, dy, dy+dx
-    int dH;
-    unsigned valid;       // bit c set if corner c contributes
+    int off[4];           // element offset of each corner from the image base (channel 0 of the view); -1: contributes 0
 };
+
+// corners that contribute nothing are read from here: unconditional loads, no zero-initialised registers, no NaN hazard
+__device__ __align__(32) const uint32_t dcn_zero32[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 struct DcnOff { float dh, dw, mk; };
 
@@ -258,12 +258,10 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             }
             return o;
         };
-        auto corner = [&](const Pix& px, const __half* ximg, int ki, int kj, const DcnOff& o) -> DcnCorner {
+        const int ixps = static_cast<int>(xps), ixrow = static_cast<int>(xrow);
+        auto corner = [&](const Pix& px, int ki, int kj, const DcnOff& o) -> DcnCorner {
             DcnCorner c;
-            c.valid = 0;
-            c.base = ximg;
-            c.dW = static_cast<int>(xps);
-            c.dH = static_cast<int>(xrow);
+            c.off[0] = c.off[1] = c.off[2] = c.off[3] = -1;
             c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0.f;
             const float h_im = static_cast<float>(px.hb + ki * dil) + o.dh;
             const float w_im = static_cast<float>(px.wb + kj * dil_w) + o.dw;
@@ -273,11 +271,15 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                 const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
                 c.w[0] = hh * hw * o.mk; c.w[1] = hh * lw * o.mk; c.w[2] = lh * hw * o.mk; c.w[3] = lh * lw * o.mk;
                 const bool t = hl >= 0, b = hl + 1 <= H - 1, l = wl >= 0, r = wl + 1 <= W - 1;
-                c.valid = (t && l ? 1u : 0u) | (t && r ? 2u : 0u) | (b && l ? 4u : 0u) | (b && r ? 8u : 0u);
-                c.base = ximg + hl * xrow + wl * xps;
+                const int base = hl * ixrow + wl * ixps;
+                c.off[0] = (t && l) ? base : -1;
+                c.off[1] = (t && r) ? base + ixps : -1;
+                c.off[2] = (b && l) ? base + ixrow : -1;
+                c.off[3] = (b && r) ? base + ixrow + ixps : -1;
             }
             return c;
         };
+        const __half* const zbuf = reinterpret_cast<const __half*>(dcn_zero32);
 
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -316,8 +318,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                     DcnCorner cn[DC_NPX][2];
 #pragma unroll
                     for (int i = 0; i < DC_NPX; ++i) {
-                        cn[i][0] = corner(px[i], ximg, ki, kj, nxt[i][0]);
-                        cn[i][1] = two ? corner(px[i], ximg, ki, kj, nxt[i][1]) : cn[i][0];
+                        cn[i][0] = corner(px[i], ki, kj, nxt[i][0]);
+                        cn[i][1] = two ? corner(px[i], ki, kj, nxt[i][1]) : cn[i][0];
                     }
                     // all 16 corner loads in flight before anything is consumed
                     uint4 u[DC_NPX][2][4];
@@ -325,29 +327,23 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                         // the lane's two K atoms (one deformable group, 32 contiguous bytes) in ONE load per corner: the four
                         // lanes of a pixel fetch a full 128-byte line per instruction (half the L1 wavefronts of 2 x LDG.128)
 #pragma unroll
-                        for (int i = 0; i < DC_NPX; ++i) {
-                            const DcnCorner& c = cn[i][0];
-                            const __half* b = c.base + ch;
+                        for (int i = 0; i < DC_NPX; ++i)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) u[i][0][k] = u[i][1][k] = make_uint4(0, 0, 0, 0);
-                            if (c.valid & 1u) ldg_nc_v8(b, u[i][0][0], u[i][1][0]);
-                            if (c.valid & 2u) ldg_nc_v8(b + c.dW, u[i][0][1], u[i][1][1]);
-                            if (c.valid & 4u) ldg_nc_v8(b + c.dH, u[i][0][2], u[i][1][2]);
-                            if (c.valid & 8u) ldg_nc_v8(b + c.dH + c.dW, u[i][0][3], u[i][1][3]);
-                        }
-                    } else
+                            for (int k = 0; k < 4; ++k) {
+                                const int o = cn[i][0].off[k];
+                                ldg_nc_v8(o >= 0 ? ximg + o + ch : zbuf, u[i][0][k], u[i][1][k]);
+                            }
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < DC_NPX; ++i)
+                        for (int i = 0; i < DC_NPX; ++i)
 #pragma unroll
-                        for (int a = 0; a < 2; ++a) {
-                            const DcnCorner& c = cn[i][a];
-                            const __half* b = c.base + ch + a * 8;
-                            u[i][a][0] = u[i][a][1] = u[i][a][2] = u[i][a][3] = make_uint4(0, 0, 0, 0);
-                            if (c.valid & 1u) u[i][a][0] = ldg_nc_v4(b);
-                            if (c.valid & 2u) u[i][a][1] = ldg_nc_v4(b + c.dW);
-                            if (c.valid & 4u) u[i][a][2] = ldg_nc_v4(b + c.dH);
-                            if (c.valid & 8u) u[i][a][3] = ldg_nc_v4(b + c.dH + c.dW);
-                        }
+                            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int o = cn[i][a].off[k];
+                                    u[i][a][k] = ldg_nc_v4(o >= 0 ? ximg + o + ch + a * 8 : zbuf);
+                                }
+                    }
                     // prefetch the next stage's offsets (next tap of this chunk, or tap 0 of the next chunk)
                     {
                         const bool last_tap = tap + 1 == K;

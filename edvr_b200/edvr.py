@@ -10,6 +10,8 @@ Inference (torch.no_grad) runs entirely on the sm_100a kernels.  With autograd e
 evaluated with differentiable PyTorch ops around the custom DCN autograd Function (edvr_b200/dcn.py) —
 the training configuration (BASELINE cfg 5) is a later row of the scope table.
 """
+import logging
+
 import torch
 from torch import nn
 from torch.nn import functional as F
@@ -308,3 +310,48 @@ class EDVR(nn.Module):
         if torch.is_grad_enabled() or not x.is_cuda or self.num_feat % 64:
             return self._autograd_forward(x)
         return self.engine().forward(x.float()).to(x.dtype)
+
+    @torch.no_grad()
+    def forward_video(self, frames, clips_per_step=4, padding="reflection_circle"):
+        """Restore every frame of one sequence [F, 3, h, w] with sliding windows (padding modes of the reference datasets);
+        per-frame features are shared between windows - see EDVREngine.forward_video."""
+        return self.engine().forward_video(frames.float(), clips_per_step, padding).to(frames.dtype)
+
+
+def load_network(net, load_path, strict=True, param_key="params"):
+    """Checkpoint wire format of the reference (`BaseModel.load_network`, basicsr/models/base_model.py:238-262; save side
+    `save_network` :171-201): a `torch.save`d dict whose `param_key` entry ('params'; None = the file IS the state_dict)
+    holds the state_dict, possibly with DataParallel's 'module.' prefix on every key.  Same behaviour: key differences are
+    logged, with strict=False tensors of a different size are skipped, then `load_state_dict(strict=strict)`."""
+    if isinstance(net, (nn.DataParallel, nn.parallel.DistributedDataParallel)):
+        net = net.module
+    log = logging.getLogger("basicsr")
+    log.info(f"Loading {net.__class__.__name__} model from {load_path}.")
+    load_net = torch.load(load_path, map_location=lambda storage, loc: storage)
+    if param_key is not None:
+        load_net = load_net[param_key]
+    load_net = {(k[7:] if k.startswith("module.") else k): v for k, v in load_net.items()}
+    cur = net.state_dict()
+    cur_keys, new_keys = set(cur.keys()), set(load_net.keys())
+    if cur_keys != new_keys:
+        log.warning("Current net - loaded net:")
+        for k in sorted(cur_keys - new_keys):
+            log.warning(f"  {k}")
+        log.warning("Loaded net - current net:")
+        for k in sorted(new_keys - cur_keys):
+            log.warning(f"  {k}")
+    if not strict:
+        for k in cur_keys & new_keys:
+            if cur[k].size() != load_net[k].size():
+                log.warning(f"Size different, ignore [{k}]: crt_net: {cur[k].shape}; load_net: {load_net[k].shape}")
+                load_net[k + ".ignore"] = load_net.pop(k)
+    net.load_state_dict(load_net, strict=strict)
+    return net
+
+
+def save_network(net, save_path, param_key="params"):
+    """Write a checkpoint the reference's `load_network` reads (base_model.py:171-201: 'module.' stripped, CPU tensors)."""
+    if isinstance(net, (nn.DataParallel, nn.parallel.DistributedDataParallel)):
+        net = net.module
+    sd = {(k[7:] if k.startswith("module.") else k): v.cpu() for k, v in net.state_dict().items()}
+    torch.save({param_key: sd} if param_key is not None else sd, save_path)

@@ -53,6 +53,22 @@ class _Arena:
         return t
 
 
+def frame_window_indices(center, n_frames, window, padding="reflection"):
+    """Indices of the `window` frames read around `center` in a sequence of n_frames, out-of-range positions folded back by
+    `padding` exactly as the reference dataset code does (basicsr/data/data_util.py:35-88; e.g. center 0, window 5:
+    replicate 0 0 0 1 2 | reflection 2 1 0 1 2 | reflection_circle 4 3 0 1 2 | circle 3 4 0 1 2)."""
+    if window % 2 != 1:
+        raise AssertionError("num_frames should be an odd number.")
+    if padding not in ("replicate", "reflection", "reflection_circle", "circle"):
+        raise AssertionError(f"Wrong padding mode: {padding}.")
+    last, half = n_frames - 1, window // 2
+    fold_low = {"replicate": lambda i: 0, "reflection": lambda i: -i,
+                "reflection_circle": lambda i: center + half - i, "circle": lambda i: window + i}[padding]
+    fold_high = {"replicate": lambda i: last, "reflection": lambda i: 2 * last - i,
+                 "reflection_circle": lambda i: (center - half) - (i - last), "circle": lambda i: i - window}[padding]
+    return [fold_low(i) if i < 0 else fold_high(i) if i > last else i for i in range(center - half, center + half + 1)]
+
+
 def pack_dcn_site(p, sd, key, dg):
     p[key] = ops.pack_conv(sd[key + ".weight"], sd.get(key + ".bias"))
     p[key + ".conv_offset"] = ops.pack_conv(sd[key + ".conv_offset.weight"], sd[key + ".conv_offset.bias"],
@@ -267,28 +283,23 @@ class EDVREngine:
         return None if self._absmean_counts is None else (self.absmean[:4].cpu() / self._absmean_counts)
 
     # ------------------------------------------------------------------ forward
-    @torch.no_grad()
-    def forward(self, x):
-        """x: fp32 [B, T, 3, h, w] on the device -> fp32 [B, 3, 4h, 4w] (or [B,3,h,w] when hr_in)."""
-        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[1] == self.T
-        x = x.contiguous()
-        B, T, _, hin, win = x.shape
+    def _check_hw(self, hin, win):
         if self.hr_in:
             assert hin % 16 == 0 and win % 16 == 0, "The height and width must be multiple of 16."
         else:
             assert hin % 4 == 0 and win % 4 == 0, "The height and width must be multiple of 4."
-        a, p, C = self.arena, self.p, self.C
-        N = B * T
-        self.absmean.zero_()
 
-        # ---- per-frame L1 features
+    def _features(self, frames):
+        """Per-frame pyramid (edvr_arch.py:371-388): fp32 [N,3,hin,win] -> L1/L2/L3 NHWC fp16 views (arena buffers) and (h, w)."""
+        a, p, C = self.arena, self.p, self.C
+        N, _, hin, win = frames.shape
         if self.with_predeblur:
-            l1 = self._predeblur(x.view(N, 3, hin, win))
+            l1 = self._predeblur(frames)
             h, w = (hin // 4, win // 4) if self.hr_in else (hin, win)
         else:
             h, w = hin, win
             l1 = a.act("l1a", N, h, w, C)
-            self._first(x.view(N, 3, h, w), l1)
+            self._first(frames, l1)
         tmp, alt = a.act("l1t", N, h, w, C), a.act("l1b", N, h, w, C)
         for i in range(self.n_extract):
             self._resblock16(f"feature_extraction.{i}", l1, tmp, alt)
@@ -300,7 +311,15 @@ class EDVREngine:
         l3t, l3 = a.act("l3t", N, h3, w3, C), a.act("l3", N, h3, w3, C)
         ops.conv2d(p["conv_l3_1"], [l2], out16=l3t, act=ACT_LRELU, out_mode=OUT_STRIDE2)
         ops.conv2d(p["conv_l3_2"], [l3t], out16=l3, act=ACT_LRELU)
+        return l1, l2, l3, h, w
 
+    def _tail(self, l1, l2, l3, B, h, w, base, base_img_stride):
+        """PCD alignment, fusion, reconstruction and upsampling for B windows whose B*T frame pyramids are l1/l2/l3
+        (edvr_arch.py:390-420).  base: fp32 centre frames, image n at base.data_ptr() + n * base_img_stride elements."""
+        a, p, C, T = self.arena, self.p, self.C, self.T
+        N = B * T
+        h2, w2, h3, w3 = h // 2, w // 2, h // 4, w // 4
+        self.absmean.zero_()
         # ---- PCD alignment, all N = B*T neighbour frames at once; reference frame = clip centre
         ref_map = (T, T, 0, self.center)
         self._absmean_counts = torch.tensor([N * h3 * w3, N * h2 * w2, N * h * w, N * h * w],
@@ -334,13 +353,57 @@ class EDVREngine:
         hr = a.act("hr", B, 4 * h, 4 * w, 64)
         ops.conv2d(p["conv_hr"], [u2], out16=hr, act=ACT_LRELU)
         out = torch.empty(B, 3, 4 * h, 4 * w, dtype=torch.float32, device=self.device)
-        xc = x[:, self.center]          # [B,3,hin,win] view: image stride T*3*hin*win
         if self.last_tc is not None:
             ops.conv2d(self.last_tc, [hr], act=ACT_NONE, out_nchw=out, nchw_C=3)
-            ops.add_base(xc, T * 3 * hin * win, 1 if self.hr_in else 4, out)
+            ops.add_base(base, base_img_stride, 1 if self.hr_in else 4, out)
         else:
-            ops.conv_last(hr, *self.raw["last"], xc, T * 3 * hin * win, 1 if self.hr_in else 4, out)
+            ops.conv_last(hr, *self.raw["last"], base, base_img_stride, 1 if self.hr_in else 4, out)
         return out
+
+    @torch.no_grad()
+    def forward(self, x):
+        """x: fp32 [B, T, 3, h, w] on the device -> fp32 [B, 3, 4h, 4w] (or [B,3,h,w] when hr_in)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[1] == self.T
+        x = x.contiguous()
+        B, T, _, hin, win = x.shape
+        self._check_hw(hin, win)
+        l1, l2, l3, h, w = self._features(x.view(B * T, 3, hin, win))
+        xc = x[:, self.center]          # [B,3,hin,win] view: image stride T*3*hin*win
+        return self._tail(l1, l2, l3, B, h, w, xc, T * 3 * hin * win)
+
+    @torch.no_grad()
+    def forward_video(self, frames, clips_per_step=4, padding="reflection_circle"):
+        """Sliding-window inference over one sequence: frames fp32 [F, 3, h, w] -> fp32 [F, 3, 4h, 4w], output i
+        restored from the window `frame_window_indices(i, F, T, padding)` like the reference's test loop
+        (video_base_model.py:44-70 over datasets built with data_util.py:35-88).  The per-frame pyramid (conv_first, feature
+        extraction, L2/L3: 24 % of the FLOPs of a clip) is computed ONCE per frame instead of once per window it appears in;
+        results are bit-identical to forward() on the explicitly gathered windows."""
+        assert frames.is_cuda and frames.dtype == torch.float32 and frames.dim() == 4 and frames.shape[1] == 3
+        frames = frames.contiguous()
+        F_, _, hin, win = frames.shape
+        self._check_hw(hin, win)
+        T, C, a = self.T, self.C, self.arena
+        per_chunk = max(1, clips_per_step * T)
+        vid = None
+        for s in range(0, F_, per_chunk):
+            l1, l2, l3, h, w = self._features(frames[s:s + per_chunk])
+            if vid is None:
+                vid = [torch.empty(F_, t.H, t.W, C, dtype=torch.float16, device=self.device) for t in (l1, l2, l3)]
+            for dst, src in zip(vid, (l1, l2, l3)):
+                dst[s:s + src.N].copy_(src.t)
+        outs = []
+        for c0 in range(0, F_, clips_per_step):
+            centers = list(range(c0, min(c0 + clips_per_step, F_)))
+            idx = torch.tensor([j for c in centers for j in frame_window_indices(c, F_, T, padding)], device=self.device)
+            B = len(centers)
+            win_feats = []
+            for name, src in zip(("vw1", "vw2", "vw3"), vid):
+                dst = a.act(name, B * T, src.shape[1], src.shape[2], C)
+                torch.index_select(src, 0, idx, out=dst.t)
+                win_feats.append(dst)
+            base = frames[centers[0]:centers[-1] + 1]
+            outs.append(self._tail(*win_feats, B, h, w, base, 3 * hin * win))
+        return torch.cat(outs, 0)
 
     # ------------------------------------------------------------------ PredeblurModule (edvr_arch.py:250-269)
     def _predeblur(self, x):

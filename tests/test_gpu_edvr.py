@@ -145,3 +145,19 @@ def test_training_step_gradients_vs_oracle_graph():
         err = float((a - b).norm() / b.norm().clamp_min(1e-20))
         print(f"grad {key}: rel-L2 {err:.2e}")
         assert err < 2e-2, (key, err)
+
+
+def test_sliding_window_video_inference_is_bit_identical_to_per_clip():
+    """forward_video shares the per-frame pyramid between windows; every output frame must equal forward()
+    on the explicitly gathered window (same kernels on the same values => torch.equal), for two padding modes."""
+    from edvr_b200.engine import EDVREngine, frame_window_indices
+    from oracle import edvr_ref
+    kw = dict(num_feat=64, num_frame=5, deformable_groups=8, num_extract_block=2, num_reconstruct_block=3)
+    eng = EDVREngine(edvr_ref.make_state_dict(**kw, seed=11), num_frame=5)
+    frames = torch.rand(9, 3, 24, 32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    for padding in ("reflection_circle", "replicate"):
+        video = eng.forward_video(frames, clips_per_step=4, padding=padding)
+        assert video.shape == (9, 3, 96, 128)
+        for c in (0, 1, 4, 8):
+            clip = frames[frame_window_indices(c, 9, 5, padding)].unsqueeze(0)
+            assert torch.equal(eng.forward(clip)[0], video[c]), (padding, c)

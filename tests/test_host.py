@@ -103,3 +103,53 @@ def test_reference_tree_imports_unchanged_with_b1_shim():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert int(r.stdout.strip().splitlines()[-1]) > 50
+
+
+def test_checkpoint_wire_format_roundtrip(tmp_path):
+    """the reference's checkpoint format ({'params': state_dict}, optional 'module.' prefixes,
+    base_model.py:171-262) loads into the drop-in EDVR with strict=True and is written back in the same format."""
+    from edvr_b200.edvr import EDVR, load_network, save_network
+    from oracle import edvr_ref
+    kw = dict(num_feat=64, num_frame=3, deformable_groups=8, num_extract_block=1, num_reconstruct_block=2)
+    sd = edvr_ref.make_state_dict(**kw, seed=3)
+    path = tmp_path / "EDVR_ckpt.pth"
+    torch.save({"params": {"module." + k: v for k, v in sd.items()}}, path)          # as saved from a DataParallel wrapper
+    net = load_network(EDVR(center_frame_idx=None, **kw), str(path), strict=True)
+    got = net.state_dict()
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    out = tmp_path / "resaved.pth"
+    save_network(net, str(out))
+    back = torch.load(out)
+    assert set(back) == {"params"} and all(torch.equal(back["params"][k], sd[k]) for k in sd)
+    # strict=False skips tensors whose size differs (base_model.py:229-236) instead of raising
+    bad = dict(sd)
+    bad["conv_first.weight"] = torch.zeros(64, 3, 5, 5)
+    torch.save({"params": bad}, path)
+    load_network(EDVR(center_frame_idx=None, **kw), str(path), strict=False)
+    with pytest.raises(RuntimeError):
+        load_network(EDVR(center_frame_idx=None, **kw), str(path), strict=True)
+
+
+def test_frame_window_indices_follow_reference_padding_modes():
+    """The four padding modes of the reference's sequence datasets (examples of data_util.py:46-53) and, when the reference
+    tree is mounted, every (mode, length, window, centre) against its generate_frame_indices."""
+    from edvr_b200.engine import frame_window_indices as f
+    assert f(0, 100, 5, "replicate") == [0, 0, 0, 1, 2]
+    assert f(0, 100, 5, "reflection") == [2, 1, 0, 1, 2]
+    assert f(0, 100, 5, "reflection_circle") == [4, 3, 0, 1, 2]
+    assert f(0, 100, 5, "circle") == [3, 4, 0, 1, 2]
+    assert f(99, 100, 5, "reflection") == [97, 98, 99, 98, 97]
+    assert f(50, 100, 7, "reflection") == list(range(47, 54))
+    with pytest.raises(AssertionError):
+        f(0, 10, 4)
+    with pytest.raises(AssertionError):
+        f(0, 10, 5, "zeros")
+    ref_file = "/root/reference/basicsr/data/data_util.py"
+    if os.path.exists(ref_file):
+        src = open(ref_file).read()
+        ns = {}
+        exec(src[src.index("def generate_frame_indices"):src.index("def paired_paths_from_lmdb")], ns)
+        for pad in ("replicate", "reflection", "reflection_circle", "circle"):
+            for n in (7, 10, 33):
+                for t in (3, 5, 7):
+                    assert all(f(c, n, t, pad) == ns["generate_frame_indices"](c, n, t, pad) for c in range(n))

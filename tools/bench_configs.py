@@ -41,7 +41,7 @@ def ref_fns():
         gx, goff, gm, gw, gb = (torch.zeros_like(t) for t in (x, off, mask, w, b))
         ext.modulated_deform_conv_backward(x, w, b, x.new_empty(0), off, mask, x.new_empty(0), gx, gw, gb, goff, gm, go, 3, 3,
                                            1, 1, 1, 1, 1, 1, 1, dg, True)
-        return gx
+        return gx, goff, gm, gw, gb
 
     return fwd, bwd
 
@@ -84,7 +84,92 @@ def edvr_cfg(name, kw, shape, hr_in=False, B=1):
             "ref_cuda_ms_per_clip": ms_ref, "ref_cuda_frames_per_s": 1e3 / ms_ref}
 
 
+def train_cfg5(B=4):
+    """BASELINE cfg 5 (per-GPU slice): EDVR-L t=5, batch 4, LR 64x64 -> GT 256x256, Charbonnier(sum), Adam(4e-4, (0.9, 0.99)):
+    forward + backward + optimizer step.  Ours: edvr_b200.edvr.EDVR under autograd (PyTorch convs around OUR DCN forward and
+    backward kernels).  Reference arm: the same functional graph with the UNMODIFIED reference DCN extension wrapped in an
+    autograd Function.  fp32 parameters, cuDNN TF32 allowed (torch default), no autocast."""
+    from edvr_b200.edvr import EDVR
+    kw = dict(num_feat=128, num_frame=5, num_reconstruct_block=40)
+    sd = edvr_ref.make_state_dict(**kw)
+    x = torch.rand(B, 5, 3, 64, 64, device="cuda")
+    gt = torch.rand(B, 3, 256, 256, device="cuda")
+    charb = lambda p, t: torch.sqrt((p - t) ** 2 + 1e-12).sum()
+    torch.backends.cudnn.benchmark = True
+
+    net = EDVR(center_frame_idx=None, **kw).cuda().train()
+    net.load_state_dict(sd, strict=True)
+    opt = torch.optim.Adam(net.parameters(), lr=4e-4, betas=(0.9, 0.99))
+
+    def step_ours():
+        opt.zero_grad(set_to_none=True)
+        loss = charb(net(x), gt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    ms_ours = timeit(step_ours, iters=5, warm=2)
+
+    rf, rb = ref_fns()
+
+    class RefDCN(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, xx, off, mask, w, b, dg):
+            ctx.save_for_backward(xx, off, mask, w, b)
+            ctx.dg = dg
+            return rf(xx.contiguous(), off.contiguous(), mask.contiguous(), w, b, dg)
+
+        @staticmethod
+        def backward(ctx, go):
+            xx, off, mask, w, b = ctx.saved_tensors
+            gx, goff, gm, gw, gb = rb(xx.contiguous(), off.contiguous(), mask.contiguous(), w, b, go.contiguous(), ctx.dg)
+            return gx, goff, gm, gw, gb, None
+
+    params = {k: v.clone().cuda().requires_grad_(True) for k, v in sd.items()}
+    opt_ref = torch.optim.Adam(list(params.values()), lr=4e-4, betas=(0.9, 0.99))
+    dcn = lambda xx, off, mask, w, b, s, p, d, g, dg: RefDCN.apply(xx, off, mask, w, b, dg)
+
+    def step_ref():
+        opt_ref.zero_grad(set_to_none=True)
+        with torch.enable_grad():
+            loss = charb(edvr_ref.edvr_forward.__wrapped__(params, x, dcn=dcn), gt)
+        loss.backward()
+        opt_ref.step()
+        return loss
+
+    ms_ref = timeit(step_ref, iters=3, warm=2)
+    return {"config": "cfg5 EDVR-L t=5 train step, batch 4 x 5x3x64x64 -> 256x256 per GPU", "ours_ms_per_step": ms_ours,
+            "ours_samples_per_s": 1e3 * B / ms_ours, "ref_cuda_ms_per_step": ms_ref, "ref_cuda_samples_per_s": 1e3 * B / ms_ref,
+            "note": "ours = autograd path (PyTorch/cuDNN convs + our DCN fwd/bwd kernels); conv dgrad/wgrad kernels are not built"}
+
+
+def video_cfg3(n_frames=32, B=4):
+    """Application-level mode: one 32-frame 180x320 sequence restored with sliding 7-frame windows
+    (EDVREngine.forward_video: per-frame features computed once) vs the same windows as independent clips."""
+    kw = dict(num_feat=128, num_frame=7, num_reconstruct_block=40)
+    eng = EDVREngine(edvr_ref.make_state_dict(**kw), num_frame=7)
+    frames = torch.rand(n_frames, 3, 180, 320, device="cuda")
+    ms_video = timeit(lambda: eng.forward_video(frames, clips_per_step=B), iters=3, warm=1)
+    x = torch.rand(B, 7, 3, 180, 320, device="cuda")
+    ms_clip = timeit(lambda: eng.forward(x), iters=5)
+    return {"config": f"cfg3 network, {n_frames}-frame sequence, sliding windows, {B} windows per step",
+            "video_ms_per_sequence": ms_video, "video_frames_per_s": 1e3 * n_frames / ms_video,
+            "independent_clips_frames_per_s": 1e3 * B / ms_clip}
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "video":
+        r = video_cfg3()
+        print("cfg3_video", json.dumps(r), flush=True)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(r, open(os.path.join(ROOT, "gpurun_out", "bench_cfg3_video.json"), "w"), indent=1)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        r = train_cfg5()
+        print("cfg5_train_step", json.dumps(r), flush=True)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(r, open(os.path.join(ROOT, "gpurun_out", "bench_cfg5_train.json"), "w"), indent=1)
+        return
     res = {"cfg1_single_dcn_layer_1x64x64x64": dcn_op(1, 64, 64, 64),
            "dcn_L1_1x128x180x320": dcn_op(1, 128, 180, 320),
            "dcn_L2_1x128x90x160": dcn_op(1, 128, 90, 160),

@@ -28,7 +28,7 @@ constexpr int CV_PLANE_BYTES = 325 * 16;              // >= 18*18*16, odd # of 1
 constexpr int CV_A_BUF_BYTES = 8 * CV_PLANE_BYTES;    // 41600
 constexpr int CV_B_STAGE_BYTES = 128 * 128;           // BN(<=128) rows x 64 ch x 2 B
 constexpr int CV_MAX_COUT = 512;
-constexpr int CV_THREADS = 448;
+constexpr int CV_THREADS = 480;          // + warp 14: forwarder (proxy fence between the cp.async loaders and the MMA issuer)
 constexpr int CV_SMEM_BYTES = CV_A_BUFS * CV_A_BUF_BYTES + CV_B_STAGES * CV_B_STAGE_BYTES +
                               CV_MAX_COUT * 4 + 256;
 
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
     uint64_t* a_empty = bars + CV_A_BUFS;                    // [CV_A_BUFS]
     uint64_t* b_full = bars + 2 * CV_A_BUFS;                 // [CV_B_STAGES]
     uint64_t* b_empty = b_full + CV_B_STAGES;                // [CV_B_STAGES]
-    uint64_t* acc_full = b_empty + CV_B_STAGES;              // [2]
+    uint64_t* a_ready = b_empty + CV_B_STAGES;               // [CV_A_BUFS]  forwarder -> MMA issuer
+    uint64_t* acc_full = a_ready + CV_A_BUFS;                // [2]
     uint64_t* acc_empty = acc_full + 2;                // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
     if (has_bias)
         for (int i = threadIdx.x; i < cout_packed; i += blockDim.x) bias_s[i] = P.epi.bias[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < CV_A_BUFS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < CV_A_BUFS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 1); }
         for (int i = 0; i < CV_B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_barrier_init();
@@ -146,45 +147,58 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_igemm_kernel(const ConvPar
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(128, P.BN);
-            const uint32_t lbo_b = static_cast<uint32_t>(P.BN) * 16u;
-            uint32_t a_it = 0, b_it = 0, acc_it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
-                const uint32_t ab = acc_it & 1u;
-                mbar_wait(&acc_empty[ab], ((acc_it >> 1) & 1u) ^ 1u);
+        // ================= MMA issuer: the whole warp runs the loops (uniform control flow), one elected lane issues, so the
+        // descriptors stay in uniform registers (see common.cuh, "lean issue path")
+        const uint32_t idesc = umma_idesc_f16(128, P.BN);
+        const uint32_t lbo_b = static_cast<uint32_t>(P.BN) * 16u;
+        const uint32_t a_hi = umma_desc_hi(RP * 16), b_hi = umma_desc_hi(128);
+        uint32_t a_it = 0, b_it = 0, acc_it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+            const uint32_t ab = acc_it & 1u;
+            mbar_wait(&acc_empty[ab], ((acc_it >> 1) & 1u) ^ 1u);
+            tc_fence_after_sync();
+            for (int c = 0; c < nchunks; ++c, ++a_it) {
+                const uint32_t as = a_it % CV_A_BUFS, aph = (a_it / CV_A_BUFS) & 1u;
+                mbar_wait(&a_ready[as], aph);
                 tc_fence_after_sync();
-                for (int c = 0; c < nchunks; ++c, ++a_it) {
-                    const uint32_t as = a_it % CV_A_BUFS, aph = (a_it / CV_A_BUFS) & 1u;
-                    mbar_wait(&a_full[as], aph);
-                    fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
+                const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_smem + as * CV_A_BUF_BYTES), CV_PLANE_BYTES);
+                for (int t = 0; t < P.taps; ++t, ++b_it) {
+                    const uint32_t bs = b_it % CV_B_STAGES, bph = (b_it / CV_B_STAGES) & 1u;
+                    mbar_wait(&b_full[bs], bph);
                     tc_fence_after_sync();
-                    const uint32_t a_base = smem_u32(a_smem + as * CV_A_BUF_BYTES);
-                    for (int t = 0; t < P.taps; ++t, ++b_it) {
-                        const uint32_t bs = b_it % CV_B_STAGES, bph = (b_it / CV_B_STAGES) & 1u;
-                        mbar_wait(&b_full[bs], bph);
-                        tc_fence_after_sync();
-                        const uint32_t b_base = smem_u32(b_smem + bs * CV_B_STAGE_BYTES);
-                        const int ki = HALO ? t / 3 : 0, kj = HALO ? t % 3 : 0;
-#pragma unroll
-                        for (int sub = 0; sub < 2; ++sub) {
-                            const uint32_t a_tap = a_base + ((ki * RP) + 8 * sub + kj) * 16;
-                            const uint32_t d = tmem_base + ab * 256u + sub * 128u;
+                    const uint32_t b_lo0 = umma_desc_lo(smem_u32(b_smem + bs * CV_B_STAGE_BYTES), lbo_b);
+                    const int ki = HALO ? t / 3 : 0, kj = HALO ? t % 3 : 0;
+                    if (elect_one()) {
+                        if (!(P.dbg & 32)) {
 #pragma unroll
                             for (int k16 = 0; k16 < 4; ++k16) {
-                                const uint64_t ad = umma_desc_nosw(a_tap + k16 * 2 * CV_PLANE_BYTES,
-                                                                   CV_PLANE_BYTES, RP * 16);
-                                const uint64_t bd = umma_desc_nosw(b_base + k16 * 2 * lbo_b, lbo_b, 128);
-                                if (!(P.dbg & 32)) umma_f16(d, ad, bd, idesc, (c | t | k16) != 0 ? 1u : 0u);
+                                const uint32_t a_lo = a_lo0 + (ki * RP + kj) + k16 * (2 * CV_PLANE_BYTES / 16);
+                                const uint32_t b_lo = b_lo0 + k16 * ((2u * lbo_b) >> 4);
+                                const uint32_t acc = (c | t | k16) != 0 ? 1u : 0u;
+                                umma_f16_lohi<1>(tmem_base + ab * 256u, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                                umma_f16_lohi<1>(tmem_base + ab * 256u + 128u, a_lo + 8, a_hi, b_lo, b_hi, idesc, acc);
                             }
                         }
                         umma_commit(&b_empty[bs]);
+                        if (t == P.taps - 1) umma_commit(&a_empty[as]);
+                        if (t == P.taps - 1 && c == nchunks - 1) umma_commit(&acc_full[ab]);
                     }
-                    umma_commit(&a_empty[as]);
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[ab]);
             }
+        }
+    } else if (warp == 14) {
+        // ================= forwarder: "chunk landed" (cp.async, generic proxy) -> fence.proxy.async -> a_ready.  In the issuing
+        // thread this fence drained the MMA queue at every chunk.
+        if (lane == 0) {
+            uint32_t a_it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+                for (int c = 0; c < nchunks; ++c, ++a_it) {
+                    const uint32_t as = a_it % CV_A_BUFS, aph = (a_it / CV_A_BUFS) & 1u;
+                    mbar_wait(&a_full[as], aph);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&a_ready[as]);
+                }
         }
     } else if (warp < 6) {
         // ================= A producers (128 threads): halo tile of one 64-channel chunk

@@ -353,6 +353,14 @@ __device__ __forceinline__ void ldg_nc_v8(const void* p, uint4& lo, uint4& hi) {
                  : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                  : "l"(p));
 }
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_v4(uint32_t saddr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y),
                  "r"(v.z), "r"(v.w)

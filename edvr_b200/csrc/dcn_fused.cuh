@@ -34,7 +34,8 @@ constexpr int DC_NPX = 1;                // output pixels per gather thread and 
 constexpr int DC_GATHER_THREADS = 512 / DC_NPX;
 constexpr int DC_THREADS = 192 + DC_GATHER_THREADS + 32;   // warps 0 B-producer, 1 MMA, 2-5 epilogue, 6.. gather, last: forwarder
 constexpr int DC_MAX_COUT = 512;
-constexpr int DC_SMEM_BYTES = DC_STAGES * (DC_A_BYTES + DC_B_BYTES) + DC_MAX_COUT * 4 + 256;
+constexpr int DC_REC_WORDS = 14;          // packed (pixel, group) record staged per gather thread: 18 offsets + 9 masks = 27 halfs
+constexpr int DC_SMEM_BYTES = DC_STAGES * (DC_A_BYTES + DC_B_BYTES) + DC_MAX_COUT * 4 + 256 + DC_REC_WORDS * DC_GATHER_THREADS * 4;
 constexpr int DC_TILE_H = 16, DC_TILE_W = 8;
 
 enum : int { OFF_NCHW_F32 = 0, OFF_PACK_F16 = 1 };
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
     uint64_t* acc_full = bars + 3 * DC_STAGES;   // [2]
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint32_t* rec_s = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [DC_REC_WORDS][DC_GATHER_THREADS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (P.Wo + DC_TILE_W - 1) / DC_TILE_W;
@@ -238,10 +240,32 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
         const long long ops = P.offpack_pix_stride;
         const bool wide = P.x_wide != 0;
 
+        // Packed-offset pipeline with one group per lane: the 64-byte (pixel, group) record is fetched ONCE per chunk with four
+        // 16-byte loads and parked in shared memory (word-major, so the per-tap reads are conflict-free 4-byte LDS).  Reading
+        // 4 + 2 bytes per tap straight from global memory cost as many L1 wavefronts as the whole corner gather (two loads per
+        // stage, 16 lines each: the lanes of a warp sit in 8 pixels x 4 groups, 64 bytes apart).
+        const bool staged = OFFMODE == OFF_PACK_F16 && cpg >= 16 && DC_NPX == 1;
+        const uint32_t rec_slot = smem_u32(rec_s) + (threadIdx.x - (DC_THREADS - 32 - DC_GATHER_THREADS)) * 4;
         struct Pix { int m, hb, wb; bool ok; const __half* rec; const float* ob; const float* mb; };
+        auto stage_record = [&](const Pix& px, int g) {
+            uint4 r[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[q] = px.ok ? ldg_nc_v4(px.rec + g * 32 + q * 8) : make_uint4(0, 0, 0, 0);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(r);
+#pragma unroll
+            for (int q = 0; q < DC_REC_WORDS; ++q) sts_u32(rec_slot + q * (DC_GATHER_THREADS * 4), w[q]);
+        };
         auto fetch = [&](const Pix& px, int g, int tap) -> DcnOff {
             DcnOff o;
             o.dh = o.dw = o.mk = 0.f;
+            if (staged) {
+                const uint32_t w0 = lds_u32(rec_slot + tap * (DC_GATHER_THREADS * 4));
+                const uint32_t wm = lds_u32(rec_slot + (9 + (tap >> 1)) * (DC_GATHER_THREADS * 4));
+                const float2 hw = unpack_h2(w0);
+                const float2 mm = unpack_h2(wm);
+                o.dh = hw.x; o.dw = hw.y; o.mk = (tap & 1) ? mm.y : mm.x;
+                return o;
+            }
             if (px.ok) {
                 if (OFFMODE == OFF_NCHW_F32) {
                     const float* ob = px.ob + (static_cast<long long>(g) * 2 * K + 2 * tap) * plane;
@@ -301,6 +325,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
             }
             // software pipeline: the (dh, dw, mask) triples of the NEXT stage are fetched while this one is gathered
             int g0 = (kc0 * 8) / cpg, g1 = (kc0 * 8 + 8) / cpg;
+            if (staged) stage_record(px[0], g0);
             DcnOff nxt[DC_NPX][2];
 #pragma unroll
             for (int i = 0; i < DC_NPX; ++i) {
@@ -350,6 +375,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dcn_fused_kernel(const DcnParam
                         const int t1 = last_tap ? 0 : tap + 1;
                         const int h0 = last_tap ? ng0 : g0, h1 = last_tap ? ng1 : g1;
                         if (!(last_tap && chunk + 1 == nchunks)) {
+                            if (staged && last_tap) stage_record(px[0], h0);     // this chunk's record is no longer needed
 #pragma unroll
                             for (int i = 0; i < DC_NPX; ++i) {
                                 nxt[i][0] = fetch(px[i], h0, t1);

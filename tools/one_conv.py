@@ -67,6 +67,9 @@ if __name__ == "__main__":
         out = ops.new_act(4, 180, 320, 128)
         for _ in range(4):
             ops.conv2d(pc, [x], out16=out, act=ops.ACT_RELU)
+        stream = ops.Blocked32(4, 180, 320, 128)             # the trunk's second conv: fp32 residual stream in and out
+        for _ in range(4):
+            ops.conv2d(pc, [x], out16=out, act=ops.ACT_NONE, res32=stream, out32=stream)
         torch.cuda.synchronize()
         sys.exit(0)
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"

@@ -260,6 +260,8 @@ class EDVREngine:
         wpad = torch.zeros(wf.shape[0], 64, 3, 3, dtype=torch.float32, device=wf.device)
         wpad[:, :3] = wf
         self.first_tc = ops.pack_conv(wpad, bf) if wf.shape[0] % 32 == 0 else None
+        if self.first_tc is not None:
+            self.first_tc.cin_real = 3          # algorithmic FLOPs of conv_first, not of the padded GEMM
         self.p, self.raw = p, raw
 
     def _first(self, x, out):

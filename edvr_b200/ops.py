@@ -70,7 +70,7 @@ def new_act(N, H, W, C, device="cuda"):
 class PackedConv:
     """MMA-ready fp16 weights + fp32 bias of one convolution (see eb_pack_weight)."""
 
-    __slots__ = ("w", "b", "BN", "n_tiles", "cin", "ksize", "cout", "wpair")
+    __slots__ = ("w", "b", "BN", "n_tiles", "cin", "ksize", "cout", "wpair", "cin_real")
 
 
 def _choose_bn(cout_packed):
@@ -97,6 +97,7 @@ def pack_conv(weight, bias=None, row_map=None, tap_major=False, cout_packed=None
     p.BN = _choose_bn(cout_packed)
     p.n_tiles = cout_packed // p.BN
     p.cin, p.ksize, p.cout = cin, k, cout
+    p.cin_real = cin        # input channels that carry data (conv_first runs on a zero-padded 64-channel input): FLOP accounting
     nbytes = L.lib().eb_packed_weight_bytes(cin, k * k, p.BN, p.n_tiles)
     p.w = torch.empty(nbytes // 2, dtype=torch.float16, device=weight.device)
     with _Rec("pack_weight", 1):
@@ -204,7 +205,7 @@ def conv2d(pc, srcs, out16=None, act=ACT_NONE, res16=None, res32=None, out32=Non
         detail = (f"{pc.cin}->{pc.cout} {N}x{v0.H}x{v0.W} act{act} mode{out_mode}"
                   f"{' res16' if res16 is not None else ''}{' res32' if res32 is not None else ''}"
                   f"{' out32' if out32 is not None else ''}{' pack' if absmean is not None else ''}")
-    with _Rec(f"conv_igemm_{pc.ksize}x{pc.ksize}", 1, 2.0 * opix * pc.cout * pc.cin * pc.ksize * pc.ksize, detail):
+    with _Rec(f"conv_igemm_{pc.ksize}x{pc.ksize}", 1, 2.0 * opix * pc.cout * pc.cin_real * pc.ksize * pc.ksize, detail):
         if pc.wpair is not None and USE_PAIR and os.environ.get("EDVR_B200_CONV_PAIR", "1") != "0":
             L.check(L.lib().eb_conv2d_pair(arr, len(srcs), N, v0.H, v0.W, pc.ksize, L.ptr(pc.wpair), pc.BN, pc.n_tiles,
                                            ctypes.byref(e), L.stream_ptr()), "eb_conv2d_pair")

@@ -190,13 +190,13 @@ static eb_encode_tiled_fn tensor_map_encoder() {
 }
 
 // NHWC fp16 view as a 5-D tensor {8 channels, W, H, pix_stride / 8 K-atoms, images}; box = halo tile of 4 K-atoms
-static int encode_halo_map(const ConvSrc& S, int H, int W, int n_images, CUtensorMap* out) {
+static int encode_halo_map(const ConvSrc& S, int H, int W, int n_images, int taps, CUtensorMap* out) {
     eb_encode_tiled_fn enc = tensor_map_encoder();
     if (!enc) return fail(EB_ERR_UNSUPPORTED, "conv2d_pair: cuTensorMapEncodeTiled unavailable");
     const cuuint64_t ps = static_cast<cuuint64_t>(S.pix_stride);
     const cuuint64_t dims[5] = {8, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), ps / 8, static_cast<cuuint64_t>(n_images)};
     const cuuint64_t strides[4] = {ps * 2, static_cast<cuuint64_t>(W) * ps * 2, 16, static_cast<cuuint64_t>(H) * W * ps * 2};
-    const cuuint32_t box[5] = {8, CP_RP, CP_RP, 4, 1};
+    const cuuint32_t box[5] = {8, taps == 9 ? CP_RP : CV_TILE, taps == 9 ? CP_RP : CV_TILE, taps == 9 ? 4u : 8u, 1};   // one stage
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(S.ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -218,10 +218,11 @@ int eb_pack_weight_pair(const float* w, int cout, int cin, int ktaps, const int*
 }
 
 int eb_conv2d_pair_supported(int cin, int ksize, int BN, int n_tiles_n) {
-    // 1x1 layers have too little work per 32-channel stage for this pipeline (measured slower than conv_igemm)
-    if (cin < 64 || cin % 64 || ksize != 3 || BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1) return 0;
+    if (cin < 64 || cin % 64 || (ksize != 3 && ksize != 1) || BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1) return 0;
     if (n_tiles_n > num_sms() / 2 || tensor_map_encoder() == nullptr) return 0;
     // 1: each CTA keeps its half of the weights resident in shared memory; 2: weights stream with the activation stages
+    // (always for 1x1 layers: 64-channel stages, no halo)
+    if (ksize == 1) return getenv("EDVR_B200_PAIR_1X1_OFF") ? 0 : 2;
     return static_cast<long long>(cin) * ksize * ksize * (BN / 2) * 2 <= CP_W_BYTES ? 1 : 2;
 }
 
@@ -396,17 +397,17 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
         const ConvSrc& S = P.src[i];
         const int last = N - 1;       // largest source image index the kernel can ask for
         const int n_images = (last / S.div) * S.mul + ((last < S.div ? last : S.div - 1)) * (S.keep > 0 ? S.keep : 0) + S.add + 1;
-        if (int rc = encode_halo_map(S, H, W, n_images < 1 ? 1 : n_images, &PP.tmap[i])) return rc;
+        if (int rc = encode_halo_map(S, H, W, n_images < 1 ? 1 : n_images, P.taps, &PP.tmap[i])) return rc;
     }
     if (nsrc == 1) PP.tmap[1] = PP.tmap[0];
     PP.tmap_w = PP.tmap[0];
     if (!resident) {
         // packed weights as rows of 256 fp16; one box = the (BN/2) x 9 x 32 slice one CTA needs for one 32-channel chunk
         eb_encode_tiled_fn enc = tensor_map_encoder();
-        const cuuint64_t total = static_cast<cuuint64_t>(n_tiles_n) * BN * cin * 9;          // fp16 elements
+        const cuuint64_t total = static_cast<cuuint64_t>(n_tiles_n) * BN * cin * P.taps;     // fp16 elements
         const cuuint64_t dims[2] = {256, total / 256};
         const cuuint64_t strides[1] = {512};
-        const cuuint32_t box[2] = {256, static_cast<cuuint32_t>(9 * 4 * (BN / 2) * 16 / 512)};
+        const cuuint32_t box[2] = {256, static_cast<cuuint32_t>((P.taps == 9 ? 9 * 4 : 8) * (BN / 2) * 16 / 512)};   // one stage
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = enc(&PP.tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(P.wpack), dims, strides, box,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -432,7 +433,7 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * nclusters);
     cfg.blockDim = dim3(CP_THREADS);
-    cfg.dynamicSmemBytes = resident ? CP_SMEM_BYTES : CP_SMEM_BYTES_STREAM;
+    cfg.dynamicSmemBytes = P.taps == 1 ? CP_SMEM_BYTES_1X1 : resident ? CP_SMEM_BYTES : CP_SMEM_BYTES_STREAM;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -443,7 +444,10 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
     cudaError_t err = cudaSuccess;
 #define EB_LAUNCH_CP(EK_, TO_)                                                                         \
     do {                                                                                               \
-        if (resident) {                                                                                \
+        if (P.taps == 1) {                                                                             \
+            if (int rc = set_smem(conv_pair_kernel<EK_, TO_, false, 1>, CP_SMEM_BYTES_1X1)) return rc; \
+            err = cudaLaunchKernelEx(&cfg, conv_pair_kernel<EK_, TO_, false, 1>, PP);                  \
+        } else if (resident) {                                                                         \
             if (int rc = set_smem(conv_pair_kernel<EK_, TO_, true>, CP_SMEM_BYTES)) return rc;         \
             err = cudaLaunchKernelEx(&cfg, conv_pair_kernel<EK_, TO_, true>, PP);                      \
         } else {                                                                                       \

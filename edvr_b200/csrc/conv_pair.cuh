@@ -1,5 +1,5 @@
-// conv_pair.cuh — 3x3 (pad 1) convolution for layers whose weights fit in shared memory (K * BN <= 147456
-// elements per CTA pair, e.g. 128 -> 128 3x3), as an implicit GEMM issued by CTA PAIRS (tcgen05 cta_group::2).
+// conv_pair.cuh — 3x3 (pad 1) and 1x1 convolutions as an implicit GEMM issued by CTA PAIRS (tcgen05 cta_group::2); weights
+// resident in shared memory when they fit (K * BN <= 147456 elements per CTA pair, e.g. 128 -> 128 3x3), streamed otherwise.
 //
 // Why (all measured on B200, tools/mma_rate.py + tools/one_conv.py, profiles/r01_one_conv_*.log):
 //   * back-to-back tcgen05.mma run at their floor (64 cycles for 128x128x16) in every layout, so the single-CTA
@@ -43,6 +43,10 @@ constexpr int CP_OUT_STAGE_BYTES = 32 * 64;                 // per epilogue warp
 constexpr int CP_W_STAGE_BYTES = 9 * 4 * 64 * 16;           // streamed mode: weights of one chunk, BN/2 <= 64 rows
 constexpr int CP_SMEM_BYTES = CP_W_BYTES + 8 * CP_OUT_STAGE_BYTES + CP_A_STAGES * CP_A_STAGE_BYTES + 128 * 4 + 256;
 constexpr int CP_SMEM_BYTES_STREAM = 8 * CP_OUT_STAGE_BYTES + CP_A_STAGES * (CP_A_STAGE_BYTES + CP_W_STAGE_BYTES) + 128 * 4 + 256;
+// 1x1 layers: no halo, 64 channels per stage (eight K atoms of a 16x16 tile = 32 KB) + 8 KB of streamed weights
+constexpr int CP1_A_STAGE_BYTES = 8 * CV_TILE * CV_TILE * 16;
+constexpr int CP1_W_STAGE_BYTES = 4 * 2 * 64 * 16;
+constexpr int CP_SMEM_BYTES_1X1 = 8 * CP_OUT_STAGE_BYTES + CP_A_STAGES * (CP1_A_STAGE_BYTES + CP1_W_STAGE_BYTES) + 128 * 4 + 256;
 
 struct PairParams {
     ConvParams c;
@@ -52,12 +56,20 @@ struct PairParams {
     int tma_out;                // 1: out16 leaves through tmap_out
 };
 
-template <int EK, bool TMA_OUT, bool RESIDENT>
+template <int EK, bool TMA_OUT, bool RESIDENT, int TAPS = 9>
 __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_constant__ PairParams PP) {
     const ConvParams& P = PP.c;
     extern __shared__ __align__(1024) uint8_t smem[];
+    static_assert(TAPS == 9 || (TAPS == 1 && !RESIDENT), "1x1 layers stream their weights");
+    constexpr int RP = TAPS == 9 ? CP_RP : CV_TILE;           // edge of the activation tile in shared memory
+    constexpr int CH = TAPS == 9 ? CP_CH : 64;                // channels per stage
+    constexpr int KSTEPS = CH / 16;                           // K16 steps per tap and stage
+    constexpr int NSTEP = TAPS * KSTEPS;                      // (tap, K16) steps per stage = MMAs per 128-pixel half
+    constexpr int PLANE_BYTES = RP * RP * 16;
+    constexpr int A_STAGE_BYTES = (CH / 8) * PLANE_BYTES;
+    constexpr int W_STAGE_BYTES = NSTEP * 2 * 64 * 16;        // streamed weights of one stage at BN/2 = 64 rows
     // resident: [weights 144 KB][output staging 16 KB][3 activation stages]; streamed: [output staging][3 x (activations, weights)]
-    constexpr int STAGE_STRIDE = RESIDENT ? CP_A_STAGE_BYTES : CP_A_STAGE_BYTES + CP_W_STAGE_BYTES;
+    constexpr int STAGE_STRIDE = RESIDENT ? A_STAGE_BYTES : A_STAGE_BYTES + W_STAGE_BYTES;
     uint8_t* w_smem = smem;
     uint8_t* o_smem = smem + (RESIDENT ? CP_W_BYTES : 0);    // 8 x 2 KB output staging (1024-byte aligned)
     uint8_t* a_smem = o_smem + 8 * CP_OUT_STAGE_BYTES;
@@ -74,17 +86,16 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    constexpr int RP = CP_RP;
 
     const int tiles_x = (P.W + CV_TILE - 1) / CV_TILE;
     const int tiles_x2 = (tiles_x + 1) / 2;
     const int tiles_y = (P.H + CV_TILE - 1) / CV_TILE;
     const int total_pt = P.N * tiles_y * tiles_x2;           // pair tiles (two horizontally adjacent 16x16 tiles)
     const int cin = P.src[0].C + (P.nsrc > 1 ? P.src[1].C : 0);
-    const int nchunks = cin / CP_CH;
+    const int nchunks = cin / CH;
     const int half = P.BN / 2;                               // output channels (B rows) held by this CTA
     const uint32_t lbo_b = static_cast<uint32_t>(half) * 16u;
-    const uint32_t stage_w_bytes = 9u * 2u * 2u * lbo_b;     // weights of one 32-channel chunk
+    const uint32_t stage_w_bytes = static_cast<uint32_t>(NSTEP) * 2u * lbo_b;     // weights of one stage (CH channels x TAPS)
     const int wgroups = nchunks < CP_MAX_WGROUPS ? nchunks : CP_MAX_WGROUPS;
     const int cpg = (nchunks + wgroups - 1) / wgroups;       // chunks per weight group
 
@@ -146,21 +157,21 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                     const int img = t / (tiles_x2 * tiles_y);
                     for (int c = 0; c < nchunks; ++c, ++a_it) {
                         if (first && !leader && c % cpg == 0) { mbar_wait(&w_full[c / cpg], 0); mbar_arrive_remote(&w_full[c / cpg], 0); }
-                        int s = 0, ch = c * CP_CH;
+                        int s = 0, ch = c * CH;
                         if (P.nsrc > 1 && ch >= P.src[0].C) { s = 1; ch -= P.src[0].C; }
                         const ConvSrc& S = P.src[s];
                         const int simg = (img / S.div) * S.mul + (img % S.div) * S.keep + S.add;
                         const uint32_t as = a_it % CP_A_STAGES, aph = (a_it / CP_A_STAGES) & 1u;
                         mbar_wait(&a_empty[as], aph ^ 1u);
                         const bool skip = (P.dbg & 16) && a_it >= CP_A_STAGES;           // profiling: reuse stale stages
-                        const uint32_t bytes = skip ? 0u : static_cast<uint32_t>(CP_A_STAGE_BYTES) + (RESIDENT ? 0u : stage_w_bytes);
+                        const uint32_t bytes = skip ? 0u : static_cast<uint32_t>(A_STAGE_BYTES) + (RESIDENT ? 0u : stage_w_bytes);
                         if (leader) mbar_arrive_expect_tx(&a_full[as], bytes);
                         else mbar_arrive_expect_tx_remote(&a_full[as], bytes, 0);
                         if (!skip) {
-                            tma_load_5d_pair(a_smem + as * STAGE_STRIDE, &PP.tmap[s], &a_full[as], 0, tx * CV_TILE - 1,
-                                             ty * CV_TILE - 1, (S.ch_off + ch) >> 3, simg);
+                            tma_load_5d_pair(a_smem + as * STAGE_STRIDE, &PP.tmap[s], &a_full[as], 0, tx * CV_TILE - (TAPS == 9),
+                                             ty * CV_TILE - (TAPS == 9), (S.ch_off + ch) >> 3, simg);
                             if (!RESIDENT)
-                                tma_load_2d_pair(a_smem + as * STAGE_STRIDE + CP_A_STAGE_BYTES, &PP.tmap_w, &a_full[as], 0,
+                                tma_load_2d_pair(a_smem + as * STAGE_STRIDE + A_STAGE_BYTES, &PP.tmap_w, &a_full[as], 0,
                                                  w_row0 + c * w_rows);
                         }
                     }
@@ -192,23 +203,22 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                     for (int c = 0; c < nchunks; ++c, ++a_it) {
                         const uint32_t as = a_it % CP_A_STAGES;
                         tc_fence_after_sync();
-                        const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_smem + as * STAGE_STRIDE), CP_PLANE_BYTES);
-                        const uint32_t b_lo0 = RESIDENT ? w_lo0 + static_cast<uint32_t>(c) * 18u * b_step
-                                                        : umma_desc_lo(smem_u32(a_smem + as * STAGE_STRIDE + CP_A_STAGE_BYTES), lbo_b);
+                        const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_smem + as * STAGE_STRIDE), PLANE_BYTES);
+                        const uint32_t b_lo0 = RESIDENT ? w_lo0 + static_cast<uint32_t>(c) * NSTEP * b_step
+                                                        : umma_desc_lo(smem_u32(a_smem + as * STAGE_STRIDE + A_STAGE_BYTES), lbo_b);
                         const bool skip = (P.dbg & 32) != 0;
+                        constexpr int SPLIT = (NSTEP + 1) / 2 + (TAPS == 9 ? 1 : 0);      // first part: 10 of 18 (tap, K16) steps
                         if (!skip && elect_one()) {
                             uint32_t acc = c != 0 ? 1u : 0u;
 #pragma unroll
-                            for (int tp = 0; tp < 5; ++tp) {
-                                const int ki = tp / 3, kj = tp % 3;
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    const uint32_t a_lo = a_lo0 + (ki * RP + kj) + h * (2 * CP_PLANE_BYTES / 16);
-                                    const uint32_t b_lo = b_lo0 + (tp * 2 + h) * b_step;
-                                    umma_f16_lohi<2>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc);
-                                    umma_f16_lohi<2>(d0 + 128u, a_lo + 8, a_hi, b_lo, b_hi, idesc, acc);
-                                    acc = 1u;
-                                }
+                            for (int i = 0; i < SPLIT; ++i) {
+                                const int tp = i / KSTEPS, h = i % KSTEPS;
+                                const int ki = TAPS == 9 ? tp / 3 : 0, kj = TAPS == 9 ? tp % 3 : 0;
+                                const uint32_t a_lo = a_lo0 + (ki * RP + kj) + h * (2 * PLANE_BYTES / 16);
+                                const uint32_t b_lo = b_lo0 + i * b_step;
+                                umma_f16_lohi<2>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                                umma_f16_lohi<2>(d0 + 128u, a_lo + 8, a_hi, b_lo, b_hi, idesc, acc);
+                                acc = 1u;
                             }
                         }
                         __syncwarp();
@@ -218,15 +228,13 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                         if (elect_one()) {
                             if (!skip) {
 #pragma unroll
-                                for (int tp = 5; tp < 9; ++tp) {
-                                    const int ki = tp / 3, kj = tp % 3;
-#pragma unroll
-                                    for (int h = 0; h < 2; ++h) {
-                                        const uint32_t a_lo = a_lo0 + (ki * RP + kj) + h * (2 * CP_PLANE_BYTES / 16);
-                                        const uint32_t b_lo = b_lo0 + (tp * 2 + h) * b_step;
-                                        umma_f16_lohi<2>(d0, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
-                                        umma_f16_lohi<2>(d0 + 128u, a_lo + 8, a_hi, b_lo, b_hi, idesc, 1u);
-                                    }
+                                for (int i = SPLIT; i < NSTEP; ++i) {
+                                    const int tp = i / KSTEPS, h = i % KSTEPS;
+                                    const int ki = TAPS == 9 ? tp / 3 : 0, kj = TAPS == 9 ? tp % 3 : 0;
+                                    const uint32_t a_lo = a_lo0 + (ki * RP + kj) + h * (2 * PLANE_BYTES / 16);
+                                    const uint32_t b_lo = b_lo0 + i * b_step;
+                                    umma_f16_lohi<2>(d0, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+                                    umma_f16_lohi<2>(d0 + 128u, a_lo + 8, a_hi, b_lo, b_hi, idesc, 1u);
                                 }
                             }
                             umma_commit_pair(&a_empty[as], 3);

@@ -98,8 +98,8 @@ int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksi
                     int BN, int n_tiles_n, const eb_epilogue_t* epi, unsigned long long* stats, void* stream);
 
 /* Same convolution on CTA pairs (tcgen05 cta_group::2), TMA in and out: available when eb_conv2d_pair_supported() is
- * non-zero (3x3 layers; 1 = each CTA keeps its half of the weights resident in shared memory, Cin * 9 * BN <= 147456,
- * e.g. 128 -> 128; 2 = weights stream with the activation stages, e.g. 256 -> 128).  `wpair` is produced by
+ * non-zero (Cin % 64 == 0; 1 = each CTA keeps its half of the weights resident in shared memory, 3x3 with
+ * Cin * 9 * BN <= 147456, e.g. 128 -> 128; 2 = weights stream with the activation stages: 3x3 256 -> 128, every 1x1).  `wpair` is produced by
  * eb_pack_weight_pair (same size as eb_packed_weight_bytes); sources, epilogue and results as eb_conv2d. */
 int eb_conv2d_pair_supported(int cin, int ksize, int BN, int n_tiles_n);
 int eb_pack_weight_pair(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN, int n_tiles_n,

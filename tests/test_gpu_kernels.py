@@ -175,7 +175,8 @@ def test_conv_pair_resident_and_streamed_weights_agree(ops, monkeypatch):
     b = torch.randn(C, device="cuda", generator=g) * 0.1
     pc = ops.pack_conv(w, b)
     assert L.lib().eb_conv2d_pair_supported(C, 3, pc.BN, pc.n_tiles) == 1 and pc.wpair is not None
-    assert L.lib().eb_conv2d_pair_supported(256, 3, 128, 1) == 2 and L.lib().eb_conv2d_pair_supported(896, 1, 128, 2) == 0
+    assert L.lib().eb_conv2d_pair_supported(256, 3, 128, 1) == 2 and L.lib().eb_conv2d_pair_supported(896, 1, 128, 2) == 2
+    assert L.lib().eb_conv2d_pair_supported(96, 3, 128, 1) == 0            # channels in multiples of 64 only
     want = F.relu(F.conv2d(x.half().double(), w.half().double(), b.double(), 1, 1)).float()
     outs = []
     for dbg in ("0", "128"):

@@ -11,10 +11,13 @@
 //             per chunk instead of nine times.
 // B operand : weights pre-packed on the host in consumption order
 //             [n_tile][chunk][tap][kc=8][BN][8] fp16, streamed by 1-D bulk async copies.
-// Pipeline  : warp 0 B-producer | warp 1 MMA issuer | warps 2-5 A-producers (cp.async with zero-fill,
-//             completion tracked by the mbarrier, so a whole chunk is in flight per SM) |
-//             warps 6-13 epilogue (one 16x8 half of the tile each); mbarrier rings; 2 x 256 TMEM columns so
-//             that the epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs.
+// Pipeline  : warp 0 B-producer | warp 1 MMA issuer (converged warp, elected lane) | warps 2-5 A-producers
+//             (cp.async with zero-fill, completion tracked by the mbarrier, so a whole chunk is in flight per
+//             SM) | warps 6-13 epilogue (one 16x8 half of the tile each) | warp 14 forwarder (generic->async
+//             proxy fence between the cp.async fills and the MMA reads); mbarrier rings; 2 x 256 TMEM columns
+//             so that the epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs.
+// Since the CTA-pair kernel (conv_pair.cuh) took over every 3x3 / 1x1 layer with Cin % 64 == 0, this kernel is the
+// fallback (no tensor-map support, EDVR_B200_CONV_PAIR=0) and the A/B partner in the tests.
 #pragma once
 #include "common.cuh"
 #include "epilogue.cuh"

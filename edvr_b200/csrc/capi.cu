@@ -429,6 +429,20 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "conv2d_pair: output tensor map failed (%d)", static_cast<int>(r));
         PP.tma_out = 1;
+    } else if (ek1 == EK_PIXSHUF && P.epi.out16 != nullptr && !(P.dbg & 64)) {
+        // PixelShuffle(2) store: the output is [N, 2H, 2W, Cout/4]; one box = 8 channels of the 16 x 8 output pixels of a warp
+        eb_encode_tiled_fn enc = tensor_map_encoder();
+        const cuuint64_t ps = static_cast<cuuint64_t>(P.epi.out16_pix_stride);
+        const cuuint64_t W2 = 2ull * W, H2 = 2ull * H;
+        const cuuint64_t dims[4] = {ps, W2, H2, static_cast<cuuint64_t>(N)};
+        const cuuint64_t strides[3] = {ps * 2, W2 * ps * 2, H2 * W2 * ps * 2};
+        const cuuint32_t box[4] = {8, 16, 8, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = enc(&PP.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, P.epi.out16, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "conv2d_pair: pixel-shuffle tensor map failed (%d)", static_cast<int>(r));
+        PP.tma_out = 1;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * nclusters);
@@ -459,7 +473,7 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
         case EK_PLAIN: if (PP.tma_out) EB_LAUNCH_CP(EK_PLAIN, true); else EB_LAUNCH_CP(EK_PLAIN, false); break;
         case EK_F32: if (PP.tma_out) EB_LAUNCH_CP(EK_F32, true); else EB_LAUNCH_CP(EK_F32, false); break;
         case EK_PACK: if (PP.tma_out) EB_LAUNCH_CP(EK_PACK, true); else EB_LAUNCH_CP(EK_PACK, false); break;
-        case EK_PIXSHUF: EB_LAUNCH_CP(EK_PIXSHUF, false); break;
+        case EK_PIXSHUF: if (PP.tma_out) EB_LAUNCH_CP(EK_PIXSHUF, true); else EB_LAUNCH_CP(EK_PIXSHUF, false); break;
         case EK_STRIDE2: EB_LAUNCH_CP(EK_STRIDE2, false); break;
         default: EB_LAUNCH_CP(EK_GENERIC, false); break;
     }

@@ -272,7 +272,29 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                     float v[32];
                     tmem_ld32(t0 + cc, v);
                     epi_store32<EK, TMA_OUT>(P.epi, has_bias ? bias_s - nt * P.BN : nullptr, v, img, y, x, nt * P.BN + cc, valid, abs_ptr);
-                    if (TMA_OUT) {
+                    if (TMA_OUT && EK == EK_PIXSHUF) {
+                        // PixelShuffle(2): conv channel 4k + 2i + j of pixel (y, x) is output channel k of pixel (2y+i, 2x+j)
+                        // (edvr_arch.py:351,410-411).  Staging = the 8 x 16 output pixels of this warp, 8 channels (16 B) each,
+                        // in the box order {8 ch, 16 x, 8 y} of the output tensor map.
+                        if (lane == 0) bulk_wait_group_read0();
+                        __syncwarp();
+                        const uint32_t sp = smem_u32(stage) + ((2 * (lane >> 3)) * 16 + 2 * (lane & 7)) * 16;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int sidx = 2 * i + j;
+                                sts_v4(sp + (i * 16 + j) * 16,
+                                       make_uint4(pack_h2(v[sidx], v[4 + sidx]), pack_h2(v[8 + sidx], v[12 + sidx]),
+                                                  pack_h2(v[16 + sidx], v[20 + sidx]), pack_h2(v[24 + sidx], v[28 + sidx])));
+                            }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && box_ok) {
+                            tma_store_4d(&PP.tmap_out, stage, P.epi.out16_ch_off + ((nt * P.BN + cc) >> 2), 2 * x0, 2 * y0, img);
+                            bulk_commit_group();
+                        }
+                    } else if (TMA_OUT) {
                         if (lane == 0) bulk_wait_group_read0();          // the previous box has been read out of the staging buffer
                         __syncwarp();
 #pragma unroll

@@ -143,6 +143,7 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
     } else if ((G && p.out_mode == OUT_PIXSHUF2) || EK == EK_PIXSHUF) {
         // nn.PixelShuffle(2): out[b, c, 2y+i, 2x+j] = in[b, 4c + 2i + j, y, x]
         // (/root/reference/basicsr/models/archs/edvr_arch.py:351,410-411)
+        if (EXT16) return;      // conv_pair.cuh stages the four output pixels and stores them with one TMA box
         const int H2 = 2 * p.H, W2 = 2 * p.W;
 #pragma unroll
         for (int i = 0; i < 2; ++i)

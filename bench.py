@@ -1,16 +1,20 @@
 #!/usr/bin/env python
 """bench.py — HR frames/s of the EDVR-L 4x SR hot path (BASELINE.json metric) on N B200s.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm (oracle port)
+    python bench.py --gpus N --steps K --warmup W                    # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port, all host cores)
+    python bench.py --mode train --gpus N --steps K --warmup W       # BASELINE cfg 5: one training step per "step" (DDP)
 
-A "step" is one forward pass of EDVR-L (num_feat 128, 7 frames, 40 reconstruction blocks) over a batch
-of B synthetic REDS-shaped clips [B,7,3,180,320] -> B HR frames [B,3,720,1280] per GPU (weak scaling:
-clips shard batch-parallel, no data-path collective).  `value` is device-timed with the
-inputs resident in HBM; `e2e` goes through the public drop-in module (edvr_b200.edvr.EDVR.forward) with
-pinned HOST buffers, H2D and D2H copies inside the timed region.  One JSON line on rank 0.
+A "step" (inference) is one forward pass of EDVR-L (num_feat 128, 7 frames, 40 reconstruction blocks) over a batch of B
+synthetic REDS-shaped clips [B,7,3,180,320] -> B HR frames [B,3,720,1280] per GPU (weak scaling: clips shard
+batch-parallel, no data-path collective).  `value` is device-timed with the inputs resident in HBM; `e2e` goes
+through the public drop-in module (edvr_b200.edvr.EDVR.forward) with pinned HOST buffers, H2D and D2H copies inside the
+timed region.  One JSON line on rank 0.  Baselines timed in the same run: `cpu_baseline` (reference graph on the host
+cores, one full clip) and `ref_cuda` (the UNMODIFIED reference: basicsr's EDVR + its own dcn CUDA extension on the same
+GPU, same batch).
 """
 import argparse
+import csv
 import json
 import os
 import subprocess
@@ -25,6 +29,7 @@ CFG3 = dict(num_feat=128, num_frame=7, deformable_groups=8, num_extract_block=5,
 LR_H, LR_W = 180, 320
 TFLOP_PER_CLIP = 5.251          # SURVEY §8(d) / BASELINE.md §2: 2*MACs of every conv + DCN GEMM, cfg 3
 METRIC = "HR frames/sec EDVR-L 4xSR 7f 180x320->1280x720"
+WORKLOAD = "EDVR-L 4xSR inference cfg 3: nf=128, 7 frames, 40 recon blocks, 7x3x180x320 -> 3x720x1280"
 
 
 def measured_peaks():
@@ -33,6 +38,20 @@ def measured_peaks():
         d = json.load(open(p))
         return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_dram_traffic(csv_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from a committed `ncu --set full` summary under
+    profiles/ (metric,unit,value rows), in bytes; None when the file is missing."""
+    path = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(path):
+        return None, path
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for row in csv.reader(open(path)):
+        if len(row) >= 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(row[2]) * mult.get(row[1], 1.0)
+    return (tot if tot > 0 else None), path
 
 
 class ClockSampler:
@@ -86,29 +105,44 @@ def dist_env():
     return rank, world, local
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(threads=None, crop=(96, 160), steps=1, warmup=1):
-    """Reference graph on the host cores: oracle port of edvr_arch.py (bit-exact, tests/test_oracle.py) with
-    the DCN via torchvision's CPU deform_conv2d.  Bounded sample: one EDVR-L clip cropped to
-    `crop` LR pixels; conv work is linear in pixels, so clips/s = (crop / full pixels) / seconds."""
+# ------------------------------------------------------------------------------------------------ CPU reference path
+def cpu_reference_rate(steps=1, warmup=0, budget_s=None):
+    """The reference graph on the host cores: oracle port of edvr_arch.py (bit-exact against the imported reference,
+    tests/test_oracle.py) with the DCN via torchvision's CPU deform_conv2d, ALL host cores
+    (torch.set_num_threads(os.cpu_count()) - torchrun exports OMP_NUM_THREADS=1, which must not reach this arm).
+    A step is one EDVR-L clip 7x3x180x320 (BASELINE cfg 3 itself, no extrapolation) whenever steps + warmup of them fit
+    in `budget_s`; otherwise each step is the clip cropped to the largest 4-aligned height that fits, stated in `sample`."""
     import torch
     from oracle import edvr_ref
-    if threads:
-        torch.set_num_threads(threads)
-    threads = torch.get_num_threads()          # PyTorch's default = all the cores it will use
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     sd = edvr_ref.make_state_dict(**CFG3, seed=0)
-    h, w = crop
-    x = torch.rand(1, 7, 3, h, w, generator=torch.Generator().manual_seed(0))
-    frac = (h * w) / float(LR_H * LR_W)
+    g = torch.Generator().manual_seed(0)
+    probe = torch.rand(1, 7, 3, 32, 64, generator=g)
+    edvr_ref.edvr_forward(sd, probe)                              # page in, spin up the thread pool (untimed)
+    t0 = time.perf_counter()
+    edvr_ref.edvr_forward(sd, probe)
+    per_px = (time.perf_counter() - t0) / (32 * 64)
+    est_full = per_px * LR_H * LR_W
+    h = LR_H
+    if budget_s is not None and est_full * (steps + warmup) > budget_s:
+        h = int(LR_H * budget_s / (est_full * (steps + warmup))) // 4 * 4
+        h = max(16, min(LR_H, h))
+    x = torch.rand(1, 7, 3, h, LR_W, generator=g)
+    frac = h / float(LR_H)
     for _ in range(warmup):
         edvr_ref.edvr_forward(sd, x)
     t0 = time.perf_counter()
     for _ in range(steps):
         edvr_ref.edvr_forward(sd, x)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": frac / dt, "unit": "HR frames/s", "cores": threads, "kind": "port",
-            "sample": f"1 EDVR-L clip cropped to 7x3x{h}x{w} LR ({frac:.4f} of 180x320) per step, {steps} step(s), "
-                      f"{dt:.2f} s/step; DCN = torchvision CPU deform_conv2d",
+    full = h == LR_H
+    return {"value": frac / dt, "unit": "HR frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "same_config": full,
+            "sample": (f"1 full EDVR-L clip 7x3x{LR_H}x{LR_W} per step" if full else
+                       f"1 EDVR-L clip cropped to 7x3x{h}x{LR_W} ({frac:.3f} of the rows; conv work is linear in pixels) per step")
+                      + f", {steps} timed step(s) after {warmup} warm-up, {dt:.2f} s/step; oracle/edvr_ref.py graph, "
+                        "DCN = torchvision CPU deform_conv2d",
             "sec_per_step": dt}
 
 
@@ -116,52 +150,76 @@ def run_reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    cb = cpu_reference_rate(steps=max(args.steps, 1), warmup=max(args.warmup, 0))
+    cb = cpu_reference_rate(steps=max(args.steps, 1), warmup=max(args.warmup, 0), budget_s=150.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "HR frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sec_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "EDVR-L 4xSR inference, 7x3x180x320 -> 3x720x1280 (cfg 3), CPU reference graph",
-                       "clips_per_step": cb["sample"]},
+            "config": {"workload": WORKLOAD + ", CPU reference graph (does not scale with --gpus: host cores only)",
+                       "clips_per_step": 1, "same_config": cb["same_config"]},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "HR frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------ reference CUDA path
 def reference_cuda_rate(sd, B, iters=5):
-    """The reference's own CUDA dcn extension (oracle/_ref, unmodified) + stock PyTorch/cuDNN graph, same box."""
+    """The reference's own CUDA path on this GPU: UNMODIFIED basicsr (archs/edvr_arch.py EDVR + its compiled
+    ops/dcn/deform_conv_ext) as pip-installed from /root/reference into baseline/_ref (git-ignored, travels with gpurun),
+    stock PyTorch/cuDNN for the convolutions, cudnn.benchmark like basicsr/test.py:17, TF32 flags at torch defaults.
+    Falls back to the oracle graph + oracle/_ref extension when baseline/_ref is absent."""
     import torch
-    from oracle import build_ref, edvr_ref
-    if not os.path.exists(build_ref.so_path()):
-        return {"unavailable": "oracle/_ref/deform_conv_ext_ref.so not built"}
-    ext = build_ref.load_ref()
+    how, net = None, None
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
     torch.backends.cudnn.benchmark = True          # as basicsr/test.py:17
-
-    def dcn(x, off, mask, w, b, s, p, d, g, dg):
-        x = x.contiguous()
-        out = x.new_empty(x.shape[0], w.shape[0], x.shape[2], x.shape[3])
-        ext.modulated_deform_conv_forward(x, w, b, x.new_empty(0), off, mask, out, x.new_empty(0), 3, 3, s, s, p, p,
-                                          d, d, g, dg, True)
-        return out
-
-    sdc = {k: v.cuda() for k, v in sd.items()}
     x = torch.rand(B, 7, 3, LR_H, LR_W, device="cuda")
-    for _ in range(2):
-        edvr_ref.edvr_forward(sdc, x, dcn=dcn)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        edvr_ref.edvr_forward(sdc, x, dcn=dcn)
-    e1.record()
-    torch.cuda.synchronize()
+    if os.path.isdir(os.path.join(ref_root, "basicsr")):
+        try:
+            sys.path.insert(0, ref_root)
+            from basicsr.models.archs.edvr_arch import EDVR as RefEDVR
+            net = RefEDVR(num_in_ch=3, num_out_ch=3, num_feat=CFG3["num_feat"], num_frame=CFG3["num_frame"],
+                          deformable_groups=CFG3["deformable_groups"], num_extract_block=CFG3["num_extract_block"],
+                          num_reconstruct_block=CFG3["num_reconstruct_block"], center_frame_idx=None, hr_in=False,
+                          with_predeblur=False, with_tsa=True).cuda().eval()
+            net.load_state_dict(sd, strict=True)
+            how = ("UNMODIFIED reference: basicsr.models.archs.edvr_arch.EDVR + its own compiled dcn extension "
+                   "(pip install --target baseline/_ref of /root/reference), cuDNN convolutions")
+            fwd = lambda: net(x)
+        except Exception as e:       # noqa: BLE001 - fall back to the shim below
+            how = None
+            sys.stderr.write(f"[bench] baseline/_ref not usable: {e!r}\n")
+    if how is None:
+        from oracle import build_ref, edvr_ref
+        if not os.path.exists(build_ref.so_path()):
+            return {"unavailable": "neither baseline/_ref nor oracle/_ref/deform_conv_ext_ref.so is built"}
+        ext = build_ref.load_ref()
+
+        def dcn(xx, off, mask, w, b, s, p, d, g, dg):
+            xx = xx.contiguous()
+            out = xx.new_empty(xx.shape[0], w.shape[0], xx.shape[2], xx.shape[3])
+            ext.modulated_deform_conv_forward(xx, w, b, xx.new_empty(0), off, mask, out, xx.new_empty(0), 3, 3, s, s, p, p,
+                                              d, d, g, dg, True)
+            return out
+        sdc = {k: v.cuda() for k, v in sd.items()}
+        how = "unmodified reference dcn CUDA ext (oracle/_ref) under the oracle/edvr_ref.py graph, cuDNN convolutions"
+        fwd = lambda: edvr_ref.edvr_forward(sdc, x, dcn=dcn)
+    with torch.no_grad():
+        for _ in range(2):
+            fwd()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fwd()
+        e1.record()
+        torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     return {"value": 1000.0 * B / ms, "unit": "HR frames/s", "ms_per_step": ms, "clips_per_step": B,
-            "how": "unmodified reference dcn CUDA ext (oracle/_ref) + oracle/edvr_ref.py graph on cuDNN, fp32, "
-                   f"cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}, cudnn.benchmark=True, 1 GPU"}
+            "how": how + f", fp32, cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}, cudnn.benchmark=True, 1 GPU, "
+                         f"{iters} timed steps"}
 
 
+# ------------------------------------------------------------------------------------------------ this repo
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -169,12 +227,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from edvr_b200 import ops
+    from edvr_b200 import ops, synth
     from edvr_b200.edvr import EDVR
-    from oracle import edvr_ref      # weight generator only (synthetic reference-format state_dict)
+    from edvr_b200.shard import max_over_ranks
 
     B = args.clips
-    sd = edvr_ref.make_state_dict(**CFG3, seed=0)
+    sd = synth.make_state_dict(**CFG3, seed=0, offset_std=args.offset_std)
     net = EDVR(center_frame_idx=None, **CFG3).cuda().eval()
     net.load_state_dict(sd, strict=True)
     eng = net.engine()
@@ -188,28 +246,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (value)
-    counter0 = ops_launch_counter()
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         flush.zero_()
         y = eng.forward(x_dev)
-    per_step_launches = None
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c_before = ops_launch_counter()
+    c_before = ops.LAUNCHES[0]
     e0.record()
     for _ in range(args.steps):
         flush.zero_()
         y = eng.forward(x_dev)
     e1.record()
     barrier()
-    c_after = ops_launch_counter()
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_step = float(ms_total.item()) / args.steps
+    launches = ops.LAUNCHES[0] - c_before
+    ms_step = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
     clocks = sampler.stop() if sampler else None
-    launches = c_after - c_before
 
     # ---------------- end-to-end through the public module API with host buffers (e2e)
     x_host = torch.rand(B, 7, 3, LR_H, LR_W).pin_memory()
@@ -225,52 +278,78 @@ def run_ours(args):
             y_host.copy_(yd, non_blocking=True)            # D2H of the HR frames
         e1.record()
         barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    ms_e2e_step = float(ms_e2e.item()) / args.steps
+    ms_e2e_step = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
+
+    # ---------------- latency configuration: one clip per step, the whole forward replayed as ONE CUDA graph
+    lat = None
+    try:
+        x1 = torch.rand(1, 7, 3, LR_H, LR_W, device="cuda", generator=g)
+        run1 = eng.graphed(x1)
+        for _ in range(3):
+            run1()
+        barrier()
+        n1 = max(10, args.steps // 4)
+        e0.record()
+        for _ in range(n1):
+            flush.zero_()
+            run1()
+        e1.record()
+        barrier()
+        ms1 = max_over_ranks(e0.elapsed_time(e1), world) / n1
+        lat = {"clips_per_step": 1, "ms_per_step": ms1, "value": world * 1000.0 / ms1, "unit": "HR frames/s",
+               "how": "EDVREngine.graphed(): the forward captured once into a CUDA graph (tensor maps cached by the capture), "
+                      "replayed per clip; 256 MiB L2 flush between clips inside the timed region"}
+    except Exception as e:           # noqa: BLE001 - the latency leg never hides the throughput number
+        lat = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         peak_tf, peak_hbm, peak_src = measured_peaks()
         prof = profile_step(eng, x_dev)
         dom = prof["dominant"]
         value = world * B * 1000.0 / ms_step
+        traffic, traffic_path = ncu_dram_traffic("r01_ncu_conv_pair_trunk_4x180x320_summary.csv")
         line = {
             "metric": METRIC, "value": value, "unit": "HR frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
-            "config": {"workload": "EDVR-L 4xSR inference cfg 3: nf=128, 7 frames, 40 recon blocks, "
-                                   "7x3x180x320 -> 3x720x1280", "clips_per_gpu_per_step": B,
+            "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B,
                        "global_clips_per_step": world * B, "parallelism": f"dp{world} (batch-sharded, no collective)",
-                       "weights": "random init, reference initialisers, conv_offset ~ N(0, 0.02^2)",
+                       "weights": f"random init, reference initialisers, conv_offset ~ N(0, {args.offset_std}^2)",
                        "l2": "256 MiB memset between steps inside the timed region; per-step activation working set >> 126 MB L2",
+                       "timed_region_s": ms_step * args.steps / 1e3,
                        "achieved_tflops": TFLOP_PER_CLIP * value, "tflop_per_clip": TFLOP_PER_CLIP},
             "clocks": clocks,
             "e2e": {"value": world * B * 1000.0 / ms_e2e_step, "unit": "HR frames/s", "ms_per_step": ms_e2e_step,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4,
                     "api": "edvr_b200.edvr.EDVR.forward (drop-in for basicsr.models.archs.edvr_arch.EDVR), pinned host buffers"},
+            "latency_b1": lat,
             "gpu_launches": launches,
             "roofline": {"kernel": dom["name"], "bound": "tensor", "achieved": dom["tflops"], "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": dom["tflops"] / peak_tf, "traffic": 74.1e6,
-                         "traffic_note": "dram read 59.3 MB + write 14.8 MB per launch of the 128->128 3x3 trunk conv at "
-                                         "4x180x320 on the CTA-pair kernel (ncu --set full, "
-                                         "profiles/r01_ncu_conv_pair_trunk_4x180x320_summary.csv); algorithmic I/O of that "
+                         "unit": "TFLOP/s", "frac": dom["tflops"] / peak_tf, "traffic": traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the class's most "
+                                         "frequent member (128->128 3x3 trunk conv at 4x180x320, CTA-pair kernel), parsed from "
+                                         f"{os.path.relpath(traffic_path, ROOT)} (ncu --set full); algorithmic I/O of that "
                                          "launch 118 MB fp16 - most of the output stays in the 126 MB L2",
                          "peak_source": peak_src + ", bf16 sustained (fp16 runs at the same tensor rate)",
                          "launches_per_step": dom["launches"], "avg_launch_ms": dom["avg_ms"],
                          "share_of_step": dom["share"],
                          "how": "algorithmic FLOPs (2*N*H*W*Cout*Cin*k*k per launch) / CUDA-event time of each launch, "
                                 "one instrumented step after the timed region"},
+            "roofline_dcn": prof["dcn"] and dict(prof["dcn"], peak_tflops=peak_tf, peak_hbm_gbs=peak_hbm,
+                                                 frac_tensor=prof["dcn"]["tflops"] / peak_tf,
+                                                 frac_hbm=prof["dcn"]["gbs"] / peak_hbm),
             "kernel_shares": prof["shares"],
         }
-        if world == 1 and os.environ.get("EDVR_BENCH_PROFILING") == "1":
+        if os.environ.get("EDVR_BENCH_PROFILING") == "1":
             # launch-list runs under ncu (profiles/): the baseline arms would only add minutes of serialised replays
             line["cpu_baseline"] = {"skipped": "EDVR_BENCH_PROFILING=1"}
-        elif world == 1:
-            line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate().items() if k != "sec_per_step"}
+        else:
+            if world == 1:
+                cb = cpu_reference_rate(steps=1, warmup=0, budget_s=90.0)
+                line["cpu_baseline"] = {k: v for k, v in cb.items() if k != "sec_per_step"}
             try:
-                line["ref_cuda"] = reference_cuda_rate(sd, 1)
-            except Exception as e:       # baseline leg only; never hides the product number
+                line["ref_cuda"] = reference_cuda_rate(sd, B)
+            except Exception as e:       # noqa: BLE001 - baseline leg only; never hides the product number
                 line["ref_cuda"] = {"unavailable": repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -278,13 +357,8 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def ops_launch_counter():
-    from edvr_b200 import ops
-    return ops.LAUNCHES[0]
-
-
 def profile_step(eng, x):
-    """One instrumented forward: CUDA events around every launch class (on the launching stream)."""
+    """One instrumented forward: CUDA events around every launch (on the launching stream), aggregated per kernel class."""
     import torch
     from edvr_b200 import ops
     ops.PROFILE = []
@@ -292,29 +366,51 @@ def profile_step(eng, x):
     torch.cuda.synchronize()
     recs, ops.PROFILE = ops.PROFILE, None
     agg, total = {}, 0.0
-    for name, flops, e0, e1, _detail in recs:
+    dcn_l1 = []
+    for name, flops, e0, e1, detail in recs:
         ms = e0.elapsed_time(e1)
         a = agg.setdefault(name, [0.0, 0.0, 0])
         a[0] += ms; a[1] += flops; a[2] += 1
         total += ms
+        if name == "dcn_site" and f"x{LR_H}x{LR_W} " in detail:
+            dcn_l1.append((ms, flops, detail))
     shares = {k: {"ms": round(v[0], 4), "share": round(v[0] / total, 4), "launches": v[2],
                   "tflops": round(v[1] / (v[0] * 1e9), 1) if v[0] > 0 and v[1] > 0 else None} for k, v in agg.items()}
     name = max(agg, key=lambda k: agg[k][0])
     v = agg[name]
-    return {"shares": shares, "dominant": {"name": name, "tflops": v[1] / (v[0] * 1e9), "launches": v[2],
-                                           "avg_ms": v[0] / v[2], "share": v[0] / total}}
+    dcn = None
+    if dcn_l1:
+        # one L1 DCN site launch (all B*T frames): algorithmic bytes of the FUSED site = x + offset features in, aligned
+        # features out (fp16 NHWC) + both weight sets once; SURVEY §8(d) counts 109.34 MB per image for the fp32 operator
+        # (x + offset + mask + W + out) - offsets and masks never reach HBM here.
+        ms = sum(d[0] for d in dcn_l1) / len(dcn_l1)
+        n_img = int(dcn_l1[0][2].split("x")[0])
+        C = CFG3["num_feat"]
+        alg = n_img * LR_H * LR_W * C * 2 * 3 + (C * C * 9 + 216 * C * 9) * 2
+        dcn = {"kernel": "dcn_site_kernel (L1 launches: conv_offset + offsets in TMEM + gather + DCN GEMM)", "launch_ms": ms,
+               "images": n_img, "tflops": dcn_l1[0][1] / (ms * 1e9), "algorithmic_bytes": alg, "gbs": alg / (ms * 1e6),
+               "survey_fp32_operator_bytes": n_img * 109.34e6, "share_of_step": agg["dcn_site"][0] / total}
+    return {"shares": shares, "dcn": dcn,
+            "dominant": {"name": name, "tflops": v[1] / (v[0] * 1e9), "launches": v[2], "avg_ms": v[0] / v[2],
+                         "share": v[0] / total}}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200, help="timed steps (200 x ~25 ms: a 5 s timed region)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"])
     ap.add_argument("--clips", type=int, default=4, help="clips per GPU per step (8 runs into the 1 kW power cap)")
+    ap.add_argument("--offset-std", type=float, default=0.02,
+                    help="std of the random conv_offset init (0.02: ~0.02 px offsets; 3: several pixels)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.mode == "train":
+        from edvr_b200 import train_bench
+        train_bench.main(args)
     else:
         run_ours(args)
 

@@ -13,6 +13,7 @@
 #include "conv_pair.cuh"
 #include "dcn_backward.cuh"
 #include "dcn_fused.cuh"
+#include "dcn_site.cuh"
 #include "elementwise.cuh"
 #include "epilogue.cuh"
 #include "selftest.cuh"
@@ -38,14 +39,17 @@ int check_launch(const char* what) {
 }
 
 int num_sms() {
-    static int n = 0;   // benign race: every thread computes the same value
-    if (n == 0) {
-        int dev = 0, v = 0;
-        cudaGetDevice(&dev);
+    // per device (a process may drive several GPUs); benign race: every thread computes the same values
+    static int n[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    if (n[slot] == 0) {
+        int v = 0;
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        n = v > 0 ? v : 148;
+        n[slot] = v > 0 ? v : 148;
     }
-    return n;
+    return n[slot];
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -529,6 +533,96 @@ int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int
     if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
     if (P.epi.out_mode != OUT_SAME) return fail(EB_ERR_UNSUPPORTED, "dcn_nhwc: out_mode");
     return launch_dcn(P, static_cast<cudaStream_t>(stream));
+}
+
+// ---- DCN site kernel (dcn_site.cuh): windows of x staged in shared memory; conv_offset optionally fused in front
+size_t eb_dcn_site_offset_weight_bytes(int C) { return static_cast<size_t>(C / 32) * 9 * DS_WO_STAGE; }
+
+int eb_dcn_site_pack_offset_weight(const float* wo, const float* bo, int C, int dg, void* wo_pack, float* bo_cols, void* stream) {
+    if (!wo || !wo_pack || !bo_cols) return fail(EB_ERR_NULLPTR, "dcn_site_pack: null pointer");
+    if (C < 64 || C % 64 || dg < 1 || dg * 27 > DS_OFF_N) return fail(EB_ERR_INVALID_SHAPE, "dcn_site_pack: C=%d dg=%d", C, dg);
+    const long long groups = static_cast<long long>(C / 32) * 9 * 4 * DS_OFF_N;
+    pack_offset_weight_kernel<<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        wo, bo, C, dg, DS_OFF_N, static_cast<__half*>(wo_pack), bo_cols);
+    return check_launch("pack_offset_weight");
+}
+
+int eb_dcn_site(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
+                const float* offset, const float* mask, long long off_img_stride, long long mask_img_stride, int mask_logit,
+                const void* feat, int f_pix_stride, int f_ch_off, const void* wo_pack, const float* bo_cols,
+                const void* wpack, int BN, int n_tiles_n, const eb_epilogue_t* epi, float* absmean, void* stream) {
+    const bool fused = feat != nullptr;
+    if (!x || !wpack || (fused ? (!wo_pack || !bo_cols) : !offset)) return fail(EB_ERR_NULLPTR, "dcn_site: null pointer");
+    if (N < 0 || H < 1 || W < 1 || C < 64 || C % 64 || dg < 1 || C % dg || ((C / dg) != 8 && (C / dg) % 16))
+        return fail(EB_ERR_INVALID_SHAPE, "dcn_site: N=%d H=%d W=%d C=%d dg=%d (C/dg must be 8 or a multiple of 16)", N, H, W, C, dg);
+    if (BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || BN * n_tiles_n > DC_MAX_COUT)
+        return fail(EB_ERR_INVALID_SHAPE, "dcn_site: BN=%d n_tiles_n=%d", BN, n_tiles_n);
+    if (!al16(x) || !al16(wpack) || x_pix_stride % 8 || x_ch_off % 8 || x_pix_stride < x_ch_off + C)
+        return fail(EB_ERR_ALIGNMENT, "dcn_site: x view must be 16-byte aligned");
+    if (fused && (dg * 27 > DS_OFF_N || !al16(feat) || !al16(wo_pack) || f_pix_stride % 8 || f_ch_off % 8 || f_pix_stride < f_ch_off + C))
+        return fail(EB_ERR_UNSUPPORTED, "dcn_site: fused conv_offset needs dg*27 <= %d and a 16-byte aligned feature view", DS_OFF_N);
+    eb_encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return fail(EB_ERR_UNSUPPORTED, "dcn_site: cuTensorMapEncodeTiled unavailable");
+    if (N == 0) return EB_OK;
+    DsParams PP;
+    memset(&PP, 0, sizeof(PP));
+    DcnParams& P = PP.d;
+    P.x = static_cast<const __half*>(x); P.x_pix_stride = x_pix_stride; P.x_ch_off = x_ch_off;
+    P.N = N; P.H = H; P.W = W; P.C = C; P.Ho = H; P.Wo = W;
+    P.kh = 3; P.kw = 3; P.stride = 1; P.pad = 1; P.dil = 1; P.stride_w = 1; P.pad_w = 1; P.dil_w = 1;
+    P.dg = dg; P.cpg = C / dg;
+    P.x_wide = (x_pix_stride % 16 == 0 && x_ch_off % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 32 == 0) ? 1 : 0;
+    P.off_mode = OFF_NCHW_F32; P.offset = offset; P.mask = mask;
+    P.wpack = static_cast<const __half*>(wpack); P.BN = BN; P.n_tiles_n = n_tiles_n;
+    if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
+    if (P.epi.out_mode != OUT_SAME) return fail(EB_ERR_UNSUPPORTED, "dcn_site: out_mode");
+    const bool nchw = P.epi.out_nchw != nullptr;
+    if (nchw && (P.epi.out16 || P.epi.out32 || P.epi.res16 || P.epi.res32)) return fail(EB_ERR_UNSUPPORTED, "dcn_site: NCHW output excludes other outputs");
+    if (!nchw && (!P.epi.out16 || P.epi.out32 || P.epi.res32 || P.epi.res16)) return fail(EB_ERR_UNSUPPORTED, "dcn_site: NHWC fp16 output only");
+    PP.off_img_stride = off_img_stride; PP.mask_img_stride = mask_img_stride; PP.mask_logit = mask_logit;
+    PP.absmean = absmean;
+    PP.f_ch_off = f_ch_off; PP.wo_pack = static_cast<const __half*>(wo_pack); PP.bo = bo_cols;
+    {
+        const cuuint64_t ps = static_cast<cuuint64_t>(x_pix_stride);
+        const cuuint64_t dims[4] = {ps, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+        const cuuint64_t strides[3] = {ps * 2, static_cast<cuuint64_t>(W) * ps * 2, static_cast<cuuint64_t>(H) * W * ps * 2};
+        const cuuint32_t box[4] = {64, DS_WW, DS_WH, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = enc(&PP.tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "dcn_site: window tensor map failed (%d)", static_cast<int>(r));
+    }
+    PP.tmap_f = PP.tmap_x;
+    if (fused) {
+        const cuuint64_t ps = static_cast<cuuint64_t>(f_pix_stride);
+        const cuuint64_t dims[5] = {8, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), ps / 8, static_cast<cuuint64_t>(N)};
+        const cuuint64_t strides[4] = {ps * 2, static_cast<cuuint64_t>(W) * ps * 2, 16, static_cast<cuuint64_t>(H) * W * ps * 2};
+        const cuuint32_t box[5] = {8, DS_F_RP_X, DS_F_RP_Y, 4, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const CUresult r = enc(&PP.tmap_f, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(feat), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "dcn_site: feature tensor map failed (%d)", static_cast<int>(r));
+    }
+    const long long tiles = static_cast<long long>(N) * ((H + DC_TILE_H - 1) / DC_TILE_H) * ((W + DC_TILE_W - 1) / DC_TILE_W) * n_tiles_n;
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool two = P.cpg == 8;       // two deformable groups per 16-channel K-atom pair (EDVR-M: 64 channels, dg 8)
+#define EB_LAUNCH_DS(OFF_, EK_)                                                                        \
+    do {                                                                                               \
+        if (two) {                                                                                     \
+            if (int rc = set_smem(dcn_site_kernel<OFF_, EK_, true>, DS_SMEM_BYTES)) return rc;         \
+            dcn_site_kernel<OFF_, EK_, true><<<grid, DS_THREADS, DS_SMEM_BYTES, st>>>(PP);             \
+        } else {                                                                                       \
+            if (int rc = set_smem(dcn_site_kernel<OFF_, EK_, false>, DS_SMEM_BYTES)) return rc;        \
+            dcn_site_kernel<OFF_, EK_, false><<<grid, DS_THREADS, DS_SMEM_BYTES, st>>>(PP);            \
+        }                                                                                              \
+    } while (0)
+    if (fused) { if (nchw) EB_LAUNCH_DS(DS_OFF_TMEM, EK_NCHW); else EB_LAUNCH_DS(DS_OFF_TMEM, EK_PLAIN); }
+    else       { if (nchw) EB_LAUNCH_DS(DS_OFF_GLOBAL, EK_NCHW); else EB_LAUNCH_DS(DS_OFF_GLOBAL, EK_PLAIN); }
+#undef EB_LAUNCH_DS
+    return check_launch("dcn_site");
 }
 
 // ---- reference-layout operator -----------------------------------------------------------

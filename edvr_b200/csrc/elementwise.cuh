@@ -111,6 +111,36 @@ __global__ void pack_weight_pair_kernel(const float* __restrict__ w, int cout, i
         h8_store(out + i * 8, v);
     }
 }
+// Fused DCN site (dcn_site.cuh): conv_offset weights [dg*27][cin][3][3] -> [chunk of 32 ch][tap][k16 2][plane 2][224 rows][8]
+// fp16, rows in TMEM column order r = g*27 + 3*tap + e with e = 0: dh, 1: dw, 2: mask logit; source rows follow the
+// reference: offsets g*18 + 2*tap + e, masks dg*18 + g*9 + tap (arch_util.py:244-247, deform_conv_cuda_kernel.cu:600-613).
+__device__ __forceinline__ int dcn_site_src_row(int r, int dg) {
+    if (r >= dg * 27) return -1;
+    const int g = r / 27, rem = r % 27, t = rem / 3, e = rem % 3;
+    return e < 2 ? g * 18 + 2 * t + e : dg * 18 + g * 9 + t;
+}
+__global__ void pack_offset_weight_kernel(const float* __restrict__ w, const float* __restrict__ b, int cin, int dg, int rows,
+                                          __half* __restrict__ out, float* __restrict__ b_out) {
+    const int nchunks = cin / 32;
+    const long long total = static_cast<long long>(nchunks) * 9 * 4 * rows;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int row = r % rows; r /= rows;
+        const int plane = r % 4; r /= 4;              // k16 * 2 + plane-in-k16
+        const int tap = r % 9; r /= 9;
+        const int chunk = static_cast<int>(r);
+        const int srow = dcn_site_src_row(row, dg);
+        H8 v;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ci = chunk * 32 + plane * 8 + e;
+            v.v[e] = srow >= 0 ? w[(static_cast<size_t>(srow) * cin + ci) * 9 + tap] : 0.f;
+        }
+        h8_store(out + i * 8, v);
+        if (i < rows) b_out[i] = (b != nullptr && srow >= 0) ? b[srow] : 0.f;      // i == row for chunk 0, tap 0, plane 0
+    }
+}
 __global__ void pack_bias_kernel(const float* __restrict__ b, int cout, const int* __restrict__ row_map,
                                  int n_packed, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -24,6 +24,8 @@ from torch.nn.modules.utils import _pair, _single
 from . import _lib as L
 from . import ops
 
+_MONITOR = ops.OffsetMonitor()       # deferred `offset_absmean > 50` warnings of the fused DCNv2Pack path
+
 
 def _out_hw(H, W, kh, kw, stride, padding, dilation):
     return ((H + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1,
@@ -207,26 +209,30 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
         k = self.kernel_size
         return (not torch.is_grad_enabled() and x.is_cuda and k == (3, 3) and self.stride == 1 and self.padding == 1
                 and self.dilation == 1 and self.groups == 1 and self.in_channels % 64 == 0
-                and (self.in_channels // self.deformable_groups) % 8 == 0)
+                and ((self.in_channels // self.deformable_groups) == 8 or (self.in_channels // self.deformable_groups) % 16 == 0))
 
-    def _packs(self):
+    def _site(self):
         key = tuple(int(p._version) for p in self.parameters()) + (self.weight.data_ptr(),)
         if self._packed is None or self._packed[0] != key:
-            pw = ops.pack_conv(self.weight.detach().float(), None if self.bias is None else self.bias.detach().float())
-            po = ops.pack_conv(self.conv_offset.weight.detach().float(), self.conv_offset.bias.detach().float(),
-                               row_map=ops.dcn_offset_row_map(self.deformable_groups))
-            self._packed = (key, pw, po)
-        return self._packed[1], self._packed[2]
+            site = ops.DcnSite(self.conv_offset.weight.detach().float(), self.conv_offset.bias.detach().float(),
+                               self.weight.detach().float(), None if self.bias is None else self.bias.detach().float(),
+                               self.deformable_groups)
+            self._packed = (key, site)
+        return self._packed[1]
 
-    def _fused_forward(self, x, feat, warn=True):
-        pw, po = self._packs()
-        xv, fv = ops.nchw_to_nhwc(x.float()), ops.nchw_to_nhwc(feat.float())
-        offp = ops.new_act(fv.N, fv.H, fv.W, self.deformable_groups * 32, x.device)
-        acc = torch.zeros(1, dtype=torch.float32, device=x.device)
-        ops.conv2d(po, [fv], out16=offp, act=ops.ACT_DCN_PACK, absmean=acc)
-        out = torch.empty(xv.N, self.out_channels, xv.H, xv.W, dtype=torch.float32, device=x.device)
-        ops.dcn_nhwc(pw, xv, offp, self.deformable_groups, out_nchw=out, nchw_C=self.out_channels)
-        self.last_offset_abssum = (acc, fv.N * fv.H * fv.W * self.deformable_groups * 18)   # checked lazily
+    def _fused_forward(self, x, feat):
+        """One launch (dcn_site.cuh): conv_offset on the tensor cores, offsets and masks stay in tensor memory; the
+        reference's `offset_absmean > 50` warning is accumulated on the device and reported by the next call."""
+        _MONITOR.poll()
+        site = self._site()
+        with torch.cuda.device(x.device):
+            xv, fv = ops.nchw_to_nhwc(x.float()), ops.nchw_to_nhwc(feat.float())
+            acc = torch.zeros(1, dtype=torch.float32, device=x.device)
+            out = torch.empty(xv.N, self.out_channels, xv.H, xv.W, dtype=torch.float32, device=x.device)
+            site(xv, fv, absmean=acc, out_nchw=out)
+            n = fv.N * fv.H * fv.W * self.deformable_groups * 18
+            self.last_offset_abssum = (acc, n)
+            _MONITOR.submit(acc, [n])
         return out.to(x.dtype)
 
     def forward(self, x):
@@ -243,9 +249,10 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
 class DCNv2Pack(ModulatedDeformConvPack):
     """Offsets and masks come from a second feature map (arch_util.py:232-257).
 
-    The reference's `offset_absmean > 50` warning forces a device->host sync on every call
-    (arch_util.py:249-253).  Here the sum is accumulated on the device; call
-    ``check_offset_absmean()`` whenever convenient to get the same warning without stalling the stream.
+    The reference's `offset_absmean > 50` warning forces a device->host sync on every call (arch_util.py:249-253).  On the
+    fused inference path the sum is accumulated on the device and the warning is emitted by the NEXT DCN call once the
+    asynchronous read-back has finished (ops.OffsetMonitor); ``check_offset_absmean()`` forces it for the last call.  Under
+    autograd (training) the reference's immediate check is kept.
     """
 
     def forward(self, x, feat):
@@ -255,7 +262,10 @@ class DCNv2Pack(ModulatedDeformConvPack):
         o1, o2, mask = torch.chunk(out, 3, dim=1)
         offset = torch.cat((o1, o2), dim=1)
         mask = torch.sigmoid(mask)
+        offset_absmean = torch.mean(torch.abs(offset.detach()))
         self.last_offset_abssum = (offset.detach().abs().sum().reshape(1), offset.numel())
+        if offset_absmean > 50:          # arch_util.py:249-253 (the training-divergence signal): immediate, like the reference
+            logging.getLogger("basicsr").warning(f"Offset abs mean is {offset_absmean}, larger than 50.")
         return modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
                                      self.dilation, self.groups, self.deformable_groups)
 

@@ -22,35 +22,30 @@ from .ops import ACT_DCN_PACK, ACT_LRELU, ACT_NONE, ACT_RELU, OUT_PIXSHUF2, OUT_
 
 
 class _Arena:
-    """Named persistent device buffers (allocated once per shape)."""
+    """Named persistent device buffers: ONE buffer per name, re-allocated when the requested shape changes, so that
+    variable-resolution inference (Vid4, ragged last chunks of forward_video) keeps a single activation set alive instead
+    of one multi-GB set per distinct shape."""
 
     def __init__(self, device):
         self.device = device
         self.bufs = {}
 
+    def _get(self, name, shape, make):
+        hit = self.bufs.get(name)
+        if hit is None or hit[0] != shape:
+            self.bufs.pop(name, None)              # release the old shape before allocating the new one
+            hit = self.bufs[name] = (shape, make())
+        return hit[1]
+
     def act(self, name, N, H, W, C, zero=False):
-        key = (name, N, H, W, C)
-        t = self.bufs.get(key)
-        if t is None:
-            t = (torch.zeros if zero else torch.empty)(N, H, W, C, dtype=torch.float16, device=self.device)
-            self.bufs[key] = t
-        return View(t)
+        return View(self._get(name, ("f16", N, H, W, C, zero), lambda: (torch.zeros if zero else torch.empty)(
+            N, H, W, C, dtype=torch.float16, device=self.device)))
 
     def blocked32(self, name, N, H, W, C):
-        key = (name, "b32", N, H, W, C)
-        t = self.bufs.get(key)
-        if t is None:
-            t = ops.Blocked32(N, H, W, C, self.device)
-            self.bufs[key] = t
-        return t
+        return self._get(name, ("b32", N, H, W, C), lambda: ops.Blocked32(N, H, W, C, self.device))
 
     def f32(self, name, *shape):
-        key = (name,) + tuple(shape)
-        t = self.bufs.get(key)
-        if t is None:
-            t = torch.empty(*shape, dtype=torch.float32, device=self.device)
-            self.bufs[key] = t
-        return t
+        return self._get(name, ("f32",) + tuple(shape), lambda: torch.empty(*shape, dtype=torch.float32, device=self.device))
 
 
 def frame_window_indices(center, n_frames, window, padding="reflection"):
@@ -70,9 +65,8 @@ def frame_window_indices(center, n_frames, window, padding="reflection"):
 
 
 def pack_dcn_site(p, sd, key, dg):
-    p[key] = ops.pack_conv(sd[key + ".weight"], sd.get(key + ".bias"))
-    p[key + ".conv_offset"] = ops.pack_conv(sd[key + ".conv_offset.weight"], sd[key + ".conv_offset.bias"],
-                                            row_map=ops.dcn_offset_row_map(dg))
+    p[key] = ops.DcnSite(sd[key + ".conv_offset.weight"], sd[key + ".conv_offset.bias"], sd[key + ".weight"],
+                         sd.get(key + ".bias"), dg)
 
 
 def pack_pcd(p, sd, pre, dg):
@@ -102,9 +96,8 @@ def pack_tsa(p, sd, pre):
 
 
 def dcn_site(a, p, key, dg, absmean_slot, x, feat, out, act):
-    offp = a.act("offpack", feat.N, feat.H, feat.W, dg * 32)
-    ops.conv2d(p[key + ".conv_offset"], [feat], out16=offp, act=ACT_DCN_PACK, absmean=absmean_slot)
-    ops.dcn_nhwc(p[key], x, offp, dg, out16=out, act=act)
+    site = p[key]
+    site(x, feat, out, act=act, absmean=absmean_slot, record=site.arena_record(a, feat))
 
 
 def run_pcd(a, p, pre, dg, absmean, nbr, ref, ref_map, aligned):
@@ -196,8 +189,12 @@ def run_tsa(a, p, pre, aligned, B, T, center, fused16, trunk32):
 
 class EDVREngine:
     def __init__(self, state_dict, num_frame, center_frame_idx=None, hr_in=False, device="cuda"):
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        device = dev
         sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in state_dict.items()}
-        self.device = torch.device(device)
+        self.device = dev
         self.T = num_frame
         self.center = num_frame // 2 if center_frame_idx is None else center_frame_idx
         self.hr_in = hr_in
@@ -211,6 +208,8 @@ class EDVREngine:
             raise ValueError(f"num_feat={self.C}: the tensor-core path needs a multiple of 64")
         self.arena = _Arena(self.device)
         self.absmean = torch.zeros(16, dtype=torch.float32, device=self.device)   # one slot per DCN site
+        self._absmean_counts = None
+        self.monitor = ops.OffsetMonitor()      # deferred "Offset abs mean is ..., larger than 50." warning
         self._pack(sd)
 
     # ------------------------------------------------------------------ weights
@@ -280,6 +279,10 @@ class EDVREngine:
         ops.conv2d(self.p[key + ".conv1"], [x], out16=tmp, act=ACT_RELU)
         ops.conv2d(self.p[key + ".conv2"], [tmp], out16=out, act=ACT_NONE, res16=x)
 
+    def _submit_offset_check(self):
+        self.monitor.submit(self.absmean[:4], self._absmean_counts.tolist(),
+                            ["dcn_pack.l3", "dcn_pack.l2", "dcn_pack.l1", "cas_dcnpack"])
+
     def offset_absmeans(self):
         """Mean |offset| per DCN site of the LAST forward (device sync; the reference warns when > 50)."""
         return None if self._absmean_counts is None else (self.absmean[:4].cpu() / self._absmean_counts)
@@ -328,6 +331,8 @@ class EDVREngine:
                                             dtype=torch.float32) * (self.dg * 18)
         aligned = a.act("aligned", N, h, w, C)
         run_pcd(a, p, "pcd_align.", self.dg, self.absmean, [l1, l2, l3], [l1, l2, l3], ref_map, aligned)
+        if not torch.cuda.is_current_stream_capturing():
+            self._submit_offset_check()
 
         # ---- fusion
         fused16 = a.act("fused16", B, h, w, C)
@@ -366,15 +371,48 @@ class EDVREngine:
     def forward(self, x):
         """x: fp32 [B, T, 3, h, w] on the device -> fp32 [B, 3, 4h, 4w] (or [B,3,h,w] when hr_in)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[1] == self.T
+        assert x.device == self.device, f"input on {x.device}, engine on {self.device}"
         x = x.contiguous()
         B, T, _, hin, win = x.shape
         self._check_hw(hin, win)
-        l1, l2, l3, h, w = self._features(x.view(B * T, 3, hin, win))
-        xc = x[:, self.center]          # [B,3,hin,win] view: image stride T*3*hin*win
-        return self._tail(l1, l2, l3, B, h, w, xc, T * 3 * hin * win)
+        with torch.cuda.device(self.device):       # every launch below uses the current stream of THIS device
+            if not torch.cuda.is_current_stream_capturing():
+                self.monitor.poll()                # offset warnings of earlier forwards whose read-back has completed
+            l1, l2, l3, h, w = self._features(x.view(B * T, 3, hin, win))
+            xc = x[:, self.center]          # [B,3,hin,win] view: image stride T*3*hin*win
+            return self._tail(l1, l2, l3, B, h, w, xc, T * 3 * hin * win)
+
+    def graphed(self, x):
+        """Latency configuration: capture forward() for inputs of x's shape ONCE into a CUDA graph (the ~140 launches of a
+        forward, their tensor maps encoded at capture time) and return run(new_x=None) -> output, which replays it.  The
+        output tensor and every intermediate live in the graph's private pool; results are bit-identical to forward()."""
+        static_x = x.clone()
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.forward(static_x)             # allocate arena buffers / load modules outside the capture
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    y = self.forward(static_x)
+            torch.cuda.current_stream().wait_stream(side)
+
+        def run(new_x=None):
+            if new_x is not None:
+                static_x.copy_(new_x)
+            graph.replay()
+            self._submit_offset_check()
+            return y
+        run.graph, run.output = graph, y
+        return run
 
     @torch.no_grad()
     def forward_video(self, frames, clips_per_step=4, padding="reflection_circle"):
+        with torch.cuda.device(self.device):
+            return self._forward_video(frames, clips_per_step, padding)
+
+    def _forward_video(self, frames, clips_per_step, padding):
         """Sliding-window inference over one sequence: frames fp32 [F, 3, h, w] -> fp32 [F, 3, 4h, 4w], output i
         restored from the window `frame_window_indices(i, F, T, padding)` like the reference's test loop
         (video_base_model.py:44-70 over datasets built with data_util.py:35-88).  The per-frame pyramid (conv_first, feature
@@ -384,6 +422,7 @@ class EDVREngine:
         frames = frames.contiguous()
         F_, _, hin, win = frames.shape
         self._check_hw(hin, win)
+        self.monitor.poll()
         T, C, a = self.T, self.C, self.arena
         per_chunk = max(1, clips_per_step * T)
         vid = None

@@ -222,6 +222,125 @@ def dcn_nhwc(pc, x, offpack, dg, out16=None, act=ACT_NONE, out_nchw=None, nchw_C
                                     L.stream_ptr()), "eb_dcn_nhwc")
 
 
+class OffsetMonitor:
+    """Deferred form of the reference's per-call check `if mean(|offset|) > 50: logger.warning(...)` (arch_util.py:249-253).
+    The reference reads the mean back on every DCN call (a device->host sync, 28 per EDVR-L forward); here the kernels add
+    sum |offset| into a device accumulator, submit() queues an asynchronous copy of it, and poll() - called at the start of
+    the next forward - emits the same warning text for every finished copy.  Nothing ever blocks the stream."""
+
+    def __init__(self):
+        self.pending = []
+
+    def submit(self, acc, counts, names=None):
+        """acc: device fp32 [k] of sum |offset|; counts: number of offset values behind each entry."""
+        host = torch.empty(acc.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(acc, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((host, [float(c) for c in counts], names, ev))
+        if len(self.pending) > 64:
+            self.poll(block=True)
+
+    def poll(self, block=False):
+        """Warn for every completed check; returns the list of means seen (oldest first)."""
+        import logging
+        seen = []
+        while self.pending and (block or self.pending[0][3].query()):
+            host, counts, names, ev = self.pending.pop(0)
+            ev.synchronize()
+            for i, c in enumerate(counts):
+                mean = float(host[i]) / max(c, 1.0)
+                seen.append(mean)
+                if mean > 50:
+                    logging.getLogger("basicsr").warning(f"Offset abs mean is {mean}, larger than 50.")
+        return seen
+
+
+class DcnSite:
+    """One DCNv2Pack site (arch_util.py:232-257): conv_offset -> (offset, sigmoid(mask)) -> modulated deformable conv.
+
+    wo/bo: conv_offset weight [dg*27, C, 3, 3] / bias, w/b: DCN weight [Cout, C, 3, 3] / bias (reference state_dict tensors).
+    __call__(x, feat, out16, act, absmean): x = features to sample, feat = offset features, both NHWC fp16 Views.
+
+    mode "fused": ONE launch (dcn_site.cuh): conv_offset runs on the tensor cores inside the DCN kernel, offsets and masks
+    stay in tensor memory.  mode "split": conv_offset as a separate convolution writing the reference's fp32 NCHW
+    offset/mask-logit tensor, then the same DCN kernel reading it (used when dg*27 > 224).  mode "legacy": the round-1
+    pipeline (fp16 offset record, dcn_fused.cuh), kept for A/B timing only - its fp16 offsets miss the 1e-3 bar at
+    multi-pixel offsets."""
+
+    def __init__(self, wo, bo, w, b, dg, mode=None):
+        self.dg = dg
+        self.C = w.shape[1]
+        self.main = pack_conv(w, b)
+        mode = mode or os.environ.get("EDVR_B200_DCN_SITE", "fused")
+        if mode == "fused" and (dg * 27 > 224 or w.shape[2] != 3):
+            mode = "split"
+        self.mode = mode
+        self.n_off = dg * 27
+        if mode == "fused":
+            nbytes = L.lib().eb_dcn_site_offset_weight_bytes(self.C)
+            self.wo_pack = torch.empty(nbytes // 2, dtype=torch.float16, device=w.device)
+            self.bo_cols = torch.empty(224, dtype=torch.float32, device=w.device)
+            with _Rec("pack_weight", 1):
+                L.check(L.lib().eb_dcn_site_pack_offset_weight(L.ptr(wo.contiguous()), L.ptr(None if bo is None else bo.contiguous()),
+                                                               self.C, dg, L.ptr(self.wo_pack), L.ptr(self.bo_cols),
+                                                               L.stream_ptr()), "eb_dcn_site_pack_offset_weight")
+        elif mode == "split":
+            self.offset = pack_conv(wo, bo, cout_packed=((dg * 27 + 127) // 128) * 128)
+        else:
+            self.offset = pack_conv(wo, bo, row_map=dcn_offset_row_map(dg))
+        self._rec = {}
+
+    def _raw(self, N, H, W, device):
+        key = (N, H, W)
+        t = self._rec.get(key)
+        if t is None:
+            self._rec.clear()           # one shape at a time: the offsets are the largest temporary of the graph
+            if self.mode == "split":
+                t = torch.empty(N, self.n_off, H, W, dtype=torch.float32, device=device)
+            else:
+                t = new_act(N, H, W, self.dg * 32, device)
+            self._rec[key] = t
+        return t
+
+    def arena_record(self, arena, feat):
+        """Scratch for the offsets shared by all sites of an executor (engine._Arena); None when nothing is materialised."""
+        if self.mode == "fused":
+            return None
+        if self.mode == "split":
+            return arena.f32("offraw", feat.N, self.n_off, feat.H, feat.W)
+        return arena.act("offpack", feat.N, feat.H, feat.W, self.dg * 32)
+
+    def __call__(self, x, feat, out16=None, act=ACT_NONE, absmean=None, record=None, out_nchw=None):
+        """out16: NHWC fp16 View, or out_nchw: fp32 [N, Cout, H, W] (the reference operator's layout)."""
+        N, H, W = feat.N, feat.H, feat.W
+        pc = self.main
+        flops = 2.0 * N * H * W * pc.cout * pc.cin * 9
+        if self.mode == "legacy":
+            offp = record if record is not None else self._raw(N, H, W, feat.t.device)
+            conv2d(self.offset, [feat], out16=offp, act=ACT_DCN_PACK, absmean=absmean)
+            dcn_nhwc(pc, x, offp, self.dg, out16=out16, act=act, out_nchw=out_nchw, nchw_C=pc.cout)
+            return
+        e = _epi(pc.b, act, out16, out_nchw=out_nchw, nchw_C=pc.cout)
+        am = None if absmean is None else absmean.data_ptr()
+        if self.mode == "split":
+            raw = record if record is not None else self._raw(N, H, W, feat.t.device)
+            conv2d(self.offset, [feat], act=ACT_NONE, out_nchw=raw, nchw_C=self.n_off)
+            plane = H * W
+            off_ptr = raw.data_ptr()
+            with _Rec("dcn_site", 1, flops, f"{N}x{H}x{W} C{x.C} split"):
+                L.check(L.lib().eb_dcn_site(L.ptr(x.t), x.pix_stride, x.ch_off, N, H, W, x.C, self.dg,
+                                            off_ptr, off_ptr + self.dg * 18 * plane * 4, self.n_off * plane, self.n_off * plane, 1,
+                                            None, 0, 0, None, None, L.ptr(pc.w), pc.BN, pc.n_tiles, ctypes.byref(e), am,
+                                            L.stream_ptr()), "eb_dcn_site")
+            return
+        with _Rec("dcn_site", 1, flops + 2.0 * N * H * W * self.n_off * pc.cin * 9, f"{N}x{H}x{W} C{x.C} fused"):
+            L.check(L.lib().eb_dcn_site(L.ptr(x.t), x.pix_stride, x.ch_off, N, H, W, x.C, self.dg,
+                                        None, None, 0, 0, 1, L.ptr(feat.t), feat.pix_stride, feat.ch_off,
+                                        L.ptr(self.wo_pack), L.ptr(self.bo_cols), L.ptr(pc.w), pc.BN, pc.n_tiles,
+                                        ctypes.byref(e), am, L.stream_ptr()), "eb_dcn_site")
+
+
 def nchw_to_nhwc(x, out=None):
     """fp32 [N,C,H,W] -> View fp16 [N,H,W,C]."""
     N, C, H, W = x.shape

@@ -28,3 +28,12 @@ def reduce_sum(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def max_over_ranks(value, world_size=None):
+    """Device-timed milliseconds -> the slowest rank's (bench.py: every multi-GPU number is the max over ranks).
+    On an NCCL group the reduction runs on the current CUDA device."""
+    if not (dist.is_available() and dist.is_initialized()) or (world_size is not None and world_size <= 1):
+        return float(value)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None
+    return reduce_max(value, device=dev)

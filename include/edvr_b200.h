@@ -118,6 +118,24 @@ int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int
                 const void* offpack, int offpack_pix_stride, const void* wpack, int BN, int n_tiles_n,
                 const eb_epilogue_t* epi, void* stream);
 
+/* ---- One DCNv2Pack site (archs/arch_util.py:243-257) for 3x3 / stride 1 / pad 1 / dilation 1 on NHWC fp16 features:
+ * the sampled window of x is staged in shared memory by TMA (dcn_site.cuh).  Two ways to supply the offsets:
+ *   feat == NULL : `offset` [N][dg*18][H][W] and `mask` [N][dg*9][H][W] (NULL = DCNv1-style, no modulation) in the
+ *                  reference's NCHW fp32 channel order (ops/dcn/src/deform_conv_cuda_kernel.cu:600-613), image strides in
+ *                  elements; mask_logit = 1 applies the sigmoid of arch_util.py:247 here.
+ *   feat != NULL : FUSED - conv_offset (Cin = C -> dg*27, 3x3, pad 1) is computed inside the kernel from the offset
+ *                  features `feat` (NHWC fp16 view) with weights from eb_dcn_site_pack_offset_weight; offsets and masks
+ *                  never exist in HBM.  offset / mask are ignored.
+ * absmean (optional): += sum |offset| over the call, the quantity behind the reference's "offset mean > 50" warning
+ * (arch_util.py:249-253), accumulated on the device (no host sync). */
+size_t eb_dcn_site_offset_weight_bytes(int C);
+int eb_dcn_site_pack_offset_weight(const float* wo /* [dg*27][C][3][3] */, const float* bo /* [dg*27] or NULL */, int C,
+                                   int dg, void* wo_pack, float* bo_cols /* [224] */, void* stream);
+int eb_dcn_site(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
+                const float* offset, const float* mask, long long off_img_stride, long long mask_img_stride, int mask_logit,
+                const void* feat, int f_pix_stride, int f_ch_off, const void* wo_pack, const float* bo_cols,
+                const void* wpack, int BN, int n_tiles_n, const eb_epilogue_t* epi, float* absmean, void* stream);
+
 /* ---- DCNv2 reference-layout operator (fp32 NCHW in / out) ------------------------------ */
 size_t eb_mdcn_forward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw);
 int eb_mdcn_forward(const float* x, const float* offset, const float* mask, const float* weight,

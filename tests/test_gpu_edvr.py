@@ -2,10 +2,14 @@
 bit-exact port of the reference's edvr_arch.py) on the same weights and inputs, plus the golden outputs
 recorded from the imported reference itself.
 
-Metric: the network's own contribution r = out - base (base = bilinear x4 of the centre frame, identical
-in both paths), because |base| ~ 1 would otherwise hide everything.  Tolerance: rel-L2(r) < 3e-2 and
-max|dr| / max|out| < 5e-3 for fp16-operand / fp32-accumulate arithmetic through ~100 conv layers; the
-measured values are printed (typically several times smaller) and recorded in DESIGN.md.
+Metrics and bars.  (1) max|out - ref| / max|ref| < 1e-3: north_star's bound, on the tensor the user receives.
+(2) rel-L2 of the network's own contribution r = out - base (base = bilinear x4 of the centre frame, identical in both
+paths; |base| ~ 1 would otherwise hide everything) < 5e-3: ~100 layers of fp16-operand / fp32-accumulate convolutions
+each add ~2-4e-4 of independent rounding noise (the same 10-bit operand mantissa as the TF32 path of the reference's
+cuDNN convs), which accumulates to a few 1e-3 on the residual alone; a single wrong tap, mask or offset shows up at
+>= 1e-1 there.  Measured values are printed and recorded in DESIGN.md (1e-5 .. 1e-4 on (1), 1e-4 .. 2e-3 on (2)).
+Offsets: `offset_std` scales the random conv_offset init, so the sampling offsets range from ~0.02 px (fresh model) to
+several pixels (trained model; the reference warns at a mean of 50 px, arch_util.py:249-253).
 """
 import glob
 import os
@@ -20,13 +24,14 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _compare(sd, x, hr_in=False, tol_l2=3e-2, tol_max=5e-3, center=None):
+def _compare(sd, x, hr_in=False, tol_l2=5e-3, tol_max=1e-3, center=None, dcn=None):
     from edvr_b200.engine import EDVREngine
     from oracle import edvr_ref
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     sdc = {k: v.cuda() for k, v in sd.items()}
-    ref = edvr_ref.edvr_forward(sdc, x.cuda(), hr_in=hr_in)           # fp32 oracle graph (torchvision DCN)
+    kw = {} if dcn is None else {"dcn": dcn}
+    ref = edvr_ref.edvr_forward(sdc, x.cuda(), hr_in=hr_in, **kw)     # fp32 oracle graph (torchvision DCN by default)
     eng = EDVREngine(sd, num_frame=x.shape[1], hr_in=hr_in)
     out = eng.forward(x.cuda())
     torch.cuda.synchronize()
@@ -62,6 +67,47 @@ def test_edvr_l_width_vs_oracle_graph():
     _compare(sd, x)
 
 
+@pytest.mark.parametrize("offset_std", [0.5, 3.0])
+def test_edvr_multi_pixel_offsets_vs_oracle_graph(offset_std):
+    """Sampling offsets of a trained model's magnitude (mean |offset| printed: ~1 px and ~5 px at L1)."""
+    from oracle import edvr_ref
+    sd = edvr_ref.make_state_dict(num_feat=64, num_frame=5, num_extract_block=2, num_reconstruct_block=4, seed=6,
+                                  offset_std=offset_std)
+    x = torch.rand(1, 5, 3, 40, 56, generator=torch.Generator().manual_seed(6))
+    _compare(sd, x)
+
+
+def _reference_ext_dcn():
+    """B2-signature DCN running the UNMODIFIED reference CUDA extension (oracle/_ref), or None if it was not built."""
+    from oracle import build_ref
+    if not os.path.exists(build_ref.so_path()):
+        return None
+    ext = build_ref.load_ref()
+
+    def dcn(x, off, mask, w, b, s, p, d, g, dg):
+        x = x.contiguous()
+        out = x.new_empty(x.shape[0], w.shape[0], x.shape[2], x.shape[3])
+        ext.modulated_deform_conv_forward(x, w, b, x.new_empty(0), off, mask, out, x.new_empty(0), 3, 3, s, s, p, p,
+                                          d, d, g, dg, True)
+        return out
+    return dcn
+
+
+@pytest.mark.parametrize("offset_std", [0.02, 1.0])
+def test_edvr_l_full_size_vs_reference_cuda_ext_live(offset_std):
+    """BASELINE cfg 3 at FULL size (EDVR-L, 2 clips of 7x3x180x320 -> 3x720x1280): the fused executor vs the oracle graph
+    with the reference's own CUDA dcn extension (compiled unmodified into oracle/_ref) running live on the same GPU, fp32,
+    TF32 off."""
+    from oracle import edvr_ref
+    dcn = _reference_ext_dcn()
+    if dcn is None:
+        pytest.skip("oracle/_ref not built (no /root/reference at build time)")
+    sd = edvr_ref.make_state_dict(num_feat=128, num_frame=7, num_extract_block=5, num_reconstruct_block=40, seed=9,
+                                  offset_std=offset_std)
+    x = torch.rand(2, 7, 3, 180, 320, generator=torch.Generator().manual_seed(9))
+    _compare(sd, x, dcn=dcn)
+
+
 def test_edvr_no_tsa_vs_oracle_graph():
     from oracle import edvr_ref
     sd = edvr_ref.make_state_dict(num_feat=64, num_frame=3, num_extract_block=1, num_reconstruct_block=2,
@@ -87,7 +133,7 @@ def test_edvr_vs_reference_import_golden(golden_dir):
     x = torch.from_numpy(z["x"])
     out, _ = _compare(sd, x)
     want = torch.from_numpy(z["y"])
-    assert float((out.cpu() - want).abs().max() / want.abs().max()) < 5e-3
+    assert float((out.cpu() - want).abs().max() / want.abs().max()) < 1e-3
 
 
 def test_drop_in_modules_state_dict_and_forward():
@@ -103,7 +149,7 @@ def test_drop_in_modules_state_dict_and_forward():
     with torch.no_grad():
         y = net(x)
     ref = edvr_ref.edvr_forward({k: v.cuda() for k, v in sd.items()}, x)
-    assert float((y - ref).abs().max() / ref.abs().max()) < 5e-3
+    assert float((y - ref).abs().max() / ref.abs().max()) < 1e-3
     with pytest.raises(AssertionError, match="multiple of 4"):
         net(torch.rand(1, 3, 3, 18, 24).cuda())
 

@@ -106,57 +106,80 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference path
-def cpu_reference_rate(steps=1, warmup=0, budget_s=None):
+def host_threads():
+    """Threads the CPU arm may use: the physical cores of the box, clipped to this process's CPU affinity.  NOT
+    os.cpu_count(): on the 2-way SMT hosts of this pool 128 logical CPUs made the oneDNN / torchvision kernels 40x slower
+    than 64 (profiles/r02_bench_c.log); and NOT torch's default under torchrun, which exports OMP_NUM_THREADS=1."""
+    affinity = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False) or affinity
+    except Exception:       # noqa: BLE001
+        physical = affinity
+    return max(1, min(physical, affinity))
+
+
+def cpu_reference_rate(steps=1, warmup=0, budget_s=None, full_clip_check_s=0.0):
     """The reference graph on the host cores: oracle port of edvr_arch.py (bit-exact against the imported reference,
-    tests/test_oracle.py) with the DCN via torchvision's CPU deform_conv2d, ALL host cores
-    (torch.set_num_threads(os.cpu_count()) - torchrun exports OMP_NUM_THREADS=1, which must not reach this arm).
-    A step is one EDVR-L clip 7x3x180x320 (BASELINE cfg 3 itself, no extrapolation) whenever steps + warmup of them fit
-    in `budget_s`; otherwise each step is the clip cropped to the largest 4-aligned height that fits, stated in `sample`."""
+    tests/test_oracle.py) with the DCN via torchvision's CPU deform_conv2d, all physical cores
+    (host_threads(), set explicitly).  A step is one EDVR-L clip 7x3x180x320 (BASELINE cfg 3 itself, no extrapolation)
+    whenever steps + warmup of them fit in `budget_s`; otherwise each step is the clip cropped to the largest 4-aligned
+    height that fits (conv work is linear in pixels), stated in `sample`, and - if `full_clip_check_s` allows - ONE full
+    clip is timed as well and reported as `full_clip`."""
     import torch
     from oracle import edvr_ref
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     sd = edvr_ref.make_state_dict(**CFG3, seed=0)
     g = torch.Generator().manual_seed(0)
-    probe = torch.rand(1, 7, 3, 32, 64, generator=g)
+    ph, pw = 48, 160
+    probe = torch.rand(1, 7, 3, ph, pw, generator=g)
     edvr_ref.edvr_forward(sd, probe)                              # page in, spin up the thread pool (untimed)
     t0 = time.perf_counter()
     edvr_ref.edvr_forward(sd, probe)
-    per_px = (time.perf_counter() - t0) / (32 * 64)
-    est_full = per_px * LR_H * LR_W
+    est_full = (time.perf_counter() - t0) / (ph * pw) * LR_H * LR_W
     h = LR_H
     if budget_s is not None and est_full * (steps + warmup) > budget_s:
         h = int(LR_H * budget_s / (est_full * (steps + warmup))) // 4 * 4
         h = max(16, min(LR_H, h))
-    x = torch.rand(1, 7, 3, h, LR_W, generator=g)
+
+    def timed(rows, n, w):
+        x = torch.rand(1, 7, 3, rows, LR_W, generator=g)
+        for _ in range(w):
+            edvr_ref.edvr_forward(sd, x)
+        t = time.perf_counter()
+        for _ in range(n):
+            edvr_ref.edvr_forward(sd, x)
+        return (time.perf_counter() - t) / n
+
+    dt = timed(h, steps, warmup)
     frac = h / float(LR_H)
-    for _ in range(warmup):
-        edvr_ref.edvr_forward(sd, x)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        edvr_ref.edvr_forward(sd, x)
-    dt = (time.perf_counter() - t0) / steps
     full = h == LR_H
-    return {"value": frac / dt, "unit": "HR frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "same_config": full,
-            "sample": (f"1 full EDVR-L clip 7x3x{LR_H}x{LR_W} per step" if full else
-                       f"1 EDVR-L clip cropped to 7x3x{h}x{LR_W} ({frac:.3f} of the rows; conv work is linear in pixels) per step")
-                      + f", {steps} timed step(s) after {warmup} warm-up, {dt:.2f} s/step; oracle/edvr_ref.py graph, "
-                        "DCN = torchvision CPU deform_conv2d",
-            "sec_per_step": dt}
+    out = {"value": frac / dt, "unit": "HR frames/s", "cores": torch.get_num_threads(), "kind": "port",
+           "same_config": full,
+           "sample": (f"1 full EDVR-L clip 7x3x{LR_H}x{LR_W} per step" if full else
+                      f"1 EDVR-L clip cropped to 7x3x{h}x{LR_W} ({frac:.3f} of the rows; conv work is linear in pixels) per step")
+                     + f", {steps} timed step(s) after {warmup} warm-up, {dt:.2f} s/step; oracle/edvr_ref.py graph, "
+                       f"DCN = torchvision CPU deform_conv2d, {torch.get_num_threads()} threads",
+           "sec_per_step": dt}
+    if not full and est_full <= full_clip_check_s:
+        dtf = timed(LR_H, 1, 0)
+        out["full_clip"] = {"value": 1.0 / dtf, "unit": "HR frames/s", "sec": dtf,
+                            "note": "one full 7x3x180x320 clip timed after the sampled steps (same config, no extrapolation)"}
+    return out
 
 
 def run_reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    cb = cpu_reference_rate(steps=max(args.steps, 1), warmup=max(args.warmup, 0), budget_s=150.0)
+    cb = cpu_reference_rate(steps=max(args.steps, 1), warmup=max(args.warmup, 0), budget_s=150.0, full_clip_check_s=75.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "HR frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sec_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD + ", CPU reference graph (does not scale with --gpus: host cores only)",
                        "clips_per_step": 1, "same_config": cb["same_config"]},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "full_clip") if k in cb},
             "e2e": {"value": cb["value"], "unit": "HR frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -345,7 +368,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"skipped": "EDVR_BENCH_PROFILING=1"}
         else:
             if world == 1:
-                cb = cpu_reference_rate(steps=1, warmup=0, budget_s=90.0)
+                cb = cpu_reference_rate(steps=1, warmup=0, budget_s=75.0)
                 line["cpu_baseline"] = {k: v for k, v in cb.items() if k != "sec_per_step"}
             try:
                 line["ref_cuda"] = reference_cuda_rate(sd, B)

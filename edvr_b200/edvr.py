@@ -43,6 +43,14 @@ def _params_key(module):
     return tuple((p.data_ptr(), int(p._version)) for p in module.parameters())
 
 
+def _wants_autograd(module, x):
+    """True when the call must stay differentiable (training, BASELINE cfg 5).  CPU tensors are an error: like the
+    reference's dcn (deform_conv.py:133-134) this package has no CPU implementation."""
+    if not x.is_cuda:
+        raise NotImplementedError(f"edvr_b200.{module.__class__.__name__} runs on CUDA tensors only")
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters()))
+
+
 def _sd(module, prefix=""):
     return {prefix + k: v for k, v in module.state_dict().items()}
 
@@ -62,8 +70,11 @@ class ResidualBlockNoBN(nn.Module):
 
     def forward(self, x):
         C = self.conv1.in_channels
-        if torch.is_grad_enabled() or not x.is_cuda or C % 64 or self.res_scale != 1:
+        if _wants_autograd(self, x):
             return x + self.conv2(F.relu(self.conv1(x))) * self.res_scale
+        if C % 64 or self.res_scale != 1:
+            raise ValueError(f"edvr_b200.ResidualBlockNoBN: num_feat={C} (multiple of 64) and res_scale={self.res_scale} (1) "
+                             "are outside the tensor-core path; there is no cuDNN fallback")
         key = _params_key(self)
         if self._cache is None or self._cache[0] != key:
             self._cache = (key, ops.pack_conv(self.conv1.weight.detach().float(), self.conv1.bias.detach().float()),
@@ -122,8 +133,10 @@ class PCDAlignment(nn.Module):
 
     def forward(self, nbr_feat_l, ref_feat_l):
         x0 = nbr_feat_l[0]
-        if torch.is_grad_enabled() or not x0.is_cuda or self.num_feat % 64:
+        if _wants_autograd(self, x0):
             return self._autograd_forward(nbr_feat_l, ref_feat_l)
+        if self.num_feat % 64:
+            raise ValueError(f"edvr_b200.PCDAlignment: num_feat={self.num_feat} must be a multiple of 64; no cuDNN fallback")
         key = _params_key(self)
         if self._cache is None or self._cache[0] != key:
             p = {}
@@ -183,8 +196,11 @@ class TSAFusion(nn.Module):
 
     def forward(self, aligned_feat):
         b, t, c, h, w = aligned_feat.size()
-        if torch.is_grad_enabled() or not aligned_feat.is_cuda or self.num_feat % 64 or h % 4 or w % 4:
+        if _wants_autograd(self, aligned_feat):
             return self._autograd_forward(aligned_feat)
+        if self.num_feat not in (64, 128, 256) or h % 4 or w % 4:
+            raise ValueError(f"edvr_b200.TSAFusion: num_feat={self.num_feat} (64/128/256) and h, w = {h}, {w} (multiples of 4) "
+                             "are outside the tensor-core path; there is no cuDNN fallback")
         key = _params_key(self)
         if self._cache is None or self._cache[0] != key:
             p = {}
@@ -307,8 +323,11 @@ class EDVR(nn.Module):
             assert h % 16 == 0 and w % 16 == 0, "The height and width must be multiple of 16."
         else:
             assert h % 4 == 0 and w % 4 == 0, "The height and width must be multiple of 4."
-        if torch.is_grad_enabled() or not x.is_cuda or self.num_feat % 64:
-            return self._autograd_forward(x)
+        if not x.is_cuda:
+            # no CPU path (north_star); the reference cannot run EDVR on CPU either: its dcn raises at deform_conv.py:133-134
+            raise NotImplementedError("edvr_b200.EDVR runs on CUDA tensors only")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._autograd_forward(x)       # training (BASELINE cfg 5): differentiable graph, see train.py
         return self.engine().forward(x.float()).to(x.dtype)
 
     @torch.no_grad()

@@ -187,6 +187,24 @@ def run_tsa(a, p, pre, aligned, B, T, center, fused16, trunk32):
     ops.tsa_modulate(f2.slice(0, C), a5, ad2, out16=fused16, out32=trunk32)
 
 
+def unsupported_reasons(sd, C, dg, with_tsa):
+    """Why a reference-format state_dict cannot run on the B200 kernels ([] = supported).  There is deliberately no
+    PyTorch / cuDNN fallback behind the drop-in modules (north_star): an unsupported configuration is an error."""
+    why = []
+    if C % 64:
+        why.append(f"num_feat={C} must be a multiple of 64 (64-channel K chunks of the implicit GEMMs)")
+    if with_tsa and C not in (64, 128, 256):
+        why.append(f"num_feat={C}: the TSA correlation kernel covers 64, 128 and 256 channels")
+    if dg < 1 or C % dg or not ((C // dg) == 8 or (C // dg) % 16 == 0):
+        why.append(f"num_feat/deformable_groups = {C}/{dg} must be 8 or a multiple of 16 (one bilinear sample per 16-byte K atom pair)")
+    first = "predeblur.conv_first.weight" if "predeblur.conv_first.weight" in sd else "conv_first.weight"
+    if sd[first].shape[1] != 3:
+        why.append(f"num_in_ch={sd[first].shape[1]}: conv_first is built for 3 input channels")
+    if sd["conv_last.weight"].shape[0] != 3:
+        why.append(f"num_out_ch={sd['conv_last.weight'].shape[0]}: the output stage is built for 3 channels")
+    return why
+
+
 class EDVREngine:
     def __init__(self, state_dict, num_frame, center_frame_idx=None, hr_in=False, device="cuda"):
         dev = torch.device(device)
@@ -204,8 +222,9 @@ class EDVREngine:
         self.with_tsa = "fusion.feat_fusion.weight" in sd
         self.n_extract = len({k.split(".")[1] for k in sd if k.startswith("feature_extraction.")})
         self.n_recon = len({k.split(".")[1] for k in sd if k.startswith("reconstruction.")})
-        if self.C % 64:
-            raise ValueError(f"num_feat={self.C}: the tensor-core path needs a multiple of 64")
+        problems = unsupported_reasons(sd, self.C, self.dg, self.with_tsa)
+        if problems:
+            raise ValueError("edvr_b200 (sm_100a tensor-core path) does not cover this EDVR configuration: " + "; ".join(problems))
         self.arena = _Arena(self.device)
         self.absmean = torch.zeros(16, dtype=torch.float32, device=self.device)   # one slot per DCN site
         self._absmean_counts = None

@@ -108,6 +108,138 @@ def test_edvr_l_full_size_vs_reference_cuda_ext_live(offset_std):
     _compare(sd, x, dcn=dcn)
 
 
+def _installed_reference():
+    """The UNMODIFIED reference package as pip-installed from /root/reference into baseline/_ref (travels with gpurun), or None."""
+    import sys
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.isdir(os.path.join(root, "basicsr", "models", "archs")):
+        return None
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import basicsr.models.archs.edvr_arch as arch      # noqa: F401  (imports the reference's own compiled dcn extension)
+    return sys.modules["basicsr.models.ops.dcn.deform_conv"], arch
+
+
+def test_unmodified_reference_edvr_runs_on_the_b1_shim():
+    """B1 boundary on the GPU: the reference's OWN EDVR graph (basicsr.models.archs.edvr_arch, unmodified, cuDNN convolutions)
+    is run twice on identical weights and input - once with the reference's compiled deform_conv_ext, once with
+    edvr_b200.deform_conv_ext bound in its place - and must agree to 1e-3.  Multi-pixel offsets."""
+    ref = _installed_reference()
+    if ref is None:
+        pytest.skip("baseline/_ref (pip install of /root/reference) not present")
+    dc, arch = ref
+    import edvr_b200.deform_conv_ext as shim
+    from oracle import edvr_ref
+    kw = dict(num_feat=64, num_frame=3, deformable_groups=8, num_extract_block=1, num_reconstruct_block=2)
+    sd = edvr_ref.make_state_dict(**kw, seed=21, offset_std=1.0)
+    net = arch.EDVR(center_frame_idx=None, **kw).cuda().eval()
+    net.load_state_dict(sd, strict=True)
+    x = torch.rand(2, 3, 3, 32, 40, generator=torch.Generator().manual_seed(21)).cuda()
+    own = dc.deform_conv_ext
+    with torch.no_grad():
+        y_ref = net(x)
+        dc.deform_conv_ext = shim
+        try:
+            y_ours = net(x)
+        finally:
+            dc.deform_conv_ext = own
+    e = rel_err(y_ours.cpu(), y_ref.cpu())
+    print(f"reference EDVR, own ext vs B1 shim: max-rel {e[0]:.3e}, rel-L2 {e[1]:.3e}")
+    assert e[0] < 1e-3 and e[1] < 1e-3, e
+
+
+def test_standalone_b3_modules_match_the_reference_modules():
+    """The drop-in module types north_star names - PCDAlignment, TSAFusion, ResidualBlockNoBN - called on their own (fp32
+    NCHW in/out like the reference's), against the reference's modules (baseline/_ref) or, without them, the oracle port."""
+    from edvr_b200 import edvr as ours
+    from oracle import edvr_ref
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = _installed_reference()
+    g = torch.Generator().manual_seed(31)
+    C, dg, T = 64, 8, 3
+
+    def rand_init(mod, std=None):
+        with torch.no_grad():
+            for name, p in mod.named_parameters():
+                if "conv_offset" in name:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.05)      # ~ +-1.5 px offsets on unit-variance features
+                elif std is not None and p.dim() == 4:
+                    p.copy_(torch.randn(p.shape, generator=g) * std)
+
+    # ---- ResidualBlockNoBN
+    m = ours.ResidualBlockNoBN(num_feat=C).cuda().eval()
+    rand_init(m, 0.03)
+    x = torch.randn(2, C, 20, 28, generator=g).cuda()
+    with torch.no_grad():
+        got = m(x)
+        want = x + F.conv2d(F.relu(F.conv2d(x, m.conv1.weight, m.conv1.bias, 1, 1)), m.conv2.weight, m.conv2.bias, 1, 1)
+    e = rel_err(got.cpu(), want.cpu())
+    assert e[0] < 1e-3, ("ResidualBlockNoBN", e)
+
+    # ---- PCDAlignment
+    m = ours.PCDAlignment(num_feat=C, deformable_groups=dg).cuda().eval()
+    rand_init(m)
+    nbr = [torch.randn(2, C, 24 >> i, 32 >> i, generator=g).cuda() for i in range(3)]
+    rf = [torch.randn(2, C, 24 >> i, 32 >> i, generator=g).cuda() for i in range(3)]
+    with torch.no_grad():
+        got = m(nbr, rf)
+        if ref is not None:
+            rm = ref[1].PCDAlignment(num_feat=C, deformable_groups=dg).cuda().eval()
+            rm.load_state_dict(m.state_dict(), strict=True)
+            want = rm(nbr, rf)
+        else:
+            sd = {"pcd_align." + k: v for k, v in m.state_dict().items()}
+            want = edvr_ref.pcd_align(sd, nbr, rf, dg, edvr_ref.dcn_torchvision)
+    e = rel_err(got.cpu(), want.cpu())
+    print(f"PCDAlignment standalone: {e}")
+    assert e[0] < 2e-3 and e[1] < 2e-3, ("PCDAlignment", e)      # 15 fp16-operand layers in sequence: 2 x the per-op bound
+
+    # ---- TSAFusion
+    m = ours.TSAFusion(num_feat=C, num_frame=T, center_frame_idx=1).cuda().eval()
+    aligned = torch.randn(2, T, C, 24, 32, generator=g).cuda()
+    with torch.no_grad():
+        got = m(aligned)
+        if ref is not None:
+            rm = ref[1].TSAFusion(num_feat=C, num_frame=T, center_frame_idx=1).cuda().eval()
+            rm.load_state_dict(m.state_dict(), strict=True)
+            want = rm(aligned)
+        else:
+            want = edvr_ref.tsa_fusion({"fusion." + k: v for k, v in m.state_dict().items()}, aligned, 1)
+    e = rel_err(got.cpu(), want.cpu())
+    print(f"TSAFusion standalone: {e}")
+    assert e[0] < 2e-3 and e[1] < 2e-3, ("TSAFusion", e)
+
+
+def test_no_silent_fallbacks():
+    """north_star: no cuDNN dispatch on the named ops, no CPU fallback - unsupported inputs are errors, not eager PyTorch."""
+    from edvr_b200 import edvr as ours
+    with pytest.raises(NotImplementedError):
+        ours.EDVR(num_feat=64, num_frame=3, num_reconstruct_block=1)(torch.rand(1, 3, 3, 16, 16))      # CPU tensor
+    with pytest.raises(NotImplementedError):
+        ours.ResidualBlockNoBN(64)(torch.rand(1, 64, 8, 8))
+    net = ours.EDVR(num_feat=96, num_frame=3, num_extract_block=1, num_reconstruct_block=1).cuda().eval()
+    with torch.no_grad(), pytest.raises(ValueError, match="multiple of 64"):
+        net(torch.rand(1, 3, 3, 16, 16).cuda())
+    with torch.no_grad(), pytest.raises(ValueError, match="multiple of 64"):
+        ours.ResidualBlockNoBN(96).cuda()(torch.rand(1, 96, 8, 8).cuda())
+
+
+def test_graphed_forward_is_bit_identical():
+    """Latency configuration: EDVREngine.graphed() replays the whole forward as one CUDA graph; same kernels, same values."""
+    from edvr_b200.engine import EDVREngine
+    from oracle import edvr_ref
+    kw = dict(num_feat=64, num_frame=3, deformable_groups=8, num_extract_block=1, num_reconstruct_block=2)
+    eng = EDVREngine(edvr_ref.make_state_dict(**kw, seed=12), num_frame=3)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x0, x1 = (torch.rand(1, 3, 3, 24, 32, device="cuda", generator=g) for _ in range(2))
+    want0, want1 = eng.forward(x0).clone(), eng.forward(x1).clone()
+    run = eng.graphed(x0)
+    assert torch.equal(run(), want0)
+    assert torch.equal(run(x1), want1)
+    assert torch.equal(run(x0), want0)
+
+
 def test_edvr_no_tsa_vs_oracle_graph():
     from oracle import edvr_ref
     sd = edvr_ref.make_state_dict(num_feat=64, num_frame=3, num_extract_block=1, num_reconstruct_block=2,

@@ -433,6 +433,8 @@ def main():
         run_reference_arm(args)
     elif args.mode == "train":
         from edvr_b200 import train_bench
+        if args.steps == 200:
+            args.steps = 20          # a training step is ~10x an inference step; keep the default run within a minute
         train_bench.main(args)
     else:
         run_ours(args)

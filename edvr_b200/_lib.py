@@ -27,7 +27,7 @@ class Epilogue(ctypes.Structure):
                 ("out16", c_void_p), ("out16_pix_stride", c_int), ("out16_ch_off", c_int),
                 ("out32", c_void_p), ("out32_pix_stride", c_int), ("out32_ch_off", c_int),
                 ("out_nchw", c_void_p), ("nchw_C", c_int), ("out_mode", c_int),
-                ("absmean_acc", c_void_p), ("f32_blocked", c_int)]
+                ("absmean_acc", c_void_p), ("f32_blocked", c_int), ("bf16", c_int)]
 
 
 _SIGS = {
@@ -42,6 +42,10 @@ _SIGS = {
                                 ctypes.POINTER(Epilogue), c_void_p, c_void_p]),
     "eb_conv2d_pair_supported": (c_int, [c_int] * 4),
     "eb_pack_weight_pair": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "eb_pack_weight_pair_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "eb_conv_wgrad_workspace": (c_size_t, [c_int] * 6),
+    "eb_conv_wgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int] + [c_int] * 7 + [c_float, c_void_p, c_void_p, c_size_t,
+                                                                                           c_void_p]),
     "eb_conv2d_pair": (c_int, [ctypes.POINTER(Src), c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                ctypes.POINTER(Epilogue), c_void_p]),
     "eb_dcn_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,

@@ -11,6 +11,7 @@
 #include "conv_igemm.cuh"
 #include "conv_igemm2.cuh"
 #include "conv_pair.cuh"
+#include "conv_train.cuh"
 #include "dcn_backward.cuh"
 #include "dcn_fused.cuh"
 #include "dcn_site.cuh"
@@ -83,6 +84,7 @@ int fill_epi(const eb_epilogue_t* e, int H, int W, int cout_packed, EpiParams* o
     o->out_mode = e->out_mode;
     o->absmean_acc = e->absmean_acc;
     o->f32_blocked = e->f32_blocked;
+    o->bf16 = e->bf16;
     o->res16_wide = (e->res16 && reinterpret_cast<uintptr_t>(e->res16) % 32 == 0 && e->res_pix_stride % 16 == 0 &&
                      e->res_ch_off % 16 == 0) ? 1 : 0;
     if (e->f32_blocked && (e->out_mode != EB_OUT_SAME || (e->out32 && (e->out32_pix_stride % 32 || e->out32_ch_off % 32)) ||
@@ -211,13 +213,22 @@ static int encode_halo_map(const ConvSrc& S, int H, int W, int n_images, int tap
 
 int eb_pack_weight_pair(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN, int n_tiles_n,
                         void* wpack, void* stream) {
+    return eb_pack_weight_pair_ex(w, cout, cin, ktaps, row_map, BN, n_tiles_n, wpack, 0, stream);
+}
+
+int eb_pack_weight_pair_ex(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN, int n_tiles_n,
+                           void* wpack, int bf16, void* stream) {
     if (!w || !wpack) return fail(EB_ERR_NULLPTR, "pack_weight_pair: null pointer");
     if (cin % 64 || BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || ktaps < 1 || cout < 1)
         return fail(EB_ERR_INVALID_SHAPE, "pack_weight_pair: cin=%d BN=%d tiles=%d taps=%d", cin, BN, n_tiles_n, ktaps);
     if (!row_map && cout > BN * n_tiles_n) return fail(EB_ERR_INVALID_SHAPE, "pack_weight_pair: cout exceeds packed rows");
     const long long groups = static_cast<long long>(n_tiles_n) * BN * (cin / 8) * ktaps;
-    pack_weight_pair_kernel<<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        w, cout, cin, ktaps, row_map, BN, n_tiles_n, static_cast<__half*>(wpack));
+    if (bf16)
+        pack_weight_pair_kernel<true><<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            w, cout, cin, ktaps, row_map, BN, n_tiles_n, static_cast<__half*>(wpack));
+    else
+        pack_weight_pair_kernel<false><<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            w, cout, cin, ktaps, row_map, BN, n_tiles_n, static_cast<__half*>(wpack));
     return check_launch("pack_weight_pair");
 }
 
@@ -242,6 +253,7 @@ static bool conv_force_v2() {
 
 static int launch_conv(const ConvParams& P, cudaStream_t st) {
     if (P.N == 0) return EB_OK;
+    if (P.epi.bf16) return fail(EB_ERR_UNSUPPORTED, "conv2d: bf16 operands are served by the CTA-pair kernel only (eb_conv2d_pair)");
     // epilogue kind of the transposed kernel (conv_igemm2.cuh); combinations it does not cover use the generic kernel
     int ek = -1;
     // measured on B200 (profiles/r01_conv_stats_*): the channel-major kernel wins when the K loop is long
@@ -448,6 +460,8 @@ int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksiz
         if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "conv2d_pair: pixel-shuffle tensor map failed (%d)", static_cast<int>(r));
         PP.tma_out = 1;
     }
+    if (P.epi.bf16 && !(ek1 == EK_PLAIN && PP.tma_out && !P.epi.res16))
+        return fail(EB_ERR_UNSUPPORTED, "conv2d_pair: bf16 needs the plain NHWC output (no residual, no index map)");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * nclusters);
     cfg.blockDim = dim3(CP_THREADS);
@@ -533,6 +547,73 @@ int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int
     if (int rc = fill_epi(epi, H, W, BN * n_tiles_n, &P.epi)) return rc;
     if (P.epi.out_mode != OUT_SAME) return fail(EB_ERR_UNSUPPORTED, "dcn_nhwc: out_mode");
     return launch_dcn(P, static_cast<cudaStream_t>(stream));
+}
+
+// ---- training step: weight gradient of a dense 3x3 (pad 1) / 1x1 convolution (conv_train.cuh)
+namespace {
+struct WgradGeo { int Hp, Wp, margin; long long body, Ppad; size_t rowsA, a_bytes, b_bytes; int copies; };
+WgradGeo wgrad_geo(int N, int H, int W, int Cin, int Cout, int ksize) {
+    WgradGeo g;
+    g.Hp = H + 2; g.Wp = (W + 2 + 7) / 8 * 8;
+    g.margin = (g.Wp + 8 + 63) / 64 * 64;
+    g.body = (static_cast<long long>(N) * g.Hp * g.Wp + 63) / 64 * 64;
+    g.Ppad = g.body + 2 * g.margin;
+    g.rowsA = static_cast<size_t>((Cout + 127) / 128) * 128;
+    g.copies = ksize == 3 ? 3 : 1;
+    g.a_bytes = (g.rowsA * g.Ppad * 2 + 255) / 256 * 256;
+    g.b_bytes = (static_cast<size_t>(g.copies) * Cin * g.Ppad * 2 + 255) / 256 * 256;
+    return g;
+}
+}  // namespace
+
+size_t eb_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ksize) {
+    const WgradGeo g = wgrad_geo(N, H, W, Cin, Cout, ksize);
+    return g.a_bytes + g.b_bytes;
+}
+
+int eb_conv_wgrad(const void* x, int x_pix_stride, int x_ch_off, const void* gy, int gy_pix_stride, int gy_ch_off, int N,
+                  int H, int W, int Cin, int Cout, int ksize, int bf16, float scale, float* grad_weight, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    if (!x || !gy || !grad_weight) return fail(EB_ERR_NULLPTR, "conv_wgrad: null pointer");
+    if (N < 1 || H < 1 || W < 1 || Cout < 1 || Cin < 32 || (ksize != 1 && ksize != 3))
+        return fail(EB_ERR_INVALID_SHAPE, "conv_wgrad: N=%d H=%d W=%d Cin=%d Cout=%d k=%d", N, H, W, Cin, Cout, ksize);
+    const int BN = Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 0));
+    if (!BN) return fail(EB_ERR_UNSUPPORTED, "conv_wgrad: Cin=%d must be a multiple of 32", Cin);
+    if (x_pix_stride < x_ch_off + Cin || gy_pix_stride < gy_ch_off + Cout) return fail(EB_ERR_INVALID_SHAPE, "conv_wgrad: views");
+    const WgradGeo g = wgrad_geo(N, H, W, Cin, Cout, ksize);
+    if (!workspace || workspace_bytes < g.a_bytes + g.b_bytes) return fail(EB_ERR_WORKSPACE, "conv_wgrad: workspace %zu < %zu", workspace_bytes, g.a_bytes + g.b_bytes);
+    if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "conv_wgrad: workspace must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint16_t* gyT = static_cast<uint16_t*>(workspace);
+    uint16_t* xT = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(workspace) + g.a_bytes);
+    if (cudaMemsetAsync(workspace, 0, g.a_bytes + g.b_bytes, st) != cudaSuccess) return fail(EB_ERR_LAUNCH, "conv_wgrad: memset");
+    const long long copy_stride = static_cast<long long>(Cin) * g.Ppad;
+    {
+        dim3 block(32, 8);
+        dim3 grid_g((W + 31) / 32, H, N * ((Cout + 31) / 32));
+        nhwc_to_cmajor_pad_kernel<<<grid_g, block, 0, st>>>(static_cast<const uint16_t*>(gy), gy_pix_stride, gy_ch_off, Cout, H, W,
+                                                            gyT, 0, g.Ppad, g.Hp, g.Wp, g.margin, 1);
+        dim3 grid_x((W + 31) / 32, H, N * ((Cin + 31) / 32));
+        nhwc_to_cmajor_pad_kernel<<<grid_x, block, 0, st>>>(static_cast<const uint16_t*>(x), x_pix_stride, x_ch_off, Cin, H, W,
+                                                            xT, copy_stride, g.Ppad, g.Hp, g.Wp, g.margin, g.copies);
+        if (int rc = check_launch("conv_wgrad transposes")) return rc;
+    }
+    const int taps = ksize * ksize;
+    const long long k_steps = g.body / 64;
+    const int tiles = taps * (Cin / BN) * static_cast<int>(g.rowsA / 128);
+    long long splits = (2LL * num_sms() + tiles - 1) / tiles;
+    if (splits > k_steps) splits = k_steps;
+    if (splits < 1) splits = 1;
+    const int steps_per_split = static_cast<int>((k_steps + splits - 1) / splits);
+    splits = (k_steps + steps_per_split - 1) / steps_per_split;
+    if (int rc = set_smem(conv_wgrad_kernel, CW_SMEM_BYTES)) return rc;
+    dim3 grid(taps * (Cin / BN), static_cast<unsigned>(g.rowsA / 128), static_cast<unsigned>(splits));
+    // 1x1: the single unshifted copy sits at copy index 0, the kernel addresses copy (dxi = 1) -> pass a base one copy earlier
+    const __half* Bbase = reinterpret_cast<const __half*>(xT) - (ksize == 1 ? copy_stride : 0);
+    conv_wgrad_kernel<<<grid, 128, CW_SMEM_BYTES, st>>>(reinterpret_cast<const __half*>(gyT), Bbase, copy_stride, grad_weight,
+                                                        Cout, Cin, taps, g.Ppad, g.Wp, BN, steps_per_split, g.margin, k_steps,
+                                                        bf16 ? 1 : 0, scale);
+    return check_launch("conv_wgrad");
 }
 
 // ---- DCN site kernel (dcn_site.cuh): windows of x staged in shared memory; conv_offset optionally fused in front

@@ -14,6 +14,7 @@
 // a 3x3 tap shift of an activation tile is just a different start address inside the same
 // halo tile: one load of the halo serves all nine taps.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -368,6 +369,10 @@ __device__ __forceinline__ void sts_v4(uint32_t saddr, uint4 v) {
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) {

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
             if (leader) {
                 // ================= MMA issuer (even CTA): M = 256 rows (128 per CTA), N = BN, K = 16 per instruction.
                 // All 32 lanes run the loops (uniform control flow), one elected lane issues.
-                const uint32_t idesc = umma_idesc_f16(256, P.BN);
+                const uint32_t idesc = umma_idesc_f16(256, P.BN, P.epi.bf16 ? 1u : 0u);
                 const uint32_t w_lo0 = umma_desc_lo(smem_u32(w_smem), lbo_b);
                 const uint32_t a_hi = umma_desc_hi(RP * 16), b_hi = umma_desc_hi(128);
                 const uint32_t b_step = (2u * lbo_b) >> 4;                 // one K16 step of the resident weights
@@ -297,11 +297,19 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                     } else if (TMA_OUT) {
                         if (lane == 0) bulk_wait_group_read0();          // the previous box has been read out of the staging buffer
                         __syncwarp();
+                        if (EK == EK_PLAIN && P.epi.bf16) {            // training step: bf16 activations
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            sts_v4(st_row + ((u * 16) ^ st_x),
-                                   make_uint4(pack_h2(v[u * 8 + 0], v[u * 8 + 1]), pack_h2(v[u * 8 + 2], v[u * 8 + 3]),
-                                              pack_h2(v[u * 8 + 4], v[u * 8 + 5]), pack_h2(v[u * 8 + 6], v[u * 8 + 7])));
+                            for (int u = 0; u < 4; ++u)
+                                sts_v4(st_row + ((u * 16) ^ st_x),
+                                       make_uint4(pack_bf2(v[u * 8 + 0], v[u * 8 + 1]), pack_bf2(v[u * 8 + 2], v[u * 8 + 3]),
+                                                  pack_bf2(v[u * 8 + 4], v[u * 8 + 5]), pack_bf2(v[u * 8 + 6], v[u * 8 + 7])));
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                sts_v4(st_row + ((u * 16) ^ st_x),
+                                       make_uint4(pack_h2(v[u * 8 + 0], v[u * 8 + 1]), pack_h2(v[u * 8 + 2], v[u * 8 + 3]),
+                                                  pack_h2(v[u * 8 + 4], v[u * 8 + 5]), pack_h2(v[u * 8 + 6], v[u * 8 + 7])));
+                        }
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0 && box_ok) {

@@ -51,8 +51,12 @@ constexpr int DS_F_PLANE = DS_F_RP_Y * DS_F_RP_X * 16;    // 2880: one K atom of
 constexpr int DS_F_STAGE = 4 * DS_F_PLANE;                // 32 channels per stage = 11520
 constexpr int DS_F_STAGES = 3;
 constexpr int DS_WO_STAGE = DS_OFF_N * 64;                // (32 channels, one tap): 224 rows x 64 B = 14336
-constexpr int DS_WO_STAGES = 4;
-static_assert(DS_F_STAGES * DS_F_STAGE + DS_WO_STAGES * DS_WO_STAGE <= DS_AB_BYTES, "phase A staging must fit under phase B");
+constexpr int DS_WO_STAGES_A = 4;                         // conv_offset weight stages under the gather/MMA stages ...
+constexpr int DS_WO_STAGES_B = 3;                         // ... and in window buffer 1, idle until the tile's second chunk
+constexpr int DS_WO_STAGES = DS_WO_STAGES_A + DS_WO_STAGES_B;    // 100 KB of weights in flight: phase A streams 516 KB per
+                                                          // tile from L2 and was latency-bound with 57 KB (r02_dcn_site_v2)
+static_assert(DS_F_STAGES * DS_F_STAGE + DS_WO_STAGES_A * DS_WO_STAGE <= DS_AB_BYTES, "phase A staging must fit under phase B");
+static_assert(DS_WO_STAGES_B * DS_WO_STAGE <= DS_WIN_BYTES, "extra weight stages must fit in the second window buffer");
 
 enum : int { DS_OFF_GLOBAL = 0, DS_OFF_TMEM = 1 };
 
@@ -107,7 +111,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
     uint8_t* a_smem = smem + 2 * DS_WIN_BYTES;                  // [DS_STAGES][DC_A_BYTES]
     uint8_t* b_smem = a_smem + DS_STAGES * DC_A_BYTES;          // [DS_STAGES][DC_B_BYTES]
     uint8_t* f_smem = a_smem;                                   // phase A: [DS_F_STAGES][DS_F_STAGE] (aliases a/b stages)
-    uint8_t* wo_smem = a_smem + DS_F_STAGES * DS_F_STAGE;       // phase A: [DS_WO_STAGES][DS_WO_STAGE]
+    uint8_t* wo_smem = a_smem + DS_F_STAGES * DS_F_STAGE;       // phase A: [DS_WO_STAGES_A][DS_WO_STAGE] + [DS_WO_STAGES_B] in window 1
+    auto wo_stage = [&](uint32_t st) -> uint8_t* {
+        return st < DS_WO_STAGES_A ? wo_smem + st * DS_WO_STAGE : win_smem + DS_WIN_BYTES + (st - DS_WO_STAGES_A) * DS_WO_STAGE;
+    };
     float* bias_s = reinterpret_cast<float*>(a_smem + DS_AB_BYTES);
     float* bo_s = bias_s + DC_MAX_COUT;                         // [256] conv_offset bias (fused)
     uint64_t* bars = reinterpret_cast<uint64_t*>(bo_s + 256);
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
                         const uint32_t s = wo_it % DS_WO_STAGES, ph = (wo_it / DS_WO_STAGES) & 1u;
                         mbar_wait_t<64>(&wo_empty[s], ph ^ 1u);
                         mbar_arrive_expect_tx(&wo_full[s], DS_WO_STAGE);
-                        bulk_g2s(wo_smem + s * DS_WO_STAGE, wsrc + static_cast<size_t>(st) * DS_WO_STAGE, DS_WO_STAGE, &wo_full[s]);
+                        bulk_g2s(wo_stage(s), wsrc + static_cast<size_t>(st) * DS_WO_STAGE, DS_WO_STAGE, &wo_full[s]);
                     }
                     // phase B stages may be refilled once phase A's MMAs have read the aliased bytes
                     mbar_wait_t<64>(off_full, tile_it & 1u);
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
                         const uint32_t ws = wo_it % DS_WO_STAGES;
                         mbar_wait_t<64>(&wo_full[ws], (wo_it / DS_WO_STAGES) & 1u);
                         tc_fence_after_sync();
-                        const uint32_t w_lo0 = umma_desc_lo(smem_u32(wo_smem + ws * DS_WO_STAGE), DS_OFF_N * 16);
+                        const uint32_t w_lo0 = umma_desc_lo(smem_u32(wo_stage(ws)), DS_OFF_N * 16);
                         const int ki = t / 3, kj = t % 3;
                         if (elect_one()) {
 #pragma unroll
@@ -290,18 +297,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
         // ================= TMA producer: sampling windows of x (one per tile and 64-channel chunk, two buffers) and, fused,
         // the halo stages of the offset features for phase A
         if (lane == 0) {
-            uint32_t w_it = 0, f_it = 0, tile_it = 0;
+            uint32_t used0 = 0, used1 = 0, f_it = 0, tile_it = 0;  // window buffer = chunk & 1 (buffer 1 doubles as weight staging in phase A)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
                 const int pt = tile / P.n_tiles_n;
                 const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
                 const int wx0 = tx * DC_TILE_W - 1 - DS_R, wy0 = ty * DC_TILE_H - 1 - DS_R;
                 int c_win = 0;
                 auto issue_window = [&]() {
-                    const uint32_t wb = w_it & 1u;
-                    mbar_wait_t<64>(&win_empty[wb], ((w_it >> 1) & 1u) ^ 1u);
+                    const uint32_t wb = c_win & 1;
+                    mbar_wait_t<64>(&win_empty[wb], ((wb ? used1 : used0) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(&win_full[wb], DS_WIN_TX);
                     tma_load_4d(win_smem + wb * DS_WIN_BYTES, &PP.tmap_x, &win_full[wb], P.x_ch_off + c_win * 64, wx0, wy0, img);
-                    ++w_it; ++c_win;
+                    if (wb) ++used1; else ++used0;
+                    ++c_win;
                 };
                 if (FUSED) {
                     // the first window of the tile does not alias anything: fetch it while phase A runs
@@ -314,6 +322,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
                         tma_load_5d(f_smem + fs * DS_F_STAGE, &PP.tmap_f, &f_full[fs], 0, tx * DC_TILE_W - 1, ty * DC_TILE_H - 1,
                                     (PP.f_ch_off + c * 32) >> 3, img);
                     }
+                    // window buffer 1 held conv_offset weight stages: free once phase A's MMAs have completed
+                    if (nchunks > 1) mbar_wait_t<64>(off_full, tile_it & 1u);
                 }
                 while (c_win < nchunks) issue_window();
             }
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
         struct Raw { float dh, dw, mk; };
         struct Geo { uint32_t a0, a1, a2; __half2 w[4]; int hl, wl; bool slow; };
 
-        uint32_t chunk_ctr = 0, tile_it = 0;
+        uint32_t chunk_ctr = 0, tile_it = 0, used0 = 0, used1 = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             const int pt = tile / P.n_tiles_n, nt = tile % P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
@@ -468,10 +478,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
                 const int ch0 = chunk * 64 + kp * 16;                  // first channel of this warp's K-atom pair
                 const int g0 = ch0 / cpg, g1 = TWO ? g0 + 1 : g0;
                 const bool count_abs = count_tile && (ch0 % cpg) == 0;    // each (pixel, group, tap) offset exactly once
-                const uint32_t wbuf = chunk_ctr & 1u;
+                const uint32_t wbuf = chunk & 1;
                 const uint32_t win = smem_u32(win_smem + wbuf * DS_WIN_BYTES);
                 Raw nx0 = fetch(g0, 0), nx1 = TWO ? fetch(g1, 0) : nx0;
-                mbar_wait_warp(&win_full[wbuf], (chunk_ctr >> 1) & 1u);
+                mbar_wait_warp(&win_full[wbuf], (wbuf ? used1 : used0) & 1u);
+                if (wbuf) ++used1; else ++used0;
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const uint32_t s = tap % 3, ph = (chunk_ctr + tap / 3) & 1u;      // == it % 3, (it / 3) & 1 with it = 9 chunk_ctr + tap

@@ -84,6 +84,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
 }
 // CTA-pair kernel (conv_pair.cuh): [nt][rank 2][chunk of 32 ch][tap][k16 step 2][plane 2][BN/2 rows][8] fp16 - each
 // CTA of a pair keeps its half of the output channels resident, K steps in consumption order.
+__device__ __forceinline__ void bf8_store(__half* p, const H8& r) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf2(r.v[0], r.v[1]), pack_bf2(r.v[2], r.v[3]),
+                                              pack_bf2(r.v[4], r.v[5]), pack_bf2(r.v[6], r.v[7]));
+}
+template <bool BF16>
 __global__ void pack_weight_pair_kernel(const float* __restrict__ w, int cout, int cin, int ktaps,
                                         const int* __restrict__ row_map, int BN, int n_tiles_n,
                                         __half* __restrict__ out) {
@@ -108,7 +113,7 @@ __global__ void pack_weight_pair_kernel(const float* __restrict__ w, int cout, i
             const int ci = chunk * 32 + h * 16 + plane * 8 + e;
             v.v[e] = srow >= 0 ? w[(static_cast<size_t>(srow) * cin + ci) * ktaps + tap] : 0.f;
         }
-        h8_store(out + i * 8, v);
+        if (BF16) bf8_store(out + i * 8, v); else h8_store(out + i * 8, v);
     }
 }
 // Fused DCN site (dcn_site.cuh): conv_offset weights [dg*27][cin][3][3] -> [chunk of 32 ch][tap][k16 2][plane 2][224 rows][8]

@@ -37,6 +37,7 @@ struct EpiParams {
     float* absmean_acc;       // ACT_DCN_PACK: sum |offset| accumulator (optional)
     int f32_blocked;          // res32 / out32 in the tile-blocked layout (blocked32_offset)
     int res16_wide;           // res16 view is 32-byte aligned per 16 channels: 2 x LDG.256 instead of 4 x LDG.128
+    int bf16;                 // operands and the 16-bit output are bf16 (training step); CTA-pair kernel, plain TMA store only
 };
 
 // Tile-blocked fp32 layout: float index of (pixel (img,y,x), channel c) for an [N,H,W,C] tensor, C % 32 == 0.

@@ -25,6 +25,15 @@ def _f32(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
+def _pow2_scale(grad_out):
+    """Power of two s (computed on the device, no host sync) with amax(|grad_out|) * s in [2^9, 2^10): the backward kernels
+    carry grad_out and W^T grad_out as fp16 tensor-core operands, so gradients of a mean-reduced loss (~1e-6 per pixel)
+    would be subnormal or flush to zero un-scaled, and very large ones overflow at 65504.  All results are linear in
+    grad_out, so dividing them by s afterwards is exact."""
+    amax = grad_out.detach().abs().amax().clamp_min(1e-30).float()
+    return torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(2.0 ** -100, 2.0 ** 100)
+
+
 def modulated_deform_conv_forward(input, weight, bias, ones, offset, mask, output, columns, kernel_h, kernel_w,
                                   stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, group, deformable_group,
                                   with_bias):
@@ -68,19 +77,14 @@ def modulated_deform_conv_backward(input, weight, bias, ones, offset, mask, colu
         raise RuntimeError("edvr_b200: anisotropic stride/pad/dilation is not supported")
     N, C, H, W = input.shape
     Cout = weight.shape[0]
-    x, w, off, m, go = _f32(input), _f32(weight), _f32(offset), _f32(mask), _f32(grad_output)
-    f32 = lambda t: t.dtype == torch.float32 and t.is_contiguous()
-    tmp = {}
-
-    def buf(name, t, accumulate=False):
-        if f32(t):
-            return t
-        tmp[name] = (t, t.float().contiguous() if accumulate else torch.empty(t.shape, dtype=torch.float32, device=t.device))
-        return tmp[name][1]
-
-    gx, goff, gm = buf("gx", grad_input), buf("goff", grad_offset), buf("gm", grad_mask)
-    gw = buf("gw", grad_weight, True)
-    gb = buf("gb", grad_bias, True) if with_bias else None
+    x, w, off, m = _f32(input), _f32(weight), _f32(offset), _f32(mask)
+    sc = _pow2_scale(grad_output)
+    go = (grad_output.float() * sc).contiguous()
+    inv = 1.0 / sc
+    new = lambda t: torch.empty(t.shape, dtype=torch.float32, device=t.device)
+    gx, goff, gm = new(grad_input), new(grad_offset), new(grad_mask)
+    gw = torch.zeros(grad_weight.shape, dtype=torch.float32, device=grad_weight.device)
+    gb = torch.zeros(grad_bias.shape, dtype=torch.float32, device=grad_bias.device) if with_bias else None
     need = L.lib().eb_mdcn_backward_workspace(N, C, H, W, Cout, kernel_h, kernel_w, stride_h, pad_h, dilation_h)
     ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
     with torch.cuda.device(input.device):
@@ -88,8 +92,12 @@ def modulated_deform_conv_backward(input, weight, bias, ones, offset, mask, colu
                                          L.ptr(gm), L.ptr(gw), L.ptr(gb), N, C, H, W, Cout, kernel_h, kernel_w,
                                          stride_h, pad_h, dilation_h, group, deformable_group, L.ptr(ws), ws.numel(),
                                          L.stream_ptr()), "eb_mdcn_backward")
-    for dst, src in tmp.values():
-        dst.copy_(src)
+    grad_input.copy_(gx * inv)                  # overwritten, like deform_conv_cuda.cpp:617-657
+    grad_offset.copy_(goff * inv)
+    grad_mask.copy_(gm * inv)
+    grad_weight.add_((gw * inv).to(grad_weight.dtype))        # accumulated into, like deform_conv_cuda.cpp:659-671
+    if with_bias:
+        grad_bias.add_((gb * inv).to(grad_bias.dtype))
 
 
 def _v1_shape_check(input, offset, grad_output, weight, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group,
@@ -190,9 +198,11 @@ def deform_conv_backward_input(input, offset, gradOutput, gradInput, gradOffset,
     if N % im2col_step:
         raise RuntimeError("im2col step must divide batchsize")
     Cout = weight.shape[0]
-    x, w, off, go = _f32(input4), _f32(weight), _f32(offset4), _f32(go4)
-    gx, gx_back = _out_buf(gradInput)
-    goff, goff_back = _out_buf(gradOffset)
+    x, w, off = _f32(input4), _f32(weight), _f32(offset4)
+    sc = _pow2_scale(go4)
+    go = (go4.float() * sc).contiguous()
+    gx = torch.empty(gradInput.shape, dtype=torch.float32, device=gradInput.device)
+    goff = torch.empty(gradOffset.shape, dtype=torch.float32, device=gradOffset.device)
     need = L.lib().eb_dcn1_backward_workspace(N, C, H, W, Cout, kH, kW, dH, dW, padH, padW, dilationH, dilationW)
     ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
     with torch.cuda.device(input.device):
@@ -200,10 +210,8 @@ def deform_conv_backward_input(input, offset, gradOutput, gradInput, gradOffset,
                                                Cout, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group,
                                                deformable_group, L.ptr(ws), ws.numel(), L.stream_ptr()),
                 "eb_dcn1_backward_input")
-    if gx_back:
-        gradInput.copy_(gx)
-    if goff_back:
-        gradOffset.copy_(goff)
+    gradInput.copy_(gx / sc)
+    gradOffset.copy_(goff / sc)
     return 1
 
 
@@ -218,8 +226,10 @@ def deform_conv_backward_parameters(input, offset, gradOutput, gradWeight, colum
     if N % im2col_step:
         raise RuntimeError("im2col step must divide batchsize")
     Cout = gradWeight.shape[0]
-    x, off, go = _f32(input4), _f32(offset4), _f32(go4)
-    gw, gw_back = _out_buf(gradWeight, accumulate=True)
+    x, off = _f32(input4), _f32(offset4)
+    sc = _pow2_scale(go4)
+    go = (go4.float() * sc).contiguous()
+    gw = torch.zeros(gradWeight.shape, dtype=torch.float32, device=gradWeight.device)
     need = L.lib().eb_dcn1_backward_workspace(N, C, H, W, Cout, kH, kW, dH, dW, padH, padW, dilationH, dilationW)
     ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
     with torch.cuda.device(input.device):
@@ -227,6 +237,5 @@ def deform_conv_backward_parameters(input, offset, gradOutput, gradWeight, colum
                                                     Cout, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group,
                                                     deformable_group, L.ptr(ws), ws.numel(), L.stream_ptr()),
                 "eb_dcn1_backward_parameters")
-    if gw_back:
-        gradWeight.copy_(gw)
+    gradWeight.add_((gw / sc).to(gradWeight.dtype))
     return 1

@@ -6,9 +6,10 @@ PredeblurModule, :272-420 EDVR; arch_util.py:51-64 make_layer, :67-95 ResidualBl
 checkpoints load with ``strict=True``.  The modules only OWN parameters; ``forward`` hands them to the
 B200 executor (edvr_b200/engine.py).  Packed weights are cached and re-packed when a parameter changes.
 
-Inference (torch.no_grad) runs entirely on the sm_100a kernels.  With autograd enabled the graph is
-evaluated with differentiable PyTorch ops around the custom DCN autograd Function (edvr_b200/dcn.py) —
-the training configuration (BASELINE cfg 5) is a later row of the scope table.
+Inference (torch.no_grad) runs entirely on the sm_100a kernels through the fused executor.  With autograd enabled
+(training, BASELINE cfg 5) the same graph is built from autograd Functions over the same kernels (edvr_b200/train.py:
+tcgen05 forward / dgrad / wgrad for every convolution, our DCN forward + backward) on NHWC 16-bit activations
+(`train_dtype`, bf16 by default) with fp32 master parameters.  There is no cuDNN / eager-PyTorch convolution on any path.
 """
 import logging
 
@@ -18,6 +19,7 @@ from torch.nn import functional as F
 from torch.nn import init
 
 from . import ops
+from . import train as T
 from .dcn import DCNv2Pack
 from .engine import EDVREngine, _Arena, pack_pcd, pack_tsa, run_pcd, run_tsa
 
@@ -51,6 +53,18 @@ def _wants_autograd(module, x):
     return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters()))
 
 
+TRAIN_DTYPE = torch.bfloat16        # activations / gradients of the training graph (BASELINE cfg 5: bf16); fp16 selectable
+
+
+def _to_nhwc(t):
+    """fp32 NCHW (the reference modules' interface) -> NHWC 16-bit tensor of the training graph."""
+    return t.permute(0, 2, 3, 1).to(TRAIN_DTYPE).contiguous()
+
+
+def _from_nhwc(t, like):
+    return t.permute(0, 3, 1, 2).to(like.dtype).contiguous()
+
+
 def _sd(module, prefix=""):
     return {prefix + k: v for k, v in module.state_dict().items()}
 
@@ -71,7 +85,9 @@ class ResidualBlockNoBN(nn.Module):
     def forward(self, x):
         C = self.conv1.in_channels
         if _wants_autograd(self, x):
-            return x + self.conv2(F.relu(self.conv1(x))) * self.res_scale
+            if self.res_scale != 1:
+                raise ValueError("edvr_b200.ResidualBlockNoBN: res_scale != 1 is not covered")
+            return _from_nhwc(T.resblock(self, _to_nhwc(x)), x)
         if C % 64 or self.res_scale != 1:
             raise ValueError(f"edvr_b200.ResidualBlockNoBN: num_feat={C} (multiple of 64) and res_scale={self.res_scale} (1) "
                              "are outside the tensor-core path; there is no cuDNN fallback")
@@ -113,23 +129,7 @@ class PCDAlignment(nn.Module):
         self._cache = None
 
     def _autograd_forward(self, nbr, ref):
-        lrelu = lambda t: F.leaky_relu(t, 0.1)
-        up_off = up_feat = feat = None
-        for i in (3, 2, 1):
-            L = f"l{i}"
-            off = lrelu(self.offset_conv1[L](torch.cat([nbr[i - 1], ref[i - 1]], 1)))
-            if i == 3:
-                off = lrelu(self.offset_conv2[L](off))
-            else:
-                off = lrelu(self.offset_conv3[L](lrelu(self.offset_conv2[L](torch.cat([off, up_off], 1)))))
-            feat = self.dcn_pack[L](nbr[i - 1], off)
-            if i < 3:
-                feat = self.feat_conv[L](torch.cat([feat, up_feat], 1))
-            if i > 1:
-                feat = lrelu(feat)
-                up_off, up_feat = self.upsample(off) * 2, self.upsample(feat)
-        off = lrelu(self.cas_offset_conv2(lrelu(self.cas_offset_conv1(torch.cat([feat, ref[0]], 1)))))
-        return lrelu(self.cas_dcnpack(feat, off))
+        return _from_nhwc(T.pcd_align(self, [_to_nhwc(t) for t in nbr], [_to_nhwc(t) for t in ref]), nbr[0])
 
     def forward(self, nbr_feat_l, ref_feat_l):
         x0 = nbr_feat_l[0]
@@ -177,22 +177,8 @@ class TSAFusion(nn.Module):
         self._cache = None
 
     def _autograd_forward(self, aligned):
-        lrelu = lambda t: F.leaky_relu(t, 0.1)
-        b, t, c, h, w = aligned.shape
-        emb_ref = self.temporal_attn1(aligned[:, self.center_frame_idx])
-        emb = self.temporal_attn2(aligned.reshape(-1, c, h, w)).view(b, t, -1, h, w)
-        prob = torch.sigmoid((emb * emb_ref.unsqueeze(1)).sum(2, keepdim=True))
-        x = (aligned * prob).reshape(b, t * c, h, w)
-        feat = lrelu(self.feat_fusion(x))
-        attn = lrelu(self.spatial_attn1(x))
-        attn = lrelu(self.spatial_attn2(torch.cat([self.max_pool(attn), self.avg_pool(attn)], 1)))
-        lvl = lrelu(self.spatial_attn_l1(attn))
-        lvl = lrelu(self.spatial_attn_l2(torch.cat([self.max_pool(lvl), self.avg_pool(lvl)], 1)))
-        lvl = self.upsample(lrelu(self.spatial_attn_l3(lvl)))
-        attn = self.upsample(lrelu(self.spatial_attn4(lrelu(self.spatial_attn3(attn)) + lvl)))
-        attn = self.spatial_attn5(attn)
-        add = self.spatial_attn_add2(lrelu(self.spatial_attn_add1(attn)))
-        return feat * torch.sigmoid(attn) * 2 + add
+        a = aligned.permute(0, 1, 3, 4, 2).to(TRAIN_DTYPE).contiguous()          # [b, t, h, w, c]
+        return _from_nhwc(T.tsa_fusion(self, a), aligned)
 
     def forward(self, aligned_feat):
         b, t, c, h, w = aligned_feat.size()
@@ -233,20 +219,9 @@ class PredeblurModule(nn.Module):
         self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
 
     def forward(self, x):
-        lrelu = lambda t: F.leaky_relu(t, 0.1)
-        l1 = lrelu(self.conv_first(x))
-        if self.hr_in:
-            l1 = lrelu(self.stride_conv_hr2(lrelu(self.stride_conv_hr1(l1))))
-        l2 = lrelu(self.stride_conv_l2(l1))
-        l3 = lrelu(self.stride_conv_l3(l2))
-        l3 = self.upsample(self.resblock_l3(l3))
-        l2 = self.upsample(self.resblock_l2_2(self.resblock_l2_1(l2) + l3))
-        for i in range(2):
-            l1 = self.resblock_l1[i](l1)
-        l1 = l1 + l2
-        for i in range(2, 5):
-            l1 = self.resblock_l1[i](l1)
-        return l1
+        if not x.is_cuda:
+            raise NotImplementedError("edvr_b200.PredeblurModule runs on CUDA tensors only")
+        return _from_nhwc(T.predeblur(self, _to_nhwc(x)), x)       # autograd Functions over the tensor-core kernels
 
 
 class EDVR(nn.Module):
@@ -293,29 +268,7 @@ class EDVR(nn.Module):
         return self._engine[1]
 
     def _autograd_forward(self, x):
-        lrelu = lambda t: F.leaky_relu(t, 0.1)
-        b, t, c, h, w = x.size()
-        xc = x[:, self.center_frame_idx].contiguous()
-        if self.with_predeblur:
-            l1 = self.conv_1x1(self.predeblur(x.view(-1, c, h, w)))
-            if self.hr_in:
-                h, w = h // 4, w // 4
-        else:
-            l1 = lrelu(self.conv_first(x.view(-1, c, h, w)))
-        l1 = self.feature_extraction(l1)
-        l2 = lrelu(self.conv_l2_2(lrelu(self.conv_l2_1(l1))))
-        l3 = lrelu(self.conv_l3_2(lrelu(self.conv_l3_1(l2))))
-        l1, l2, l3 = l1.view(b, t, -1, h, w), l2.view(b, t, -1, h // 2, w // 2), l3.view(b, t, -1, h // 4, w // 4)
-        ci = self.center_frame_idx
-        ref = [l1[:, ci], l2[:, ci], l3[:, ci]]
-        aligned = torch.stack([self.pcd_align([l1[:, i], l2[:, i], l3[:, i]], ref) for i in range(t)], 1)
-        feat = self.fusion(aligned if self.with_tsa else aligned.view(b, -1, h, w))
-        out = self.reconstruction(feat)
-        out = lrelu(self.pixel_shuffle(self.upconv1(out)))
-        out = lrelu(self.pixel_shuffle(self.upconv2(out)))
-        out = self.conv_last(lrelu(self.conv_hr(out)))
-        base = xc if self.hr_in else F.interpolate(xc, scale_factor=4, mode="bilinear", align_corners=False)
-        return out + base
+        return T.edvr_forward(self, x.float(), dtype=getattr(self, "train_dtype", TRAIN_DTYPE)).to(x.dtype)
 
     def forward(self, x):
         b, t, c, h, w = x.size()
@@ -374,3 +327,47 @@ def save_network(net, save_path, param_key="params"):
         net = net.module
     sd = {(k[7:] if k.startswith("module.") else k): v.cpu() for k, v in net.state_dict().items()}
     torch.save({param_key: sd} if param_key is not None else sd, save_path)
+
+
+# ---- official-release key map (SURVEY §8 f4 tail) -------------------------------------------------------------------------------
+_OFFICIAL_RULES = (      # (regex on the BasicSR key, replacement) - first match wins; restates the renames of
+    # /root/reference/scripts/model_conversion/convert_models.py:17-103 (EDVR official release -> BasicSR names)
+    (r"^predeblur\.stride_conv_hr1\.", "pre_deblur.conv_first_2."),
+    (r"^predeblur\.stride_conv_hr2\.", "pre_deblur.conv_first_3."),
+    (r"^predeblur\.conv_first\.", "pre_deblur.conv_first_1."),
+    (r"^predeblur\.stride_conv_l([23])\.", r"pre_deblur.deblur_L\1_conv."),
+    (r"^predeblur\.resblock_l3\.", "pre_deblur.RB_L3_1."),
+    (r"^predeblur\.resblock_l2_([12])\.", r"pre_deblur.RB_L2_\1."),
+    (r"^predeblur\.resblock_l1\.(\d+)\.", lambda m: f"pre_deblur.RB_L1_{int(m.group(1)) + 1}."),
+    (r"^conv_l([23])_([12])\.", r"fea_L\1_conv\2."),
+    (r"^pcd_align\.dcn_pack\.l(\d)\.conv_offset\.", r"pcd_align.L\1_dcnpack.conv_offset_mask."),
+    (r"^pcd_align\.dcn_pack\.l(\d)\.", r"pcd_align.L\1_dcnpack."),
+    (r"^pcd_align\.offset_conv(\d)\.l(\d)\.", r"pcd_align.L\2_offset_conv\1."),
+    (r"^pcd_align\.feat_conv\.l(\d)\.", r"pcd_align.L\1_fea_conv."),
+    (r"^pcd_align\.cas_dcnpack\.conv_offset\.", "pcd_align.cas_dcnpack.conv_offset_mask."),
+    (r"^fusion\.temporal_attn1\.", "tsa_fusion.tAtt_2."),
+    (r"^fusion\.temporal_attn2\.", "tsa_fusion.tAtt_1."),
+    (r"^fusion\.feat_fusion\.", "tsa_fusion.fea_fusion."),
+    (r"^fusion\.spatial_attn_add(\d)\.", r"tsa_fusion.sAtt_add_\1."),
+    (r"^fusion\.spatial_attn_l(\d)\.", r"tsa_fusion.sAtt_L\1."),
+    (r"^fusion\.spatial_attn(\d)\.", r"tsa_fusion.sAtt_\1."),
+    (r"^reconstruction\.", "recon_trunk."),
+    (r"^conv_hr\.", "HRconv."),
+    (r"^fusion\.", "tsa_fusion."),
+)
+
+
+def official_key(key):
+    """Name of BasicSR parameter `key` in the original EDVR release's checkpoints."""
+    import re
+    for pat, rep in _OFFICIAL_RULES:
+        new, n = re.subn(pat, rep, key, count=1)
+        if n:
+            return new
+    return key          # conv_first, feature_extraction, cas_offset_conv*, upconv*, conv_last, conv_1x1 keep their names
+
+
+def convert_official_state_dict(official_sd, net):
+    """Official-release EDVR weights -> a state_dict for `net` (ours or the reference's EDVR): what
+    scripts/model_conversion/convert_models.py::convert_edvr does with hard-coded paths."""
+    return {k: official_sd[official_key(k)] for k in net.state_dict()}

@@ -45,7 +45,7 @@ class View:
     __slots__ = ("t", "ch_off", "C")
 
     def __init__(self, t, ch_off=0, C=None):
-        assert t.dtype == torch.float16 and t.dim() == 4 and t.is_contiguous() and t.is_cuda
+        assert t.dtype in (torch.float16, torch.bfloat16) and t.dim() == 4 and t.is_contiguous() and t.is_cuda
         self.t, self.ch_off = t, ch_off
         self.C = t.shape[3] - ch_off if C is None else C
         assert 0 <= ch_off and ch_off + self.C <= t.shape[3]
@@ -162,8 +162,9 @@ class Blocked32:
 
 
 def _epi(pc_bias, act, out16=None, out32=None, res16=None, res32=None, out_nchw=None, nchw_C=0,
-         out_mode=OUT_SAME, absmean=None):
+         out_mode=OUT_SAME, absmean=None, bf16=False):
     e = L.Epilogue()
+    e.bf16 = 1 if bf16 else 0
     e.bias = None if pc_bias is None else pc_bias.data_ptr()
     e.act = act
     if res16 is not None:
@@ -198,7 +199,9 @@ def conv2d(pc, srcs, out16=None, act=ACT_NONE, res16=None, res32=None, out32=Non
         m = (1, 1, 0, 0) if src_maps is None or src_maps[i] is None else src_maps[i]
         arr[i] = _src(v, *m)
     assert sum(v.C for v in srcs) == pc.cin, (sum(v.C for v in srcs), pc.cin)
-    e = _epi(pc.b, act, out16, out32, res16, res32, out_nchw=out_nchw, nchw_C=nchw_C, out_mode=out_mode, absmean=absmean)
+    bf16 = v0.t.dtype == torch.bfloat16
+    e = _epi(pc.b, act, out16, out32, res16, res32, out_nchw=out_nchw, nchw_C=nchw_C, out_mode=out_mode, absmean=absmean,
+             bf16=bf16)
     opix = N * v0.H * v0.W if out_mode != OUT_STRIDE2 else N * ((v0.H + 1) // 2) * ((v0.W + 1) // 2)
     detail = ""
     if PROFILE is not None:

@@ -68,6 +68,8 @@ typedef struct {
     int out_mode;
     float* absmean_acc;       /* optional: sum |offset| (EB_ACT_DCN_PACK), for the >50 warning */
     int f32_blocked;          /* res32/out32 use the tile-blocked private layout of eb_f32_blocked_elems() */
+    int bf16;                 /* 1: inputs, packed weights and out16 are bf16 instead of fp16 (training step; eb_conv2d_pair,
+                                 plain NHWC output only) */
 } eb_epilogue_t;
 
 /* ---- library info ------------------------------------------------------------------- */
@@ -104,6 +106,8 @@ int eb_conv2d_stats(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksi
 int eb_conv2d_pair_supported(int cin, int ksize, int BN, int n_tiles_n);
 int eb_pack_weight_pair(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN, int n_tiles_n,
                         void* wpair, void* stream);
+int eb_pack_weight_pair_ex(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN, int n_tiles_n,
+                           void* wpair, int bf16, void* stream);
 int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpair, int BN,
                    int n_tiles_n, const eb_epilogue_t* epi, void* stream);
 
@@ -117,6 +121,17 @@ size_t eb_f32_blocked_elems(int N, int H, int W, int C);
 int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
                 const void* offpack, int offpack_pix_stride, const void* wpack, int BN, int n_tiles_n,
                 const eb_epilogue_t* epi, void* stream);
+
+/* ---- Training step (BASELINE cfg 5): weight gradient of a dense 3x3 (pad 1, stride 1) or 1x1 convolution,
+ *   grad_weight[co][ci][ky][kx] += scale * sum_{n,y,x} gy[n,y,x,co] * x[n, y+ky-1, x+kx-1, ci]
+ * == the cuDNN wgrad behind autograd of nn.Conv2d in the reference's training loop (basicsr/models/base_model.py:62-69,
+ * options/train/EDVR/train_EDVR_L_x4_SR_REDS.yml).  x, gy: NHWC 16-bit views (fp16, or bf16 with bf16 = 1), Cin % 32 == 0;
+ * grad_weight fp32 [Cout][Cin][k][k] is ACCUMULATED into (zero it for a plain gradient).  The data gradient is
+ * eb_conv2d_pair on weights packed from the transposed, flipped tensor; the bias gradient is a plain reduction. */
+size_t eb_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ksize);
+int eb_conv_wgrad(const void* x, int x_pix_stride, int x_ch_off, const void* gy, int gy_pix_stride, int gy_ch_off, int N,
+                  int H, int W, int Cin, int Cout, int ksize, int bf16, float scale, float* grad_weight, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* ---- One DCNv2Pack site (archs/arch_util.py:243-257) for 3x3 / stride 1 / pad 1 / dilation 1 on NHWC fp16 features:
  * the sampled window of x is staged in shared memory by TMA (dcn_site.cuh).  Two ways to supply the offsets:

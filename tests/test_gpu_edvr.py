@@ -286,12 +286,17 @@ def test_drop_in_modules_state_dict_and_forward():
         net(torch.rand(1, 3, 3, 18, 24).cuda())
 
 
-def test_training_step_gradients_vs_oracle_graph():
-    """BASELINE cfg 5 (reduced): one Charbonnier-loss training step through the drop-in modules with autograd ON.
-    The graph runs differentiable PyTorch ops around OUR DCN forward + backward kernels (edvr_b200.dcn); gradients
-    are compared with the oracle graph differentiated through torchvision's deform_conv2d (fp32, TF32 off).
-    Offsets are kept away from the -1 edge by the random conv_offset init."""
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-2), (torch.bfloat16, 6e-2)], ids=["fp16", "bf16"])
+def test_training_step_gradients_vs_oracle_graph(dtype, tol):
+    """BASELINE cfg 5 (reduced): one Charbonnier-loss training step through the drop-in EDVR module with autograd ON.
+    The graph is edvr_b200/train.py: every convolution forward / dgrad / wgrad on the tcgen05 kernels, DCN forward +
+    backward on ours, NHWC 16-bit activations, fp32 master weights; gradients are compared with the fp32 oracle graph
+    differentiated through torchvision's deform_conv2d (TF32 off).  Bars on rel-L2 of a parameter's gradient: fp16 2e-2
+    (as the round-1 cuDNN-fp32 graph around our fp16-operand DCN), bf16 6e-2 - 8-bit mantissas on every activation AND
+    every back-propagated gradient through ~25 layers; the 1e-3 operator bound does not apply to bf16 training, which the
+    reference (fp32 only, no AMP in its yml) does not offer at all.  No cuDNN convolution runs in this step."""
     from edvr_b200.edvr import EDVR
+    from edvr_b200 import train as T
     from oracle import edvr_ref
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -301,28 +306,29 @@ def test_training_step_gradients_vs_oracle_graph():
     x = torch.rand(2, 3, 3, 16, 16, generator=g).cuda()
     gt = torch.rand(2, 3, 64, 64, generator=g).cuda()
 
-    def charbonnier(p, t):       # losses.py:24-25 with reduction='sum' (train_EDVR_L_x4_SR_REDS.yml:90-93)
-        return torch.sqrt((p - t) ** 2 + 1e-12).sum()
-
     net = EDVR(center_frame_idx=None, **kw).cuda().train()
+    net.train_dtype = dtype
     net.load_state_dict(sd, strict=True)
-    loss = charbonnier(net(x), gt)
+    loss = T.charbonnier_loss(net(x), gt)          # losses.py:24-25 with reduction='sum' (train_EDVR_L_x4_SR_REDS.yml:90-93)
     loss.backward()
 
     ref_params = {k: v.clone().cuda().requires_grad_(True) for k, v in sd.items()}
     with torch.enable_grad():
         out_ref = edvr_ref.edvr_forward.__wrapped__(ref_params, x)      # un-decorated (no_grad) forward
-        loss_ref = charbonnier(out_ref, gt)
+        loss_ref = T.charbonnier_loss(out_ref, gt)
     loss_ref.backward()
-    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 1e-3
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < (1e-3 if dtype == torch.float16 else 5e-3)
     named = dict(net.named_parameters())
+    worst = 0.0
     for key in ("conv_first.weight", "pcd_align.dcn_pack.l1.weight", "pcd_align.dcn_pack.l1.conv_offset.weight",
-                "pcd_align.cas_dcnpack.bias", "fusion.feat_fusion.weight", "reconstruction.1.conv2.weight",
-                "conv_last.weight"):
+                "pcd_align.cas_dcnpack.bias", "fusion.feat_fusion.weight", "fusion.temporal_attn1.weight",
+                "reconstruction.1.conv2.weight", "upconv1.weight", "conv_last.weight", "conv_last.bias"):
         a, b = named[key].grad, ref_params[key].grad
         err = float((a - b).norm() / b.norm().clamp_min(1e-20))
+        worst = max(worst, err)
         print(f"grad {key}: rel-L2 {err:.2e}")
-        assert err < 2e-2, (key, err)
+        assert err < tol, (key, err)
+    print(f"training step {dtype}: loss {loss.item():.4f} vs {loss_ref.item():.4f}, worst sampled grad rel-L2 {worst:.2e}")
 
 
 def test_sliding_window_video_inference_is_bit_identical_to_per_clip():

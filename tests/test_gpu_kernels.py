@@ -326,6 +326,72 @@ def test_mdcn_backward_vs_oracle_and_accumulates(ops):
         assert e[0] < TOL and e[1] < TOL, (name, e)
 
 
+@pytest.mark.parametrize("scale", [1e-6, 1e3])
+def test_mdcn_backward_tiny_and_huge_grad_out(ops, scale):
+    """grad_out far outside the fp16 range of the backward kernels' operands (mean-reduced losses give ~1e-6 per pixel):
+    the power-of-two pre-scaling keeps all five gradients within 1e-3 of the oracle."""
+    from oracle import dcn_oracle
+    from edvr_b200.dcn import mdcn_backward
+    shape = (1, 64, 11, 13, 64, 8)
+    x, off, mask, w, b, go = _dcn_case(*shape, seed=5)
+    go = go * scale
+    ref = dcn_oracle.backward(x.numpy(), off.numpy(), mask.numpy(), w.numpy(), go.numpy(), True, 1, 1, 1, 1, 8)
+    got = mdcn_backward(x.cuda(), off.cuda(), mask.cuda(), w.cuda(), go.cuda(), True, 1, 1, 1, 1, 8)
+    for name, g, r in zip(("gx", "goff", "gmask", "gw", "gb"), got, ref):
+        e = rel_err(g.cpu(), r)
+        assert e[0] < TOL and e[1] < TOL, (name, scale, e)
+
+
+TRAIN_CONV_CASES = [   # name, N, H, W, Cin, Cout, k, stride, act
+    ("3x3_c128", 2, 20, 28, 128, 128, 3, 1, "lrelu"),
+    ("3x3_c256_o128_ragged", 1, 19, 37, 256, 128, 3, 1, "none"),
+    ("3x3_stride2", 2, 24, 32, 64, 64, 3, 2, "lrelu"),
+    ("3x3_first_cin3", 2, 16, 24, 3, 64, 3, 1, "lrelu"),
+    ("3x3_last_cout3", 1, 32, 40, 64, 3, 3, 1, "none"),
+    ("3x3_conv_offset_cout216", 1, 18, 22, 128, 216, 3, 1, "none"),
+    ("1x1_c640_o128", 1, 16, 20, 640, 128, 1, 1, "relu"),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("case", TRAIN_CONV_CASES, ids=[c[0] for c in TRAIN_CONV_CASES])
+def test_training_conv_function_vs_torch_autograd(ops, case, dtype):
+    """The training step's convolution Function (edvr_b200/train.py: tcgen05 forward, dgrad = forward kernel on flipped
+    weights, split-K tcgen05 wgrad) against fp32 autograd of F.conv2d.  Bars: fp16 operands 2e-3, bf16 (8-bit mantissa,
+    the dtype BASELINE cfg 5 names) 1e-2 on max-rel and rel-L2 - operand rounding alone is 2^-9 per bf16 value."""
+    from edvr_b200 import train as T
+    _, N, H, W, cin, cout, k, stride, act = case
+    tol = 2e-3 if dtype == torch.float16 else 1e-2
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(N, cin, H, W, device="cuda", generator=g)
+    m = torch.nn.Conv2d(cin, cout, k, stride, k // 2).cuda()
+    with torch.no_grad():
+        m.weight.copy_(torch.randn(m.weight.shape, device="cuda", generator=g) / (cin * k * k) ** 0.5)
+        m.bias.copy_(torch.randn(cout, device="cuda", generator=g) * 0.1)
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    go = torch.randn(N, cout, Ho, Wo, device="cuda", generator=g)
+    xq = x.to(dtype).float()                                   # the activations the kernel sees
+    a = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "lrelu": ops.ACT_LRELU}[act]
+    f = {"none": lambda t: t, "relu": F.relu, "lrelu": lambda t: F.leaky_relu(t, 0.1)}[act]
+    # reference: fp32 autograd
+    xr = xq.clone().requires_grad_(True)
+    yr = f(F.conv2d(xr, m.weight, m.bias, stride, k // 2))
+    yr.backward(go)
+    gw_ref, gb_ref, gx_ref = m.weight.grad.clone(), m.bias.grad.clone(), xr.grad.clone()
+    m.zero_grad()
+    # ours
+    xo = xq.permute(0, 2, 3, 1).to(dtype).contiguous().requires_grad_(True)
+    yo = T.conv(xo, m, a)
+    assert yo.shape == (N, Ho, Wo, cout) and yo.dtype == dtype
+    yo.backward(go.permute(0, 2, 3, 1).to(dtype).contiguous())
+    for name, got, want in (("y", yo.detach().permute(0, 3, 1, 2).float(), yr.detach()),
+                            ("grad_x", xo.grad.permute(0, 3, 1, 2).float(), gx_ref),
+                            ("grad_weight", m.weight.grad, gw_ref), ("grad_bias", m.bias.grad, gb_ref)):
+        e = rel_err(got.cpu(), want.cpu())
+        assert e[0] < tol * 2 and e[1] < tol, (name, e)        # max-rel on a heavy-tailed gradient: 2 x the L2 bar
+
+
 def test_autograd_function_matches_oracle(ops):
     from oracle import dcn_oracle
     from edvr_b200.dcn import modulated_deform_conv

@@ -687,22 +687,37 @@ int eb_dcn_site(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int
         if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "dcn_site: feature tensor map failed (%d)", static_cast<int>(r));
     }
     const long long tiles = static_cast<long long>(N) * ((H + DC_TILE_H - 1) / DC_TILE_H) * ((W + DC_TILE_W - 1) / DC_TILE_W) * n_tiles_n;
-    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // clusters of two CTAs share one L2 read of every weight stage (811 KB of weights are re-streamed per 128-pixel tile)
+    const char* mc_env = getenv("EDVR_B200_DCN_MC");
+    PP.multicast = (grid >= 2 && !(mc_env && mc_env[0] == '0')) ? 1 : 0;
+    if (PP.multicast) grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(DS_THREADS);
+    cfg.dynamicSmemBytes = DS_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = PP.multicast ? 1 : 0;
+    cudaError_t lerr = cudaSuccess;
     const bool two = P.cpg == 8;       // two deformable groups per 16-channel K-atom pair (EDVR-M: 64 channels, dg 8)
 #define EB_LAUNCH_DS(OFF_, EK_)                                                                        \
     do {                                                                                               \
         if (two) {                                                                                     \
             if (int rc = set_smem(dcn_site_kernel<OFF_, EK_, true>, DS_SMEM_BYTES)) return rc;         \
-            dcn_site_kernel<OFF_, EK_, true><<<grid, DS_THREADS, DS_SMEM_BYTES, st>>>(PP);             \
+            lerr = cudaLaunchKernelEx(&cfg, dcn_site_kernel<OFF_, EK_, true>, PP);                     \
         } else {                                                                                       \
             if (int rc = set_smem(dcn_site_kernel<OFF_, EK_, false>, DS_SMEM_BYTES)) return rc;        \
-            dcn_site_kernel<OFF_, EK_, false><<<grid, DS_THREADS, DS_SMEM_BYTES, st>>>(PP);            \
+            lerr = cudaLaunchKernelEx(&cfg, dcn_site_kernel<OFF_, EK_, false>, PP);                    \
         }                                                                                              \
     } while (0)
     if (fused) { if (nchw) EB_LAUNCH_DS(DS_OFF_TMEM, EK_NCHW); else EB_LAUNCH_DS(DS_OFF_TMEM, EK_PLAIN); }
     else       { if (nchw) EB_LAUNCH_DS(DS_OFF_GLOBAL, EK_NCHW); else EB_LAUNCH_DS(DS_OFF_GLOBAL, EK_PLAIN); }
 #undef EB_LAUNCH_DS
+    if (lerr != cudaSuccess) return fail(EB_ERR_LAUNCH, "dcn_site: %s", cudaGetErrorString(lerr));
     return check_launch("dcn_site");
 }
 

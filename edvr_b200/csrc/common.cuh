@@ -332,6 +332,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+// same copy delivered to the same shared-memory offset of every CTA in `cta_mask` of the cluster; each destination CTA's
+// mbarrier at the offset of `bar` receives the complete_tx (L2 is read once for the whole cluster)
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// tcgen05.commit (cta_group::1) whose arrival is delivered to the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     uint4 r;

@@ -66,6 +66,7 @@ struct DsParams {
     long long off_img_stride, mask_img_stride;     // DS_OFF_GLOBAL: elements between images of d.offset / d.mask
     int mask_logit;            // DS_OFF_GLOBAL: 1 = d.mask holds logits (sigmoid applied here), 0 = probabilities
     float* absmean;            // optional: += sum |offset| over the call (n-tile 0 only), for the ">50" warning
+    int multicast;             // 1: launched as clusters of 2 CTAs that share ONE L2 read of every weight stage (bulk-copy multicast)
     // ---- DS_OFF_TMEM
     CUtensorMap tmap_f;        // offset features as {8, W, H, pix_stride/8, N}, box {8, 10, 18, 4, 1} (K-atom planes)
     int f_ch_off;              // first channel of the offset-feature view
@@ -150,15 +151,26 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
         for (int i = threadIdx.x; i < cout_packed; i += blockDim.x) bias_s[i] = P.epi.bias[i];
     if (FUSED)
         for (int i = threadIdx.x; i < 256; i += blockDim.x) bo_s[i] = i < DS_OFF_N ? PP.bo[i] : 0.f;
+    // Weight multicast (clusters of 2): both CTAs walk the same weight-stage sequence; the leader's producer writes every stage
+    // into BOTH CTAs with one multicast bulk copy, so a stage is re-used only when both CTAs' MMAs have consumed it: every
+    // "stage consumed" / "aliased region free" commit is delivered to both CTAs and those barriers expect two arrivals.
+    const bool mc = PP.multicast != 0;
+    const uint32_t crank = mc ? cluster_ctarank() : 0u;
+    const uint32_t both = mc ? 2u : 1u;
+    // tiles per CTA: in a cluster both CTAs must run the same number of rounds (a CTA without a tile runs a dead one)
+    const int n_iter = mc ? (total_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                          : (total_tiles > static_cast<int>(blockIdx.x)
+                                 ? (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0);
+    auto commit = [&](uint64_t* bar) { if (mc) umma_commit_multicast(bar, 3); else umma_commit(bar); };
     if (threadIdx.x == 0) {
-        for (int i = 0; i < DS_STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); mbar_init(&gathered[i], DS_GATHER_WARPS); }
+        for (int i = 0; i < DS_STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], both); mbar_init(&gathered[i], DS_GATHER_WARPS); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], DS_GATHER_WARPS);
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
         }
         for (int i = 0; i < DS_F_STAGES; ++i) { mbar_init(&f_full[i], 1); mbar_init(&f_empty[i], 1); }
-        for (int i = 0; i < DS_WO_STAGES; ++i) { mbar_init(&wo_full[i], 1); mbar_init(&wo_empty[i], 1); }
-        mbar_init(off_full, 1); mbar_init(off_empty, DS_GATHER_WARPS); mbar_init(ab_free, 1);
+        for (int i = 0; i < DS_WO_STAGES; ++i) { mbar_init(&wo_full[i], 1); mbar_init(&wo_empty[i], both); }
+        mbar_init(off_full, both); mbar_init(off_empty, DS_GATHER_WARPS); mbar_init(ab_free, both);
         fence_barrier_init();
         tma_prefetch_desc(&PP.tmap_x);
         if (FUSED) tma_prefetch_desc(&PP.tmap_f);
@@ -166,16 +178,26 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     tc_fence_before_sync();
     __syncthreads();
+    if (mc) cluster_sync_all();           // both CTAs' barriers exist before any multicast copy or commit targets them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+#define DS_TILE_LOOP(IT_)                                                                                          \
+    for (int IT_ = 0; IT_ < n_iter; ++IT_)
+#define DS_TILE_OF(IT_) (blockIdx.x + (IT_) * gridDim.x < static_cast<unsigned>(total_tiles) ? static_cast<int>(blockIdx.x + (IT_) * gridDim.x) : 0)
+#define DS_LIVE(IT_) (blockIdx.x + (IT_) * gridDim.x < static_cast<unsigned>(total_tiles))
 
     if (warp == 0) {
         // ================= weight producer.  Phase A (fused): conv_offset weight stages, one per (32-channel chunk, tap);
         // phase B: DCN weight stages, one per (64-channel chunk, tap).  Both rings alias the same shared memory, so phase A
         // of a tile starts only when the MMAs of the previous tile's phase B have drained (ab_free).
         if (lane == 0) {
-            uint32_t it = 0, wo_it = 0, tile_it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+            uint32_t it = 0, wo_it = 0;
+            auto copy = [&](void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+                if (!mc) bulk_g2s(dst, src, bytes, bar);
+                else if (crank == 0) bulk_g2s_multicast(dst, src, bytes, bar, 3);      // the peer only arms its barrier
+            };
+            DS_TILE_LOOP(tile_it) {
+                const int tile = DS_TILE_OF(tile_it);
                 if (FUSED) {
                     if (tile_it > 0) mbar_wait_t<64>(ab_free, (tile_it - 1) & 1u);
                     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(PP.wo_pack);
@@ -183,7 +205,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
                         const uint32_t s = wo_it % DS_WO_STAGES, ph = (wo_it / DS_WO_STAGES) & 1u;
                         mbar_wait_t<64>(&wo_empty[s], ph ^ 1u);
                         mbar_arrive_expect_tx(&wo_full[s], DS_WO_STAGE);
-                        bulk_g2s(wo_stage(s), wsrc + static_cast<size_t>(st) * DS_WO_STAGE, DS_WO_STAGE, &wo_full[s]);
+                        copy(wo_stage(s), wsrc + static_cast<size_t>(st) * DS_WO_STAGE, DS_WO_STAGE, &wo_full[s]);
                     }
                     // phase B stages may be refilled once phase A's MMAs have read the aliased bytes
                     mbar_wait_t<64>(off_full, tile_it & 1u);
@@ -194,7 +216,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
                     const uint32_t s = it % DS_STAGES, ph = (it / DS_STAGES) & 1u;
                     mbar_wait_t<64>(&empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&full[s], b_bytes);
-                    bulk_g2s(b_smem + s * DC_B_BYTES, w + static_cast<size_t>(st) * b_bytes, b_bytes, &full[s]);
+                    copy(b_smem + s * DC_B_BYTES, w + static_cast<size_t>(st) * b_bytes, b_bytes, &full[s]);
                 }
             }
         }
@@ -204,8 +226,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
         const uint32_t idesc_off = umma_idesc_f16(128, DS_OFF_N);
         const uint32_t lbo_b = static_cast<uint32_t>(P.BN) * 16u;
         const uint32_t a_hi = umma_desc_hi(128), b_hi = umma_desc_hi(128), f_hi = umma_desc_hi(DS_F_RP_X * 16);
-        uint32_t it = 0, acc_it = 0, f_it = 0, wo_it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+        uint32_t it = 0, f_it = 0, wo_it = 0;
+        DS_TILE_LOOP(acc_it_) {
+            const uint32_t acc_it = acc_it_;
             if (FUSED) {
                 // ---- phase A: D_off[128 px, 224] = halo(feat) x Wo, K = C x 9, into TMEM columns [256, 480)
                 if (acc_it > 0) mbar_wait_t<64>(off_empty, (acc_it - 1) & 1u);       // the gather has read the previous tile's offsets
@@ -227,9 +250,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
                             for (int k16 = 0; k16 < 2; ++k16)
                                 umma_f16_lohi<1>(d_off, f_lo0 + (ki * DS_F_RP_X + kj) + k16 * (2 * DS_F_PLANE / 16), f_hi,
                                                  w_lo0 + k16 * (2 * DS_OFF_N * 16 / 16), b_hi, idesc_off, (c | t | k16) != 0 ? 1u : 0u);
-                            umma_commit(&wo_empty[ws]);
+                            commit(&wo_empty[ws]);
                             if (t == 8) umma_commit(&f_empty[fs]);
-                            if (t == 8 && c == 2 * nchunks - 1) umma_commit(off_full);
+                            if (t == 8 && c == 2 * nchunks - 1) commit(off_full);
                         }
                         __syncwarp();
                     }
@@ -251,8 +274,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
                     for (int k16 = 0; k16 < 4; ++k16)
                         umma_f16_lohi<1>(d, a_lo0 + k16 * (2 * DC_A_LBO / 16), a_hi, b_lo0 + k16 * ((2u * lbo_b) >> 4), b_hi, idesc,
                                          (st | k16) != 0 ? 1u : 0u);
-                    umma_commit(&empty[s]);
-                    if (st == nstages - 1) { umma_commit(&acc_full[ab]); if (FUSED) umma_commit(ab_free); }
+                    commit(&empty[s]);
+                    if (st == nstages - 1) { umma_commit(&acc_full[ab]); if (FUSED) commit(ab_free); }
                 }
                 __syncwarp();
             }
@@ -260,8 +283,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
     } else if (warp < 6) {
         // ================= epilogue: warps 2..5 -> TMEM lane quarters 2,3,0,1
         const int q = warp & 3;
-        uint32_t acc_it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+        DS_TILE_LOOP(acc_it_) {
+            const uint32_t acc_it = acc_it_;
+            const int tile = DS_TILE_OF(acc_it_);
             const int nt = tile % P.n_tiles_n, pt = tile / P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
             const uint32_t ab = acc_it & 1u;
@@ -269,7 +293,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
             tc_fence_after_sync();
             const int y = ty * DC_TILE_H + 4 * q + (lane >> 3);
             const int x = tx * DC_TILE_W + (lane & 7);
-            const bool valid = (y < P.Ho) && (x < P.Wo);
+            const bool valid = DS_LIVE(acc_it_) && (y < P.Ho) && (x < P.Wo);
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 128u;
 #pragma unroll 1
             for (int cc = 0; cc < P.BN; cc += 32) {
@@ -285,7 +309,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
         // ================= forwarder: every gather warp has written stage s -> generic->async proxy fence -> full[s]
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+            DS_TILE_LOOP(k_)
                 for (int st = 0; st < nstages; ++st, ++it) {
                     const uint32_t s = it % DS_STAGES, ph = (it / DS_STAGES) & 1u;
                     mbar_wait_t<64>(&gathered[s], ph);
@@ -297,8 +321,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
         // ================= TMA producer: sampling windows of x (one per tile and 64-channel chunk, two buffers) and, fused,
         // the halo stages of the offset features for phase A
         if (lane == 0) {
-            uint32_t used0 = 0, used1 = 0, f_it = 0, tile_it = 0;  // window buffer = chunk & 1 (buffer 1 doubles as weight staging in phase A)
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+            uint32_t used0 = 0, used1 = 0, f_it = 0;  // window buffer = chunk & 1 (buffer 1 doubles as weight staging in phase A)
+            DS_TILE_LOOP(tile_it) {
+                const int tile = DS_TILE_OF(tile_it);
                 const int pt = tile / P.n_tiles_n;
                 const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
                 const int wx0 = tx * DC_TILE_W - 1 - DS_R, wy0 = ty * DC_TILE_H - 1 - DS_R;
@@ -355,13 +380,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
         struct Raw { float dh, dw, mk; };
         struct Geo { uint32_t a0, a1, a2; __half2 w[4]; int hl, wl; bool slow; };
 
-        uint32_t chunk_ctr = 0, tile_it = 0, used0 = 0, used1 = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+        uint32_t chunk_ctr = 0, used0 = 0, used1 = 0;
+        DS_TILE_LOOP(tile_it) {
+            const int tile = DS_TILE_OF(tile_it);
             const int pt = tile / P.n_tiles_n, nt = tile % P.n_tiles_n;
             const int tx = pt % tiles_x, ty = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
             const __half* const ximg = xview + static_cast<long long>(img) * H * ixrow;
             const int ho = ty * DC_TILE_H + (m >> 3), wo = tx * DC_TILE_W + (m & 7);
-            const bool ok = (ho < Ho) && (wo < Wo);
+            const bool ok = DS_LIVE(tile_it) && (ho < Ho) && (wo < Wo);
             const float hbf = static_cast<float>(ho - 1), wbf = static_cast<float>(wo - 1);
             const int wy0 = ty * DC_TILE_H - 1 - DS_R, wx0 = tx * DC_TILE_W - 1 - DS_R;
             const long long pix = static_cast<long long>(ho) * Wo + wo;
@@ -520,8 +546,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dcn_site_kernel(const __grid_co
         }
     }
 
+#undef DS_TILE_LOOP
+#undef DS_TILE_OF
+#undef DS_LIVE
     tc_fence_before_sync();
     __syncthreads();
+    if (mc) cluster_sync_all();           // nobody leaves while the peer may still multicast into this CTA or signal its barriers
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 

@@ -43,9 +43,10 @@ _SIGS = {
     "eb_conv2d_pair_supported": (c_int, [c_int] * 4),
     "eb_pack_weight_pair": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "eb_pack_weight_pair_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "eb_pack_weight_pair_dgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "eb_conv_wgrad_workspace": (c_size_t, [c_int] * 6),
-    "eb_conv_wgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int] + [c_int] * 7 + [c_float, c_void_p, c_void_p, c_size_t,
-                                                                                           c_void_p]),
+    "eb_conv_wgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int] + [c_int] * 7 + [c_float, c_void_p, c_void_p, c_void_p,
+                                                                                           c_size_t, c_void_p]),
     "eb_conv2d_pair": (c_int, [ctypes.POINTER(Src), c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                ctypes.POINTER(Epilogue), c_void_p]),
     "eb_dcn_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,

@@ -232,6 +232,22 @@ int eb_pack_weight_pair_ex(const float* w, int cout, int cin, int ktaps, const i
     return check_launch("pack_weight_pair");
 }
 
+int eb_pack_weight_pair_dgrad(const float* w, int cout, int cin, int ktaps, int k_channels, int BN, int n_tiles_n, void* wpack,
+                              int bf16, void* stream) {
+    if (!w || !wpack) return fail(EB_ERR_NULLPTR, "pack_weight_pair_dgrad: null pointer");
+    if (k_channels % 64 || k_channels < cout || BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1 || ktaps < 1 || cin < 1 ||
+        BN * n_tiles_n < cin)
+        return fail(EB_ERR_INVALID_SHAPE, "pack_weight_pair_dgrad: cout=%d cin=%d K=%d BN=%d tiles=%d", cout, cin, k_channels, BN, n_tiles_n);
+    const long long groups = static_cast<long long>(n_tiles_n) * BN * (k_channels / 8) * ktaps;
+    if (bf16)
+        pack_weight_pair_dgrad_kernel<true><<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            w, cout, cin, ktaps, k_channels, BN, n_tiles_n, static_cast<__half*>(wpack));
+    else
+        pack_weight_pair_dgrad_kernel<false><<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            w, cout, cin, ktaps, k_channels, BN, n_tiles_n, static_cast<__half*>(wpack));
+    return check_launch("pack_weight_pair_dgrad");
+}
+
 int eb_conv2d_pair_supported(int cin, int ksize, int BN, int n_tiles_n) {
     if (cin < 64 || cin % 64 || (ksize != 3 && ksize != 1) || BN % 32 || BN < 32 || BN > 128 || n_tiles_n < 1) return 0;
     if (n_tiles_n > num_sms() / 2 || tensor_map_encoder() == nullptr) return 0;
@@ -551,7 +567,7 @@ int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int
 
 // ---- training step: weight gradient of a dense 3x3 (pad 1) / 1x1 convolution (conv_train.cuh)
 namespace {
-struct WgradGeo { int Hp, Wp, margin; long long body, Ppad; size_t rowsA, a_bytes, b_bytes; int copies; };
+struct WgradGeo { int Hp, Wp, margin, BN, splits, steps_per_split; long long body, Ppad, k_steps; size_t rowsA, a_bytes, b_bytes, p_bytes; int copies; };
 WgradGeo wgrad_geo(int N, int H, int W, int Cin, int Cout, int ksize) {
     WgradGeo g;
     g.Hp = H + 2; g.Wp = (W + 2 + 7) / 8 * 8;
@@ -562,58 +578,75 @@ WgradGeo wgrad_geo(int N, int H, int W, int Cin, int Cout, int ksize) {
     g.copies = ksize == 3 ? 3 : 1;
     g.a_bytes = (g.rowsA * g.Ppad * 2 + 255) / 256 * 256;
     g.b_bytes = (static_cast<size_t>(g.copies) * Cin * g.Ppad * 2 + 255) / 256 * 256;
+    g.BN = Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 0));
+    g.k_steps = g.body / 64;
+    const int tiles = g.BN ? ksize * ksize * (Cin / g.BN) * static_cast<int>(g.rowsA / 128) : 1;
+    long long splits = (2LL * 148 + tiles - 1) / tiles;          // ~2 CTAs per SM; at least 8 K steps per split
+    if (splits > g.k_steps / 8) splits = g.k_steps / 8;
+    if (splits < 1) splits = 1;
+    g.steps_per_split = static_cast<int>((g.k_steps + splits - 1) / splits);
+    g.splits = static_cast<int>((g.k_steps + g.steps_per_split - 1) / g.steps_per_split);
+    g.p_bytes = (static_cast<size_t>(g.splits) * ksize * ksize * Cin * g.rowsA * 4 + 255) / 256 * 256;
     return g;
 }
 }  // namespace
 
 size_t eb_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ksize) {
     const WgradGeo g = wgrad_geo(N, H, W, Cin, Cout, ksize);
-    return g.a_bytes + g.b_bytes;
+    return g.a_bytes + g.b_bytes + g.p_bytes;
 }
 
 int eb_conv_wgrad(const void* x, int x_pix_stride, int x_ch_off, const void* gy, int gy_pix_stride, int gy_ch_off, int N,
-                  int H, int W, int Cin, int Cout, int ksize, int bf16, float scale, float* grad_weight, void* workspace,
-                  size_t workspace_bytes, void* stream) {
+                  int H, int W, int Cin, int Cout, int ksize, int bf16, float scale, float* grad_weight, float* grad_bias,
+                  void* workspace, size_t workspace_bytes, void* stream) {
     if (!x || !gy || !grad_weight) return fail(EB_ERR_NULLPTR, "conv_wgrad: null pointer");
     if (N < 1 || H < 1 || W < 1 || Cout < 1 || Cin < 32 || (ksize != 1 && ksize != 3))
         return fail(EB_ERR_INVALID_SHAPE, "conv_wgrad: N=%d H=%d W=%d Cin=%d Cout=%d k=%d", N, H, W, Cin, Cout, ksize);
-    const int BN = Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 0));
+    const WgradGeo g = wgrad_geo(N, H, W, Cin, Cout, ksize);
+    const int BN = g.BN;
     if (!BN) return fail(EB_ERR_UNSUPPORTED, "conv_wgrad: Cin=%d must be a multiple of 32", Cin);
     if (x_pix_stride < x_ch_off + Cin || gy_pix_stride < gy_ch_off + Cout) return fail(EB_ERR_INVALID_SHAPE, "conv_wgrad: views");
-    const WgradGeo g = wgrad_geo(N, H, W, Cin, Cout, ksize);
-    if (!workspace || workspace_bytes < g.a_bytes + g.b_bytes) return fail(EB_ERR_WORKSPACE, "conv_wgrad: workspace %zu < %zu", workspace_bytes, g.a_bytes + g.b_bytes);
+    const size_t need = g.a_bytes + g.b_bytes + g.p_bytes;
+    if (!workspace || workspace_bytes < need) return fail(EB_ERR_WORKSPACE, "conv_wgrad: workspace %zu < %zu", workspace_bytes, need);
     if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "conv_wgrad: workspace must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint16_t* gyT = static_cast<uint16_t*>(workspace);
     uint16_t* xT = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(workspace) + g.a_bytes);
+    float* partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + g.a_bytes + g.b_bytes);
     if (cudaMemsetAsync(workspace, 0, g.a_bytes + g.b_bytes, st) != cudaSuccess) return fail(EB_ERR_LAUNCH, "conv_wgrad: memset");
     const long long copy_stride = static_cast<long long>(Cin) * g.Ppad;
     {
         dim3 block(32, 8);
-        dim3 grid_g((W + 31) / 32, H, N * ((Cout + 31) / 32));
-        nhwc_to_cmajor_pad_kernel<<<grid_g, block, 0, st>>>(static_cast<const uint16_t*>(gy), gy_pix_stride, gy_ch_off, Cout, H, W,
-                                                            gyT, 0, g.Ppad, g.Hp, g.Wp, g.margin, 1);
-        dim3 grid_x((W + 31) / 32, H, N * ((Cin + 31) / 32));
-        nhwc_to_cmajor_pad_kernel<<<grid_x, block, 0, st>>>(static_cast<const uint16_t*>(x), x_pix_stride, x_ch_off, Cin, H, W,
-                                                            xT, copy_stride, g.Ppad, g.Hp, g.Wp, g.margin, g.copies);
+        const unsigned gy_rows = static_cast<unsigned>((H + CT_ROWS - 1) / CT_ROWS);
+        dim3 grid_g((W + 31) / 32, gy_rows, N * ((Cout + 31) / 32));
+        dim3 grid_x((W + 31) / 32, gy_rows, N * ((Cin + 31) / 32));
+        if (bf16) {
+            nhwc_to_cmajor_pad_kernel<true><<<grid_g, block, 0, st>>>(static_cast<const uint16_t*>(gy), gy_pix_stride, gy_ch_off, Cout,
+                                                                      H, W, gyT, 0, g.Ppad, g.Hp, g.Wp, g.margin, 1, grad_bias);
+            nhwc_to_cmajor_pad_kernel<true><<<grid_x, block, 0, st>>>(static_cast<const uint16_t*>(x), x_pix_stride, x_ch_off, Cin, H,
+                                                                      W, xT, copy_stride, g.Ppad, g.Hp, g.Wp, g.margin, g.copies, nullptr);
+        } else {
+            nhwc_to_cmajor_pad_kernel<false><<<grid_g, block, 0, st>>>(static_cast<const uint16_t*>(gy), gy_pix_stride, gy_ch_off, Cout,
+                                                                       H, W, gyT, 0, g.Ppad, g.Hp, g.Wp, g.margin, 1, grad_bias);
+            nhwc_to_cmajor_pad_kernel<false><<<grid_x, block, 0, st>>>(static_cast<const uint16_t*>(x), x_pix_stride, x_ch_off, Cin, H,
+                                                                       W, xT, copy_stride, g.Ppad, g.Hp, g.Wp, g.margin, g.copies, nullptr);
+        }
         if (int rc = check_launch("conv_wgrad transposes")) return rc;
     }
     const int taps = ksize * ksize;
-    const long long k_steps = g.body / 64;
-    const int tiles = taps * (Cin / BN) * static_cast<int>(g.rowsA / 128);
-    long long splits = (2LL * num_sms() + tiles - 1) / tiles;
-    if (splits > k_steps) splits = k_steps;
-    if (splits < 1) splits = 1;
-    const int steps_per_split = static_cast<int>((k_steps + splits - 1) / splits);
-    splits = (k_steps + steps_per_split - 1) / steps_per_split;
     if (int rc = set_smem(conv_wgrad_kernel, CW_SMEM_BYTES)) return rc;
-    dim3 grid(taps * (Cin / BN), static_cast<unsigned>(g.rowsA / 128), static_cast<unsigned>(splits));
+    const unsigned m_tiles = static_cast<unsigned>(g.rowsA / 128);
+    dim3 grid(taps * (Cin / BN), m_tiles, static_cast<unsigned>(g.splits));
     // 1x1: the single unshifted copy sits at copy index 0, the kernel addresses copy (dxi = 1) -> pass a base one copy earlier
     const __half* Bbase = reinterpret_cast<const __half*>(xT) - (ksize == 1 ? copy_stride : 0);
-    conv_wgrad_kernel<<<grid, 128, CW_SMEM_BYTES, st>>>(reinterpret_cast<const __half*>(gyT), Bbase, copy_stride, grad_weight,
-                                                        Cout, Cin, taps, g.Ppad, g.Wp, BN, steps_per_split, g.margin, k_steps,
-                                                        bf16 ? 1 : 0, scale);
-    return check_launch("conv_wgrad");
+    conv_wgrad_kernel<<<grid, 128, CW_SMEM_BYTES, st>>>(reinterpret_cast<const __half*>(gyT), Bbase, copy_stride, partial,
+                                                        Cout, Cin, taps, g.Ppad, g.Wp, BN, g.steps_per_split, g.margin, g.k_steps,
+                                                        bf16 ? 1 : 0);
+    if (int rc = check_launch("conv_wgrad")) return rc;
+    const long long total = static_cast<long long>(taps) * Cout * Cin;
+    conv_wgrad_reduce_kernel<<<grid_1d(total, 256), 256, 0, st>>>(partial, grad_weight, Cout, Cin, taps, BN, static_cast<int>(m_tiles),
+                                                                   g.splits, scale);
+    return check_launch("conv_wgrad_reduce");
 }
 
 // ---- DCN site kernel (dcn_site.cuh): windows of x staged in shared memory; conv_offset optionally fused in front

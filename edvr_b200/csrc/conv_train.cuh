@@ -21,32 +21,54 @@ namespace eb {
 
 // src: NHWC 2-byte elements (view: pix_stride, ch_off, C channels) -> dst[dx][c][p] for dx in [0, ncopies): ncopies == 3
 // writes the three shifted copies (dst copy i holds xpad shifted by dx = i - 1), ncopies == 1 the unshifted one.
-// grid: (ceil(W/32), H, N * ceil(C/32)), block (32, 8); dst must be zero-filled (borders, padding columns, margins).
+// grid: (ceil(W/32), ceil(H/CT_ROWS), N * ceil(C/32)), block (32, 8); dst must be zero-filled (borders, padding, margins).
+// colsum (optional, fp32 [C]): += sum over all pixels of src[.., c] - the bias gradient when src is grad_out, taken while
+// the tile is in flight (a separate ATen reduction over NHWC bf16 cost 37 us per layer, 11 % of the training step).
+constexpr int CT_ROWS = 8;
+template <bool BF16>
 __global__ void nhwc_to_cmajor_pad_kernel(const uint16_t* __restrict__ src, int pix_stride, int ch_off, int C, int H, int W,
                                           uint16_t* __restrict__ dst, long long copy_stride, long long Ppad, int Hp, int Wp,
-                                          int margin, int ncopies) {
+                                          int margin, int ncopies, float* __restrict__ colsum) {
     __shared__ uint16_t tile[32][34];
+    __shared__ float red[8][33];
     const int cblocks = (C + 31) / 32;
     const int n = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 32;
-    const int y = blockIdx.y, x0 = blockIdx.x * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {                    // i: pixel within the tile, threadIdx.x: channel
-        const int x = x0 + i, c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (x < W && c < C)
-            ? src[((static_cast<size_t>(n) * H + y) * W + x) * pix_stride + ch_off + c] : static_cast<uint16_t>(0);
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {                    // i: channel, threadIdx.x: pixel
-        const int c = c0 + i, x = x0 + threadIdx.x;
-        if (c < C && x < W) {
-            const long long p = margin + (static_cast<long long>(n) * Hp + y + 1) * Wp + x + 1;
-            const uint16_t v = tile[threadIdx.x][i];
-            if (ncopies == 1) {
-                dst[static_cast<size_t>(c) * Ppad + p] = v;
-            } else {
+    const int x0 = blockIdx.x * 32;
+    float acc = 0.f;
+    for (int y = blockIdx.y * CT_ROWS; y < H && y < (blockIdx.y + 1) * CT_ROWS; ++y) {
+        for (int i = threadIdx.y; i < 32; i += 8) {                    // i: pixel within the tile, threadIdx.x: channel
+            const int x = x0 + i, c = c0 + threadIdx.x;
+            const uint16_t v = (x < W && c < C)
+                ? src[((static_cast<size_t>(n) * H + y) * W + x) * pix_stride + ch_off + c] : static_cast<uint16_t>(0);
+            tile[i][threadIdx.x] = v;
+            if (colsum != nullptr)
+                acc += BF16 ? __uint_as_float(static_cast<uint32_t>(v) << 16) : __half2float(__ushort_as_half(v));
+        }
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += 8) {                    // i: channel, threadIdx.x: pixel
+            const int c = c0 + i, x = x0 + threadIdx.x;
+            if (c < C && x < W) {
+                const long long p = margin + (static_cast<long long>(n) * Hp + y + 1) * Wp + x + 1;
+                const uint16_t v = tile[threadIdx.x][i];
+                if (ncopies == 1) {
+                    dst[static_cast<size_t>(c) * Ppad + p] = v;
+                } else {
 #pragma unroll
-                for (int d = 0; d < 3; ++d)         // copy d holds xpad[p + (d - 1)]  =>  x lands at p - (d - 1)
-                    dst[d * copy_stride + static_cast<size_t>(c) * Ppad + p - (d - 1)] = v;
+                    for (int d = 0; d < 3; ++d)         // copy d holds xpad[p + (d - 1)]  =>  x lands at p - (d - 1)
+                        dst[d * copy_stride + static_cast<size_t>(c) * Ppad + p - (d - 1)] = v;
+                }
             }
+        }
+        __syncthreads();
+    }
+    if (colsum != nullptr) {
+        red[threadIdx.y][threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.y == 0 && c0 + threadIdx.x < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+            atomicAdd(colsum + c0 + threadIdx.x, s);
         }
     }
 }
@@ -54,12 +76,15 @@ __global__ void nhwc_to_cmajor_pad_kernel(const uint16_t* __restrict__ src, int 
 constexpr int CW_STAGES = 3;
 constexpr int CW_SMEM_BYTES = CW_STAGES * (128 * 128 + 128 * 128);
 
-// gW[co][ci][tap] += scale * sum_p A[co][p] * B_tap[ci][p]; A = gyT (rows padded to a multiple of 128), B_tap = xT_dx(tap)
-// at row offset dy(tap) * Wp.  grid: (taps * (Cin / BN), ceil(Cout / 128), splits), 128 threads.
+// partial[split][tile][co 128][ci BN] = sum over this split's pixels of A[co][p] * B_tap[ci][p]; A = gyT (rows padded to a
+// multiple of 128), B_tap = xT_dx(tap) at row offset dy(tap) * Wp.  grid: (taps * (Cin / BN), ceil(Cout / 128), splits),
+// 128 threads.  Split-K partial tiles go to a workspace and are summed by conv_wgrad_reduce_kernel in a fixed order:
+// deterministic, and 30x fewer memory operations than fp32 atomics on [co][ci][tap] (4.7 M atomics per layer made this
+// kernel 37 % of the first training step profile, profiles/r02_train_profile_v1.txt).
 __global__ void __launch_bounds__(128, 1)
-conv_wgrad_kernel(const __half* __restrict__ A, const __half* __restrict__ B, long long b_copy_stride, float* __restrict__ gW,
+conv_wgrad_kernel(const __half* __restrict__ A, const __half* __restrict__ B, long long b_copy_stride, float* __restrict__ partial,
                   int Cout, int Cin, int taps, long long Ppad, int Wp, int BN, int steps_per_split, long long k_begin,
-                  long long k_steps, int ab_fmt, float scale) {
+                  long long k_steps, int ab_fmt) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t stage_free[CW_STAGES];
     __shared__ uint64_t done_bar;
@@ -120,23 +145,48 @@ conv_wgrad_kernel(const __half* __restrict__ A, const __half* __restrict__ B, lo
         }
     }
     if (tid == 0) umma_commit(&done_bar);
-    if (nsteps > 0) {
-        mbar_wait(&done_bar, 0);
-        tc_fence_after_sync();
-        const int co = mt * 128 + tid;
+    {
+        // this CTA's tile of the partial sums: [co = tid][BN] contiguous floats (zeros when the split got no K steps)
+        float* out = partial + ((static_cast<size_t>(blockIdx.z) * gridDim.y + mt) * gridDim.x + blockIdx.x) * (128 * static_cast<size_t>(BN)) +
+                     static_cast<size_t>(tid) * BN;
+        if (nsteps > 0) {
+            mbar_wait(&done_bar, 0);
+            tc_fence_after_sync();
+        }
         for (int cc = 0; cc < BN; cc += 32) {
             float v[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + cc, v);
-            if (co < Cout) {
+            if (nsteps > 0) tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + cc, v);
+            else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    atomicAdd(gW + (static_cast<size_t>(co) * Cin + c0 + cc + j) * taps + tap, v[j] * scale);
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
     }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// grad_weight[co][ci][tap] += scale * sum_split partial[split][mt][tile = tap * (Cin / BN) + ci / BN][co % 128][ci % BN]
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gW, int Cout, int Cin, int taps,
+                                         int BN, int m_tiles, int splits, float scale) {
+    const int ntc = Cin / BN, tiles = taps * ntc;
+    const long long total = static_cast<long long>(taps) * Cout * Cin;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = i % Cin;
+        const int co = (i / Cin) % Cout;
+        const int tap = i / (static_cast<long long>(Cin) * Cout);
+        const int mt = co / 128, tile = tap * ntc + ci / BN;
+        const float* src = partial + (static_cast<size_t>(mt) * tiles + tile) * (128 * static_cast<size_t>(BN)) +
+                           static_cast<size_t>(co % 128) * BN + ci % BN;
+        const size_t split_stride = static_cast<size_t>(m_tiles) * tiles * 128 * BN;
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += src[k * split_stride];
+        gW[(static_cast<size_t>(co) * Cin + ci) * taps + tap] += s * scale;
+    }
 }
 
 }  // namespace eb

@@ -146,6 +146,35 @@ __global__ void pack_offset_weight_kernel(const float* __restrict__ w, const flo
         if (i < rows) b_out[i] = (b != nullptr && srow >= 0) ? b[srow] : 0.f;      // i == row for chunk 0, tap 0, plane 0
     }
 }
+// Training step, data gradient: dgrad of a stride-1 convolution with weights w[co][ci][tap] is the convolution of grad_out
+// with W'[ci][co][taps-1-tap] (transposed, spatially flipped).  This packs W' straight from w in the CTA-pair layout
+// ([nt][rank 2][chunk of 32 grad_out channels][tap][k16 2][plane 2][BN/2 rows = input channels][8]); grad_out channels beyond
+// `cout` and rows beyond `cin` are zero.
+template <bool BF16>
+__global__ void pack_weight_pair_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int ktaps, int k_channels,
+                                              int BN, int n_tiles_n, __half* __restrict__ out) {
+    const int nchunks = k_channels / 32, half = BN / 2;
+    const long long total = static_cast<long long>(n_tiles_n) * 2 * nchunks * ktaps * 4 * half;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int row = r % half; r /= half;
+        const int plane = r % 2; r /= 2;
+        const int h = r % 2; r /= 2;
+        const int tap = r % ktaps; r /= ktaps;
+        const int chunk = r % nchunks; r /= nchunks;
+        const int rank = r % 2; r /= 2;
+        const int nt = static_cast<int>(r);
+        const int ci = nt * BN + rank * half + row;                 // output row of the dgrad conv = input channel of w
+        H8 v;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int co = chunk * 32 + h * 16 + plane * 8 + e;     // K index of the dgrad conv = output channel of w
+            v.v[e] = (ci < cin && co < cout) ? w[(static_cast<size_t>(co) * cin + ci) * ktaps + (ktaps - 1 - tap)] : 0.f;
+        }
+        if (BF16) bf8_store(out + i * 8, v); else h8_store(out + i * 8, v);
+    }
+}
 __global__ void pack_bias_kernel(const float* __restrict__ b, int cout, const int* __restrict__ row_map,
                                  int n_packed, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -38,27 +38,39 @@ def _workspace(nbytes, device):
     return t
 
 
-def _pack_pair(weight, bias, bf16):
-    """fp32 [Cout, Cin, k, k] (Cin % 64 == 0) -> PackedConv for the CTA-pair kernel only (no single-CTA copy)."""
-    weight = weight.detach().float().contiguous()
+def _pack_pair(weight, bias, bf16, dgrad_k=0):
+    """fp32 master weights [Cout, Cin, k, k] -> PackedConv for the CTA-pair kernel only (no single-CTA copy).
+    dgrad_k == 0: the forward convolution (Cin % 64 == 0).  dgrad_k > 0: the DATA-GRADIENT convolution, i.e. weights
+    W'[ci][co][flipped tap] with `dgrad_k` (>= Cout, multiple of 64) grad_out channels, packed straight from `weight`."""
+    weight = weight.detach()
+    if weight.dtype != torch.float32 or not weight.is_contiguous():
+        weight = weight.float().contiguous()
     cout, cin, k, _ = weight.shape
-    cp = ((cout + 31) // 32) * 32
+    rows, kch = (cout, cin) if not dgrad_k else (cin, dgrad_k)
+    cp = ((rows + 31) // 32) * 32
     pc = PackedConv()
     pc.BN = ops._choose_bn(cp)
     pc.n_tiles = cp // pc.BN
-    pc.cin, pc.ksize, pc.cout, pc.cin_real = cin, k, cout, cin
-    if not L.lib().eb_conv2d_pair_supported(cin, k, pc.BN, pc.n_tiles):
-        raise ValueError(f"conv {cin}->{cout} k{k}: outside the CTA-pair kernel (Cin % 64 == 0, k in (1, 3))")
-    nbytes = L.lib().eb_packed_weight_bytes(cin, k * k, pc.BN, pc.n_tiles)
+    pc.cin, pc.ksize, pc.cout, pc.cin_real = kch, k, rows, kch
+    if not L.lib().eb_conv2d_pair_supported(kch, k, pc.BN, pc.n_tiles):
+        raise ValueError(f"conv {kch}->{rows} k{k}: outside the CTA-pair kernel (Cin % 64 == 0, k in (1, 3))")
+    nbytes = L.lib().eb_packed_weight_bytes(kch, k * k, pc.BN, pc.n_tiles)
     pc.w = None
     pc.wpair = torch.empty(nbytes // 2, dtype=torch.float16, device=weight.device)      # raw 16-bit storage
     with ops._Rec("pack_weight", 1):
-        L.check(L.lib().eb_pack_weight_pair_ex(L.ptr(weight), cout, cin, k * k, None, pc.BN, pc.n_tiles, L.ptr(pc.wpair),
-                                               1 if bf16 else 0, L.stream_ptr()), "eb_pack_weight_pair_ex")
-    b = torch.zeros(cp, dtype=torch.float32, device=weight.device)
-    if bias is not None:
-        b[:cout] = bias.detach().float()
-    pc.b = b
+        if dgrad_k:
+            L.check(L.lib().eb_pack_weight_pair_dgrad(L.ptr(weight), cout, cin, k * k, kch, pc.BN, pc.n_tiles, L.ptr(pc.wpair),
+                                                      1 if bf16 else 0, L.stream_ptr()), "eb_pack_weight_pair_dgrad")
+        else:
+            L.check(L.lib().eb_pack_weight_pair_ex(L.ptr(weight), cout, cin, k * k, None, pc.BN, pc.n_tiles, L.ptr(pc.wpair),
+                                                   1 if bf16 else 0, L.stream_ptr()), "eb_pack_weight_pair_ex")
+    if bias is not None and cp == rows and bias.dtype == torch.float32 and bias.is_contiguous():
+        pc.b = bias.detach()
+    elif bias is not None:
+        pc.b = torch.zeros(cp, dtype=torch.float32, device=weight.device)
+        pc.b[:rows] = bias.detach().float()
+    else:
+        pc.b = None
     return pc
 
 
@@ -73,10 +85,11 @@ def _pad_channels(t, mult=64):
     return out
 
 
-def _run_conv(x, weight, bias, act):
-    """y = act(conv(x) + bias); x NHWC 16-bit contiguous with Cin % 64 == 0 -> y NHWC [N,H,W,Cout] (same dtype)."""
+def _run_conv(x, weight, bias, act, dgrad=False):
+    """y = act(conv(x) + bias); x NHWC 16-bit contiguous with C % 64 == 0 -> y NHWC (same dtype).  dgrad: x is grad_out
+    (channels padded to 64) and the result is the gradient w.r.t. the convolution's input, [N,H,W,Cin]."""
     bf16 = x.dtype == torch.bfloat16
-    pc = _pack_pair(weight, bias, bf16)
+    pc = _pack_pair(weight, bias, bf16, dgrad_k=x.shape[3] if dgrad else 0)
     N, H, W, _ = x.shape
     cp = pc.BN * pc.n_tiles
     y = torch.empty(N, H, W, cp, dtype=x.dtype, device=x.device)
@@ -108,9 +121,9 @@ class _ConvFn(Function):
         bf16 = xp.dtype == torch.bfloat16
         gy = gy.contiguous()
         if act == ACT_RELU:
-            gy = gy * (y > 0).to(gy.dtype)
+            gy = torch.ops.aten.threshold_backward(gy, y, 0)                  # one elementwise pass on the saved output
         elif act == ACT_LRELU:
-            gy = gy * torch.where(y > 0, 1.0, 0.1).to(gy.dtype)
+            gy = torch.ops.aten.leaky_relu_backward(gy, y, 0.1, True)
         N, H, W, cin = xp.shape
         cout, _, k, _ = weight.shape
         if stride == 2:                                # zero-stuff to the stride-1 grid
@@ -121,24 +134,22 @@ class _ConvFn(Function):
         with torch.cuda.device(xp.device):
             if ctx.needs_input_grad[0]:
                 # dgrad: conv of grad_out with W'[ci][co][ky][kx] = W[co][ci][2-ky][2-kx]; grad_out channels padded to 64
-                gyp = _pad_channels(gy)
-                wt = weight.detach().transpose(0, 1).flip(2, 3)
-                if gyp.shape[3] != cout:
-                    wt = F.pad(wt, (0, 0, 0, 0, 0, gyp.shape[3] - cout))
-                gx = _run_conv(gyp, wt.contiguous(), None, ACT_NONE)
-                if gx.shape[3] != cin_real:
-                    gx = gx[..., :cin_real].contiguous()
+                gx = _run_conv(_pad_channels(gy), weight, None, ACT_NONE, dgrad=True)      # [N,H,W,cin_real]
             if ctx.needs_input_grad[1]:
-                gwp = torch.zeros(cout, cin, k, k, dtype=torch.float32, device=xp.device)
+                want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+                # one zero-filled fp32 buffer for grad_weight (+ grad_bias): the kernels accumulate into it
+                buf = torch.zeros(cout * cin * k * k + (cout if want_gb else 0), dtype=torch.float32, device=xp.device)
+                gwp = buf[:cout * cin * k * k].view(cout, cin, k, k)
+                gb = buf[cout * cin * k * k:] if want_gb else None
                 need = L.lib().eb_conv_wgrad_workspace(N, H, W, cin, cout, k)
                 ws = _workspace(need, xp.device)
-                with ops._Rec("conv_wgrad", 3, 2.0 * N * H * W * cout * cin * k * k):
+                with ops._Rec("conv_wgrad", 4, 2.0 * N * H * W * cout * cin * k * k):
                     L.check(L.lib().eb_conv_wgrad(L.ptr(xp), cin, 0, L.ptr(gy), cout, 0, N, H, W, cin, cout, k,
-                                                  1 if bf16 else 0, 1.0, L.ptr(gwp), L.ptr(ws), ws.numel(), L.stream_ptr()),
-                            "eb_conv_wgrad")
+                                                  1 if bf16 else 0, 1.0, L.ptr(gwp), L.ptr(gb), L.ptr(ws), ws.numel(),
+                                                  L.stream_ptr()), "eb_conv_wgrad")
                 gw = gwp if cin == cin_real else gwp[:, :cin_real].contiguous()
-            if ctx.has_bias and ctx.needs_input_grad[2]:
-                gb = gy.float().sum((0, 1, 2))
+            elif ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = gy.sum((0, 1, 2), dtype=torch.float32)
         return gx, gw, gb, None, None
 
 
@@ -167,9 +178,12 @@ def dcn_pack(m, x, feat):
     o1, o2, mask = torch.chunk(out, 3, dim=1)
     offset = torch.cat((o1, o2), dim=1)
     mask = torch.sigmoid(mask)
-    offset_absmean = torch.mean(torch.abs(offset.detach()))
-    if offset_absmean > 50:                       # the reference's immediate check (training-divergence signal)
-        logging.getLogger("basicsr").warning(f"Offset abs mean is {offset_absmean}, larger than 50.")
+    if not torch.cuda.is_current_stream_capturing():
+        # the reference's immediate check (arch_util.py:249-253, the training-divergence signal); it is a device->host sync,
+        # so it is left out of a CUDA-graph capture of the step (GraphedTrainStep) - replay cannot branch on the host
+        offset_absmean = torch.mean(torch.abs(offset.detach()))
+        if offset_absmean > 50:
+            logging.getLogger("basicsr").warning(f"Offset abs mean is {offset_absmean}, larger than 50.")
     y = modulated_deform_conv(_nchw(x).float().contiguous(), offset.contiguous(), mask.contiguous(), m.weight, m.bias,
                               m.stride, m.padding, m.dilation, m.groups, m.deformable_groups)
     return _nhwc(y.to(x.dtype))
@@ -259,9 +273,12 @@ def edvr_forward(net, x, dtype=torch.bfloat16):
     C = l1.shape[3]
     l1, l2, l3 = l1.view(b, t, h, w, C), l2.view(b, t, h // 2, w // 2, C), l3.view(b, t, h // 4, w // 4, C)
     ci = net.center_frame_idx
-    ref = [l1[:, ci].contiguous(), l2[:, ci].contiguous(), l3[:, ci].contiguous()]
-    aligned = torch.stack([pcd_align(net.pcd_align, [l1[:, i].contiguous(), l2[:, i].contiguous(), l3[:, i].contiguous()], ref)
-                           for i in range(t)], 1)                                             # [b, t, h, w, C]
+    # all t neighbour frames of all clips go through PCD alignment as ONE batch (the reference loops over frames in Python,
+    # edvr_arch.py:397-402; samples are independent, so the result is the same): reference features repeated per frame
+    def rep(z):
+        return z[:, ci].unsqueeze(1).expand(-1, t, -1, -1, -1).reshape(b * t, *z.shape[2:])
+    nbr = [z.reshape(b * t, *z.shape[2:]) for z in (l1, l2, l3)]
+    aligned = pcd_align(net.pcd_align, nbr, [rep(l1), rep(l2), rep(l3)]).view(b, t, h, w, C)
     if net.with_tsa:
         feat = tsa_fusion(net.fusion, aligned)
     else:
@@ -281,3 +298,37 @@ def charbonnier_loss(pred, target, eps=1e-12, reduction="sum", loss_weight=1.0):
     """basicsr/models/losses/losses.py:24-25,115-150 (CharbonnierLoss; the REDS yml uses reduction='sum')."""
     v = torch.sqrt((pred - target) ** 2 + eps)
     return loss_weight * (v.sum() if reduction == "sum" else v.mean())
+
+
+class GraphedTrainStep:
+    """One optimisation step (forward, loss, backward, optimizer.step) captured ONCE into a CUDA graph and replayed:
+    an EDVR-L step is ~4000 small launches (weight packs, transposes, elementwise glue, 20 DCN calls) and is host-bound when
+    issued eagerly; every shape is static, so the whole step replays from one launch.  The optimizer must be capturable
+    (torch.optim.Adam(..., capturable=True)).  __call__(x, target) copies the batch into the static buffers, replays,
+    and returns the (static) loss tensor."""
+
+    def __init__(self, net, optimizer, loss_fn, x, target, warmup=3):
+        self.x, self.target = x.clone(), target.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # allocate workspaces / optimizer state outside the capture
+                optimizer.zero_grad(set_to_none=True)
+                loss_fn(net(self.x), self.target).backward()
+                optimizer.step()
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self.graph, stream=side):
+                self.loss = loss_fn(net(self.x), self.target)
+                self.loss.backward()
+                optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+
+    def __call__(self, x=None, target=None):
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if target is not None:
+            self.target.copy_(target, non_blocking=True)
+        self.graph.replay()
+        return self.loss

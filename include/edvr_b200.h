@@ -108,6 +108,10 @@ int eb_pack_weight_pair(const float* w, int cout, int cin, int ktaps, const int*
                         void* wpair, void* stream);
 int eb_pack_weight_pair_ex(const float* w, int cout, int cin, int ktaps, const int* row_map, int BN, int n_tiles_n,
                            void* wpair, int bf16, void* stream);
+/* Weights of the DATA-GRADIENT convolution packed straight from the forward weights w[cout][cin][k][k]: row ci, K index co,
+ * tap flipped (training step; k_channels = cout rounded up to a multiple of 64 = channels of the padded grad_out view). */
+int eb_pack_weight_pair_dgrad(const float* w, int cout, int cin, int ktaps, int k_channels, int BN, int n_tiles_n, void* wpair,
+                              int bf16, void* stream);
 int eb_conv2d_pair(const eb_src_t* srcs, int nsrc, int N, int H, int W, int ksize, const void* wpair, int BN,
                    int n_tiles_n, const eb_epilogue_t* epi, void* stream);
 
@@ -126,11 +130,13 @@ int eb_dcn_nhwc(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int
  *   grad_weight[co][ci][ky][kx] += scale * sum_{n,y,x} gy[n,y,x,co] * x[n, y+ky-1, x+kx-1, ci]
  * == the cuDNN wgrad behind autograd of nn.Conv2d in the reference's training loop (basicsr/models/base_model.py:62-69,
  * options/train/EDVR/train_EDVR_L_x4_SR_REDS.yml).  x, gy: NHWC 16-bit views (fp16, or bf16 with bf16 = 1), Cin % 32 == 0;
- * grad_weight fp32 [Cout][Cin][k][k] is ACCUMULATED into (zero it for a plain gradient).  The data gradient is
- * eb_conv2d_pair on weights packed from the transposed, flipped tensor; the bias gradient is a plain reduction. */
+ * grad_weight fp32 [Cout][Cin][k][k] is ACCUMULATED into (zero it for a plain gradient), deterministically (split-K partial
+ * tiles summed in a fixed order); grad_bias, when given, is accumulated while grad_out is transposed.  The data gradient is
+ * eb_conv2d_pair on weights packed by eb_pack_weight_pair_dgrad. */
 size_t eb_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ksize);
 int eb_conv_wgrad(const void* x, int x_pix_stride, int x_ch_off, const void* gy, int gy_pix_stride, int gy_ch_off, int N,
-                  int H, int W, int Cin, int Cout, int ksize, int bf16, float scale, float* grad_weight, void* workspace,
+                  int H, int W, int Cin, int Cout, int ksize, int bf16, float scale, float* grad_weight,
+                  float* grad_bias /* optional fp32 [Cout]: += sum of gy over all pixels */, void* workspace,
                   size_t workspace_bytes, void* stream);
 
 /* ---- One DCNv2Pack site (archs/arch_util.py:243-257) for 3x3 / stride 1 / pad 1 / dilation 1 on NHWC fp16 features:

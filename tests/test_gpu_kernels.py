@@ -374,20 +374,28 @@ def test_training_conv_function_vs_torch_autograd(ops, case, dtype):
     xq = x.to(dtype).float()                                   # the activations the kernel sees
     a = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "lrelu": ops.ACT_LRELU}[act]
     f = {"none": lambda t: t, "relu": F.relu, "lrelu": lambda t: F.leaky_relu(t, 0.1)}[act]
-    # reference: fp32 autograd
-    xr = xq.clone().requires_grad_(True)
-    yr = f(F.conv2d(xr, m.weight, m.bias, stride, k // 2))
-    yr.backward(go)
-    gw_ref, gb_ref, gx_ref = m.weight.grad.clone(), m.bias.grad.clone(), xr.grad.clone()
-    m.zero_grad()
     # ours
     xo = xq.permute(0, 2, 3, 1).to(dtype).contiguous().requires_grad_(True)
     yo = T.conv(xo, m, a)
     assert yo.shape == (N, Ho, Wo, cout) and yo.dtype == dtype
     yo.backward(go.permute(0, 2, 3, 1).to(dtype).contiguous())
+    gw_ours, gb_ours = m.weight.grad.clone(), m.bias.grad.clone()
+    m.zero_grad()
+    # reference: fp32 autograd of the convolution; the activation's derivative is taken at OUR forward output - (Leaky)ReLU'
+    # is discontinuous at 0, so the ~4e-5 of the pre-activations whose sign flips under 16-bit rounding would otherwise
+    # contribute O(1) differences that say nothing about the dgrad / wgrad kernels (measured: 0.9 % rel-L2 from 4e-5 flips)
+    xr = xq.clone().requires_grad_(True)
+    pre = F.conv2d(xr, m.weight, m.bias, stride, k // 2)
+    yr = f(pre)
+    y_ours = yo.detach().permute(0, 3, 1, 2).float()
+    slope = {"none": None, "relu": 0.0, "lrelu": 0.1}[act]
+    gpre = go if slope is None else go * torch.where(y_ours > 0, 1.0, slope)
+    assert float(((y_ours > 0) != (pre.detach() > 0)).float().mean()) < 5e-3        # the flipped fraction stays tiny
+    pre.backward(gpre)
+    gw_ref, gb_ref, gx_ref = m.weight.grad.clone(), m.bias.grad.clone(), xr.grad.clone()
     for name, got, want in (("y", yo.detach().permute(0, 3, 1, 2).float(), yr.detach()),
                             ("grad_x", xo.grad.permute(0, 3, 1, 2).float(), gx_ref),
-                            ("grad_weight", m.weight.grad, gw_ref), ("grad_bias", m.bias.grad, gb_ref)):
+                            ("grad_weight", gw_ours, gw_ref), ("grad_bias", gb_ours, gb_ref)):
         e = rel_err(got.cpu(), want.cpu())
         assert e[0] < tol * 2 and e[1] < tol, (name, e)        # max-rel on a heavy-tailed gradient: 2 x the L2 bar
 

@@ -581,8 +581,8 @@ WgradGeo wgrad_geo(int N, int H, int W, int Cin, int Cout, int ksize) {
     g.BN = Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 0));
     g.k_steps = g.body / 64;
     const int tiles = g.BN ? ksize * ksize * (Cin / g.BN) * static_cast<int>(g.rowsA / 128) : 1;
-    long long splits = (2LL * 148 + tiles - 1) / tiles;          // ~2 CTAs per SM; at least 8 K steps per split
-    if (splits > g.k_steps / 8) splits = g.k_steps / 8;
+    long long splits = (2LL * 148) / tiles;                      // one wave of 2 CTAs per SM; at least 24 K steps per split
+    if (splits > g.k_steps / 24) splits = g.k_steps / 24;        // (prologue + 64 KB partial tile amortised over >= 1.5K pixels)
     if (splits < 1) splits = 1;
     g.steps_per_split = static_cast<int>((g.k_steps + splits - 1) / splits);
     g.splits = static_cast<int>((g.k_steps + g.steps_per_split - 1) / g.steps_per_split);
@@ -617,19 +617,19 @@ int eb_conv_wgrad(const void* x, int x_pix_stride, int x_ch_off, const void* gy,
     const long long copy_stride = static_cast<long long>(Cin) * g.Ppad;
     {
         dim3 block(32, 8);
-        const unsigned gy_rows = static_cast<unsigned>((H + CT_ROWS - 1) / CT_ROWS);
-        dim3 grid_g((W + 31) / 32, gy_rows, N * ((Cout + 31) / 32));
-        dim3 grid_x((W + 31) / 32, gy_rows, N * ((Cin + 31) / 32));
+        const int rows_g = grad_bias ? CT_ROWS : 1;
+        dim3 grid_g((W + 31) / 32, static_cast<unsigned>((H + rows_g - 1) / rows_g), N * ((Cout + 31) / 32));
+        dim3 grid_x((W + 31) / 32, static_cast<unsigned>(H), N * ((Cin + 31) / 32));
         if (bf16) {
             nhwc_to_cmajor_pad_kernel<true><<<grid_g, block, 0, st>>>(static_cast<const uint16_t*>(gy), gy_pix_stride, gy_ch_off, Cout,
-                                                                      H, W, gyT, 0, g.Ppad, g.Hp, g.Wp, g.margin, 1, grad_bias);
+                                                                      H, W, gyT, 0, g.Ppad, g.Hp, g.Wp, g.margin, 1, grad_bias, rows_g);
             nhwc_to_cmajor_pad_kernel<true><<<grid_x, block, 0, st>>>(static_cast<const uint16_t*>(x), x_pix_stride, x_ch_off, Cin, H,
-                                                                      W, xT, copy_stride, g.Ppad, g.Hp, g.Wp, g.margin, g.copies, nullptr);
+                                                                      W, xT, copy_stride, g.Ppad, g.Hp, g.Wp, g.margin, g.copies, nullptr, 1);
         } else {
             nhwc_to_cmajor_pad_kernel<false><<<grid_g, block, 0, st>>>(static_cast<const uint16_t*>(gy), gy_pix_stride, gy_ch_off, Cout,
-                                                                       H, W, gyT, 0, g.Ppad, g.Hp, g.Wp, g.margin, 1, grad_bias);
+                                                                       H, W, gyT, 0, g.Ppad, g.Hp, g.Wp, g.margin, 1, grad_bias, rows_g);
             nhwc_to_cmajor_pad_kernel<false><<<grid_x, block, 0, st>>>(static_cast<const uint16_t*>(x), x_pix_stride, x_ch_off, Cin, H,
-                                                                       W, xT, copy_stride, g.Ppad, g.Hp, g.Wp, g.margin, g.copies, nullptr);
+                                                                       W, xT, copy_stride, g.Ppad, g.Hp, g.Wp, g.margin, g.copies, nullptr, 1);
         }
         if (int rc = check_launch("conv_wgrad transposes")) return rc;
     }
@@ -637,11 +637,30 @@ int eb_conv_wgrad(const void* x, int x_pix_stride, int x_ch_off, const void* gy,
     if (int rc = set_smem(conv_wgrad_kernel, CW_SMEM_BYTES)) return rc;
     const unsigned m_tiles = static_cast<unsigned>(g.rowsA / 128);
     dim3 grid(taps * (Cin / BN), m_tiles, static_cast<unsigned>(g.splits));
-    // 1x1: the single unshifted copy sits at copy index 0, the kernel addresses copy (dxi = 1) -> pass a base one copy earlier
-    const __half* Bbase = reinterpret_cast<const __half*>(xT) - (ksize == 1 ? copy_stride : 0);
-    conv_wgrad_kernel<<<grid, 128, CW_SMEM_BYTES, st>>>(reinterpret_cast<const __half*>(gyT), Bbase, copy_stride, partial,
-                                                        Cout, Cin, taps, g.Ppad, g.Wp, BN, g.steps_per_split, g.margin, g.k_steps,
-                                                        bf16 ? 1 : 0);
+    eb_encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return fail(EB_ERR_UNSUPPORTED, "conv_wgrad: cuTensorMapEncodeTiled unavailable");
+    WgradParams WP;
+    memset(&WP, 0, sizeof(WP));
+    {
+        // channel-major rows [rows][Ppad] as {8 elements, rows, Ppad / 8 atoms}: a box {8, R, 8} is one 64-pixel K step in the
+        // no-swizzle K-major operand layout ([K atom][row][16 B])
+        const cuuint64_t atoms = static_cast<cuuint64_t>(g.Ppad / 8);
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.Ppad) * 2, 16};
+        const cuuint64_t dims_a[3] = {8, static_cast<cuuint64_t>(g.rowsA), atoms};
+        const cuuint32_t box_a[3] = {8, 128, 8};
+        CUresult r = enc(&WP.tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, gyT, dims_a, strides, box_a, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "conv_wgrad: tensor map A failed (%d)", static_cast<int>(r));
+        const cuuint64_t dims_b[3] = {8, static_cast<cuuint64_t>(g.copies) * Cin, atoms};
+        const cuuint32_t box_b[3] = {8, static_cast<cuuint32_t>(BN), 8};
+        r = enc(&WP.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, xT, dims_b, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "conv_wgrad: tensor map B failed (%d)", static_cast<int>(r));
+    }
+    WP.partial = partial; WP.Cin = Cin; WP.taps = taps; WP.BN = BN; WP.Wp = g.Wp; WP.steps_per_split = g.steps_per_split;
+    WP.ab_fmt = bf16 ? 1 : 0; WP.k_begin = g.margin; WP.k_steps = g.k_steps;
+    conv_wgrad_kernel<<<grid, CW_THREADS, CW_SMEM_BYTES, st>>>(WP);
     if (int rc = check_launch("conv_wgrad")) return rc;
     const long long total = static_cast<long long>(taps) * Cout * Cin;
     conv_wgrad_reduce_kernel<<<grid_1d(total, 256), 256, 0, st>>>(partial, grad_weight, Cout, Cin, taps, BN, static_cast<int>(m_tiles),

@@ -271,6 +271,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint64_t* bar, uint
         ::"r"(smem_u32(bar)), "r"(target), "r"(bytes)
         : "memory");
 }
+// plain (single-CTA) tensor-map loads: the box lands in this CTA's shared memory, bytes counted on its own mbarrier
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 // shared -> global tile store (bulk async group of the issuing thread); out-of-range parts of the box are clipped
 __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* src_smem, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"

@@ -15,27 +15,29 @@
 // tcgen05 kernel of the DCN weight gradient (dcn_backward.cuh) with a per-tap operand base.  2-byte elements are moved
 // as raw bits, so fp16 and bf16 share the transposes; the MMA operand format is selected by the instruction descriptor.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace eb {
 
 // src: NHWC 2-byte elements (view: pix_stride, ch_off, C channels) -> dst[dx][c][p] for dx in [0, ncopies): ncopies == 3
 // writes the three shifted copies (dst copy i holds xpad shifted by dx = i - 1), ncopies == 1 the unshifted one.
-// grid: (ceil(W/32), ceil(H/CT_ROWS), N * ceil(C/32)), block (32, 8); dst must be zero-filled (borders, padding, margins).
+// grid: (ceil(W/32), ceil(H/rows), N * ceil(C/32)), block (32, 8); dst must be zero-filled (borders, padding, margins).
 // colsum (optional, fp32 [C]): += sum over all pixels of src[.., c] - the bias gradient when src is grad_out, taken while
 // the tile is in flight (a separate ATen reduction over NHWC bf16 cost 37 us per layer, 11 % of the training step).
-constexpr int CT_ROWS = 8;
+constexpr int CT_ROWS = 8;          // image rows per block when the column sum is taken (one atomic per channel and block)
 template <bool BF16>
 __global__ void nhwc_to_cmajor_pad_kernel(const uint16_t* __restrict__ src, int pix_stride, int ch_off, int C, int H, int W,
                                           uint16_t* __restrict__ dst, long long copy_stride, long long Ppad, int Hp, int Wp,
-                                          int margin, int ncopies, float* __restrict__ colsum) {
+                                          int margin, int ncopies, float* __restrict__ colsum, int rows) {
     __shared__ uint16_t tile[32][34];
     __shared__ float red[8][33];
     const int cblocks = (C + 31) / 32;
     const int n = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 32;
     const int x0 = blockIdx.x * 32;
     float acc = 0.f;
-    for (int y = blockIdx.y * CT_ROWS; y < H && y < (blockIdx.y + 1) * CT_ROWS; ++y) {
+    for (int y = blockIdx.y * rows; y < H && y < (blockIdx.y + 1) * rows; ++y) {
         for (int i = threadIdx.y; i < 32; i += 8) {                    // i: pixel within the tile, threadIdx.x: channel
             const int x = x0 + i, c = c0 + threadIdx.x;
             const uint16_t v = (x < W && c < C)
@@ -73,89 +75,101 @@ __global__ void nhwc_to_cmajor_pad_kernel(const uint16_t* __restrict__ src, int 
     }
 }
 
-constexpr int CW_STAGES = 3;
-constexpr int CW_SMEM_BYTES = CW_STAGES * (128 * 128 + 128 * 128);
+constexpr int CW_STAGES = 3;                               // 96 KB per CTA: two CTAs per SM keep 192 KB in flight
+constexpr int CW_STAGE_BYTES = 128 * 128 + 128 * 128;      // A: 128 rows x 64 K x 2 B as 8 K-atom planes, B: BN <= 128 rows
+constexpr int CW_SMEM_BYTES = CW_STAGES * CW_STAGE_BYTES + 256;
+constexpr int CW_THREADS = 192;                            // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
 
-// partial[split][tile][co 128][ci BN] = sum over this split's pixels of A[co][p] * B_tap[ci][p]; A = gyT (rows padded to a
-// multiple of 128), B_tap = xT_dx(tap) at row offset dy(tap) * Wp.  grid: (taps * (Cin / BN), ceil(Cout / 128), splits),
-// 128 threads.  Split-K partial tiles go to a workspace and are summed by conv_wgrad_reduce_kernel in a fixed order:
-// deterministic, and 30x fewer memory operations than fp32 atomics on [co][ci][tap] (4.7 M atomics per layer made this
-// kernel 37 % of the first training step profile, profiles/r02_train_profile_v1.txt).
-__global__ void __launch_bounds__(128, 1)
-conv_wgrad_kernel(const __half* __restrict__ A, const __half* __restrict__ B, long long b_copy_stride, float* __restrict__ partial,
-                  int Cout, int Cin, int taps, long long Ppad, int Wp, int BN, int steps_per_split, long long k_begin,
-                  long long k_steps, int ab_fmt) {
+struct WgradParams {
+    CUtensorMap tmap_a;        // gyT as {8, rowsA, Ppad / 8}: box {8, 128, 8} lands as [K atom][row][16 B] (no-swizzle K-major)
+    CUtensorMap tmap_b;        // xT copies as {8, copies * Cin, Ppad / 8}: box {8, BN, 8}
+    float* partial;            // [split][m tile][tile][128][BN] fp32
+    int Cin, taps, BN, Wp, steps_per_split, ab_fmt;
+    long long k_begin, k_steps;
+};
+
+// partial[split][mt][tile][co 128][ci BN] = sum over this split's pixels of A[co][p] * B_tap[ci][p]; A = gyT (rows padded to a
+// multiple of 128), B_tap = xT_dx(tap) at row offset dy(tap) * Wp.  grid: (taps * (Cin / BN), ceil(Cout / 128), splits).
+// Warp-specialised: one thread streams both operand tiles of a 64-pixel K step with two TMA boxes per stage (3 stages,
+// two CTAs per SM = 192 KB in flight), one thread issues 4 tcgen05.mma per stage, four warps drain the 128 x BN accumulator.  The first version
+// (128 threads loading with LDG -> STS -> __syncthreads per step) ran at 95 TFLOP/s and was a third of the training step
+// (profiles/r02_train_profile_v2.txt).  Split-K partial tiles go to a workspace and are summed in a fixed order by
+// conv_wgrad_reduce_kernel: deterministic, no atomics.
+__global__ void __launch_bounds__(CW_THREADS, 2) conv_wgrad_kernel(const __grid_constant__ WgradParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t stage_free[CW_STAGES];
-    __shared__ uint64_t done_bar;
-    __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int ntiles_c = Cin / BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CW_STAGES * CW_STAGE_BYTES);
+    uint64_t* full = bars;                    // [CW_STAGES]
+    uint64_t* empty = bars + CW_STAGES;       // [CW_STAGES]
+    uint64_t* done_bar = empty + CW_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int BN = P.BN, ntiles_c = P.Cin / BN;
     const int tap = blockIdx.x / ntiles_c, c0 = (blockIdx.x % ntiles_c) * BN, mt = blockIdx.y;
-    const long long s0 = static_cast<long long>(blockIdx.z) * steps_per_split;
-    long long s1 = s0 + steps_per_split;
-    if (s1 > k_steps) s1 = k_steps;
+    const long long s0 = static_cast<long long>(blockIdx.z) * P.steps_per_split;
+    long long s1 = s0 + P.steps_per_split;
+    if (s1 > P.k_steps) s1 = P.k_steps;
     const int nsteps = s1 > s0 ? static_cast<int>(s1 - s0) : 0;
-    const int dy = taps == 9 ? tap / 3 - 1 : 0, dxi = taps == 9 ? tap % 3 : 1;      // copy index dxi holds dx = dxi - 1
+    const int dy = P.taps == 9 ? tap / 3 - 1 : 0, dxi = P.taps == 9 ? tap % 3 : 0;      // copy index dxi holds dx = dxi - 1
 
     if (tid == 0) {
-        for (int i = 0; i < CW_STAGES; ++i) mbar_init(&stage_free[i], 1);
-        mbar_init(&done_bar, 1);
+        for (int i = 0; i < CW_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done_bar, 1);
         fence_barrier_init();
+        tma_prefetch_desc(&P.tmap_a);
+        tma_prefetch_desc(&P.tmap_b);
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_slot;
-    const uint32_t idesc = umma_idesc_f16(128, BN, static_cast<uint32_t>(ab_fmt));
-    const uint32_t lbo_b = static_cast<uint32_t>(BN) * 16u;
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t b_bytes = static_cast<uint32_t>(BN) * 128u;
 
-    const __half* Arow = A + (static_cast<size_t>(mt) * 128 + tid) * Ppad + k_begin;                 // one A row per thread
-    const __half* Brow = B + dxi * b_copy_stride + (static_cast<size_t>(c0) + (tid < BN ? tid : 0)) * Ppad + k_begin +
-                         static_cast<long long>(dy) * Wp;
-    for (int i = 0; i < nsteps; ++i) {
-        const int s = i % CW_STAGES;
-        if (i >= CW_STAGES) mbar_wait(&stage_free[s], ((i / CW_STAGES) - 1) & 1);
-        uint8_t* a_s = smem + s * (2 * 128 * 128);
-        uint8_t* b_s = a_s + 128 * 128;
-        const long long p0 = (s0 + i) * 64;
-        uint4 va[8];
-#pragma unroll
-        for (int kc = 0; kc < 8; ++kc) va[kc] = ldg_nc_v4(Arow + p0 + kc * 8);
-#pragma unroll
-        for (int kc = 0; kc < 8; ++kc) sts_v4(smem_u32(a_s) + kc * 2048 + tid * 16, va[kc]);
-        if (tid < BN) {
-#pragma unroll
-            for (int kc = 0; kc < 8; ++kc) va[kc] = ldg_nc_v4(Brow + p0 + kc * 8);
-#pragma unroll
-            for (int kc = 0; kc < 8; ++kc) sts_v4(smem_u32(b_s) + kc * lbo_b + tid * 16, va[kc]);
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-#pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) {
-                const uint64_t ad = umma_desc_nosw(smem_u32(a_s) + k16 * 2 * 2048, 2048, 128);
-                const uint64_t bd = umma_desc_nosw(smem_u32(b_s) + k16 * 2 * lbo_b, lbo_b, 128);
-                umma_f16(tmem_base, ad, bd, idesc, (i | k16) != 0 ? 1u : 0u);
+    if (warp == 0) {
+        if (lane == 0) {
+            const int a_atom0 = static_cast<int>((P.k_begin + s0 * 64) >> 3);
+            const int b_atom0 = static_cast<int>((P.k_begin + s0 * 64 + static_cast<long long>(dy) * P.Wp) >> 3);
+            for (int i = 0; i < nsteps; ++i) {
+                const int s = i % CW_STAGES;
+                mbar_wait_t<32>(&empty[s], ((i / CW_STAGES) & 1) ^ 1);
+                uint8_t* a_s = smem + s * CW_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[s], 128u * 128u + b_bytes);
+                tma_load_3d(a_s, &P.tmap_a, &full[s], 0, mt * 128, a_atom0 + i * 8);
+                tma_load_3d(a_s + 128 * 128, &P.tmap_b, &full[s], 0, dxi * P.Cin + c0, b_atom0 + i * 8);
             }
-            umma_commit(&stage_free[s]);
         }
-    }
-    if (tid == 0) umma_commit(&done_bar);
-    {
-        // this CTA's tile of the partial sums: [co = tid][BN] contiguous floats (zeros when the split got no K steps)
-        float* out = partial + ((static_cast<size_t>(blockIdx.z) * gridDim.y + mt) * gridDim.x + blockIdx.x) * (128 * static_cast<size_t>(BN)) +
-                     static_cast<size_t>(tid) * BN;
+    } else if (warp == 1) {
+        const uint32_t idesc = umma_idesc_f16(128, BN, static_cast<uint32_t>(P.ab_fmt));
+        const uint32_t lbo_b = static_cast<uint32_t>(BN) * 16u;
+        const uint32_t hi = umma_desc_hi(128);
+        for (int i = 0; i < nsteps; ++i) {
+            const int s = i % CW_STAGES;
+            mbar_wait(&full[s], (i / CW_STAGES) & 1);
+            tc_fence_after_sync();
+            const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem + s * CW_STAGE_BYTES), 2048);
+            const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem + s * CW_STAGE_BYTES + 128 * 128), lbo_b);
+            if (elect_one()) {
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16)
+                    umma_f16_lohi<1>(tmem_base, a_lo0 + k16 * (2 * 2048 / 16), hi, b_lo0 + k16 * ((2u * lbo_b) >> 4), hi, idesc,
+                                     (i | k16) != 0 ? 1u : 0u);
+                umma_commit(&empty[s]);
+                if (i == nsteps - 1) umma_commit(done_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        // this CTA's tile of the partial sums: row co = 32 q + lane (q = TMEM lane quarter of the warp), BN contiguous floats
+        const int q = warp & 3;
+        float* out = P.partial + ((static_cast<size_t>(blockIdx.z) * gridDim.y + mt) * gridDim.x + blockIdx.x) * (128 * static_cast<size_t>(BN)) +
+                     static_cast<size_t>(32 * q + lane) * BN;
         if (nsteps > 0) {
-            mbar_wait(&done_bar, 0);
+            mbar_wait_t<64>(done_bar, 0);
             tc_fence_after_sync();
         }
         for (int cc = 0; cc < BN; cc += 32) {
             float v[32];
-            if (nsteps > 0) tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + cc, v);
+            if (nsteps > 0) tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + cc, v);
             else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;

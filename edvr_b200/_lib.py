@@ -57,6 +57,12 @@ _SIGS = {
                             c_void_p, c_void_p, c_ll, c_ll, c_int,
                             c_void_p, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p, c_void_p]),
+    "eb_dcn_pair_supported": (c_int, [c_int] * 4),
+    "eb_dcn_pair_offset_weight_bytes": (c_size_t, [c_int]),
+    "eb_dcn_pair_pack_offset_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "eb_dcn_site_pair": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_int, ctypes.POINTER(Epilogue), c_void_p, c_void_p]),
     "eb_mdcn_forward_workspace": (c_size_t, [c_int] * 7),
     "eb_mdcn_forward": (c_int, [c_void_p] * 6 + [c_int] * 12 + [c_void_p, c_size_t, c_void_p]),
     "eb_mdcn_backward_workspace": (c_size_t, [c_int] * 10),

@@ -15,6 +15,7 @@
 #include "dcn_backward.cuh"
 #include "dcn_fused.cuh"
 #include "dcn_site.cuh"
+#include "dcn_pair.cuh"
 #include "elementwise.cuh"
 #include "epilogue.cuh"
 #include "selftest.cuh"
@@ -771,6 +772,126 @@ int eb_dcn_site(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int
 #undef EB_LAUNCH_DS
     if (lerr != cudaSuccess) return fail(EB_ERR_LAUNCH, "dcn_site: %s", cudaGetErrorString(lerr));
     return check_launch("dcn_site");
+}
+
+// ---- CTA-pair DCN site kernel (dcn_pair.cuh): conv_offset of the next half tile overlaps the gather of this one
+int eb_dcn_pair_supported(int C, int dg, int BN, int n_tiles_n) {
+    if (C < 64 || C % 64 || dg < 2 || dg % 2 || C % dg || (dg / 2) * 27 > DP_OFF_HALF) return 0;
+    const int cpg = C / dg;
+    if (cpg != 8 && cpg % 16) return 0;
+    if (BN % 32 || BN < 32 || BN > 128 || n_tiles_n != 1) return 0;
+    if (num_sms() < 2 || tensor_map_encoder() == nullptr) return 0;
+    return 1;
+}
+
+size_t eb_dcn_pair_offset_weight_bytes(int C) { return static_cast<size_t>(4) * (C / 32) * 9 * DP_WO_STAGE; }
+
+int eb_dcn_pair_pack_offset_weight(const float* wo, const float* bo, int C, int dg, void* wo_pack, float* bo_cols, void* stream) {
+    if (!wo || !wo_pack || !bo_cols) return fail(EB_ERR_NULLPTR, "dcn_pair_pack: null pointer");
+    if (C < 64 || C % 64 || dg < 2 || dg % 2 || (dg / 2) * 27 > DP_OFF_HALF) return fail(EB_ERR_INVALID_SHAPE, "dcn_pair_pack: C=%d dg=%d", C, dg);
+    const long long groups = 4ll * (C / 32) * 9 * 4 * DP_WO_ROWS;
+    pack_offset_weight_pair_kernel<<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        wo, bo, C, dg, static_cast<__half*>(wo_pack), bo_cols);
+    return check_launch("pack_offset_weight_pair");
+}
+
+int eb_dcn_site_pair(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
+                     const void* feat, int f_pix_stride, int f_ch_off, const void* wo_pack, const float* bo_cols,
+                     const void* wpair, int BN, const eb_epilogue_t* epi, float* absmean, void* stream) {
+    if (!x || !feat || !wo_pack || !bo_cols || !wpair) return fail(EB_ERR_NULLPTR, "dcn_site_pair: null pointer");
+    if (N < 0 || H < 1 || W < 1) return fail(EB_ERR_INVALID_SHAPE, "dcn_site_pair: N=%d H=%d W=%d", N, H, W);
+    if (!eb_dcn_pair_supported(C, dg, BN, 1))
+        return fail(EB_ERR_UNSUPPORTED, "dcn_site_pair: C=%d dg=%d BN=%d (see eb_dcn_pair_supported)", C, dg, BN);
+    if (!al16(x) || !al16(wpair) || x_pix_stride % 8 || x_ch_off % 8 || x_pix_stride < x_ch_off + C)
+        return fail(EB_ERR_ALIGNMENT, "dcn_site_pair: x view must be 16-byte aligned");
+    if (!al16(feat) || !al16(wo_pack) || f_pix_stride % 8 || f_ch_off % 8 || f_pix_stride < f_ch_off + C)
+        return fail(EB_ERR_ALIGNMENT, "dcn_site_pair: feature view must be 16-byte aligned");
+    eb_encode_tiled_fn enc = tensor_map_encoder();
+    if (N == 0) return EB_OK;
+    DpParams PP;
+    memset(&PP, 0, sizeof(PP));
+    DcnParams& P = PP.d;
+    P.x = static_cast<const __half*>(x); P.x_pix_stride = x_pix_stride; P.x_ch_off = x_ch_off;
+    P.N = N; P.H = H; P.W = W; P.C = C; P.Ho = H; P.Wo = W;
+    P.kh = 3; P.kw = 3; P.stride = 1; P.pad = 1; P.dil = 1; P.stride_w = 1; P.pad_w = 1; P.dil_w = 1;
+    P.dg = dg; P.cpg = C / dg;
+    P.x_wide = (x_pix_stride % 16 == 0 && x_ch_off % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 32 == 0) ? 1 : 0;
+    P.wpack = static_cast<const __half*>(wpair); P.BN = BN; P.n_tiles_n = 1;
+    if (int rc = fill_epi(epi, H, W, BN, &P.epi)) return rc;
+    if (P.epi.out_mode != OUT_SAME) return fail(EB_ERR_UNSUPPORTED, "dcn_site_pair: out_mode");
+    const bool nchw = P.epi.out_nchw != nullptr;
+    if (nchw && (P.epi.out16 || P.epi.out32 || P.epi.res16 || P.epi.res32)) return fail(EB_ERR_UNSUPPORTED, "dcn_site_pair: NCHW output excludes other outputs");
+    if (!nchw && (!P.epi.out16 || P.epi.out32 || P.epi.res32 || P.epi.res16)) return fail(EB_ERR_UNSUPPORTED, "dcn_site_pair: NHWC fp16 output only");
+    PP.absmean = absmean;
+    PP.f_ch_off = f_ch_off; PP.wo_pack = static_cast<const __half*>(wo_pack); PP.bo = bo_cols;
+    {
+        const cuuint64_t ps = static_cast<cuuint64_t>(x_pix_stride);
+        const cuuint64_t dims[4] = {ps, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+        const cuuint64_t strides[3] = {ps * 2, static_cast<cuuint64_t>(W) * ps * 2, static_cast<cuuint64_t>(H) * W * ps * 2};
+        const cuuint32_t box[4] = {32, DP_WW, DP_WH, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = enc(&PP.tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "dcn_site_pair: window tensor map failed (%d)", static_cast<int>(r));
+    }
+    {
+        const cuuint64_t ps = static_cast<cuuint64_t>(f_pix_stride);
+        const cuuint64_t dims[5] = {8, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), ps / 8, static_cast<cuuint64_t>(N)};
+        const cuuint64_t strides[4] = {ps * 2, static_cast<cuuint64_t>(W) * ps * 2, 16, static_cast<cuuint64_t>(H) * W * ps * 2};
+        const cuuint32_t box[5] = {8, DS_F_RP_X, DS_F_RP_Y, 4, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const CUresult r = enc(&PP.tmap_f, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(feat), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "dcn_site_pair: feature tensor map failed (%d)", static_cast<int>(r));
+    }
+    {
+        // packed weight arrays as rows of 256 fp16 (512 B); one box = one pipeline stage of one CTA, landing as a linear copy
+        const cuuint32_t estr[2] = {1, 1};
+        const cuuint64_t strides[1] = {512};
+        const cuuint64_t dims_w[2] = {256, static_cast<cuuint64_t>(2) * (C / 32) * 9 * (BN / 16)};
+        const cuuint32_t box_w[2] = {256, static_cast<cuuint32_t>(BN / 16)};
+        CUresult r = enc(&PP.tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(wpair), dims_w, strides, box_w, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "dcn_site_pair: weight tensor map failed (%d)", static_cast<int>(r));
+        const cuuint64_t dims_o[2] = {256, static_cast<cuuint64_t>(4) * (C / 32) * 9 * (DP_WO_STAGE / 512)};
+        const cuuint32_t box_o[2] = {256, DP_WO_STAGE / 512};
+        r = enc(&PP.tmap_wo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(wo_pack), dims_o, strides, box_o, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "dcn_site_pair: offset weight tensor map failed (%d)", static_cast<int>(r));
+    }
+    const long long tiles = static_cast<long long>(N) * ((H + DC_TILE_H - 1) / DC_TILE_H) * ((W + DC_TILE_W - 1) / DC_TILE_W);
+    const long long npairs = (tiles + 1) / 2;
+    const int max_clusters = num_sms() / 2;
+    const int nclusters = static_cast<int>(npairs < max_clusters ? npairs : max_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * nclusters);
+    cfg.blockDim = dim3(DP_THREADS);
+    cfg.dynamicSmemBytes = DP_SMEM_BYTES;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t lerr = cudaSuccess;
+    const bool two = P.cpg == 8;
+#define EB_LAUNCH_DP(EK_)                                                                          \
+    do {                                                                                           \
+        if (two) {                                                                                 \
+            if (int rc = set_smem(dcn_pair_kernel<EK_, true>, DP_SMEM_BYTES)) return rc;           \
+            lerr = cudaLaunchKernelEx(&cfg, dcn_pair_kernel<EK_, true>, PP);                       \
+        } else {                                                                                   \
+            if (int rc = set_smem(dcn_pair_kernel<EK_, false>, DP_SMEM_BYTES)) return rc;          \
+            lerr = cudaLaunchKernelEx(&cfg, dcn_pair_kernel<EK_, false>, PP);                      \
+        }                                                                                          \
+    } while (0)
+    if (nchw) EB_LAUNCH_DP(EK_NCHW); else EB_LAUNCH_DP(EK_PLAIN);
+#undef EB_LAUNCH_DP
+    if (lerr != cudaSuccess) return fail(EB_ERR_LAUNCH, "dcn_site_pair: %s", cudaGetErrorString(lerr));
+    return check_launch("dcn_site_pair");
 }
 
 // ---- reference-layout operator -----------------------------------------------------------

@@ -208,6 +208,19 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t targe
         ::"r"(smem_u32(bar)), "r"(target)
         : "memory");
 }
+// Same signal WITHOUT a cluster-scope release (what CUTLASS' ClusterBarrier::arrive(cta_id) emits).  The .release.cluster
+// form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive (~0.3 us each, profiles/r02_ncu_dcn_pair_v1):
+// fine once per tile, ruinous once per pipeline stage.  Use it when the arrival only tells the peer "go": the data it
+// announces never crosses the CTA boundary through the generic proxy (shared memory read by the local tensor core after a
+// local fence.proxy.async, or tensor memory whose reads were fenced with tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint64_t* bar, uint32_t target) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(target)
+        : "memory");
+}
 // ---- lean issue path.  The MMA warp runs its loops with all 32 lanes converged and elects ONE lane per instruction:
 // written like this the compiler keeps descriptors in uniform registers.  Issued from inside an `if (lane == 0)` region
 // every MMA was wrapped in an election loop with 2-3 R2UR transfers (~15 dependent instructions, ~130 cycles per MMA

@@ -146,6 +146,44 @@ __global__ void pack_offset_weight_kernel(const float* __restrict__ w, const flo
         if (i < rows) b_out[i] = (b != nullptr && srow >= 0) ? b[srow] : 0.f;      // i == row for chunk 0, tap 0, plane 0
     }
 }
+// CTA-pair DCN site (dcn_pair.cuh): conv_offset weights -> [half 2][cta 2][chunk of 32 ch][tap][k16 2][plane 2][56 rows][8] fp16.
+// Column j of offset half h (TMEM column 256 + 112 h + j) is deformable group h * dg/2 + j / 27, tap (j % 27) / 3, component
+// j % 3 (dh, dw, mask logit); CTA k of the pair holds the rows j in [56 k, 56 k + 56) (B operand split along N); columns
+// beyond (dg/2) * 27 are zero.  Source rows follow the reference: offsets g*18 + 2*tap + e, masks dg*18 + g*9 + tap
+// (arch_util.py:244-247, deform_conv_cuda_kernel.cu:600-613).  b_out[112 h + j] = bias of that column.
+__device__ __forceinline__ int dcn_pair_src_row(int h, int j, int dg) {
+    const int gph = dg >> 1;
+    if (j >= gph * 27) return -1;
+    const int g = h * gph + j / 27, rem = j % 27, t = rem / 3, e = rem % 3;
+    return e < 2 ? g * 18 + 2 * t + e : dg * 18 + g * 9 + t;
+}
+__global__ void pack_offset_weight_pair_kernel(const float* __restrict__ w, const float* __restrict__ b, int cin, int dg,
+                                               __half* __restrict__ out, float* __restrict__ b_out) {
+    const int nchunks = cin / 32;
+    const long long total = 4ll * nchunks * 9 * 4 * 56;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int row = r % 56; r /= 56;
+        const int plane = r % 4; r /= 4;              // k16 * 2 + plane-in-k16
+        const int tap = r % 9; r /= 9;
+        const int chunk = r % nchunks; r /= nchunks;
+        const int rank = r % 2; r /= 2;
+        const int h = static_cast<int>(r);
+        const int srow = dcn_pair_src_row(h, rank * 56 + row, dg);
+        H8 v;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ci = chunk * 32 + plane * 8 + e;
+            v.v[e] = srow >= 0 ? w[(static_cast<size_t>(srow) * cin + ci) * 9 + tap] : 0.f;
+        }
+        h8_store(out + i * 8, v);
+        if (i < 224) {
+            const int sb = dcn_pair_src_row(static_cast<int>(i) / 112, static_cast<int>(i) % 112, dg);
+            b_out[i] = (b != nullptr && sb >= 0) ? b[sb] : 0.f;
+        }
+    }
+}
 // Training step, data gradient: dgrad of a stride-1 convolution with weights w[co][ci][tap] is the convolution of grad_out
 // with W'[ci][co][taps-1-tap] (transposed, spatially flipped).  This packs W' straight from w in the CTA-pair layout
 // ([nt][rank 2][chunk of 32 grad_out channels][tap][k16 2][plane 2][BN/2 rows = input channels][8]); grad_out channels beyond

@@ -265,8 +265,9 @@ class DcnSite:
     wo/bo: conv_offset weight [dg*27, C, 3, 3] / bias, w/b: DCN weight [Cout, C, 3, 3] / bias (reference state_dict tensors).
     __call__(x, feat, out16, act, absmean): x = features to sample, feat = offset features, both NHWC fp16 Views.
 
-    mode "fused": ONE launch (dcn_site.cuh): conv_offset runs on the tensor cores inside the DCN kernel, offsets and masks
-    stay in tensor memory.  mode "split": conv_offset as a separate convolution writing the reference's fp32 NCHW
+    mode "pair" (default): ONE launch of the CTA-pair kernel (dcn_pair.cuh): conv_offset runs on the tensor cores inside the
+    DCN kernel, overlapped with the gather; offsets and masks stay in tensor memory.  mode "fused": the single-CTA form of
+    the same fusion (dcn_site.cuh; odd dg, more than one output-channel tile).  mode "split": conv_offset as a separate convolution writing the reference's fp32 NCHW
     offset/mask-logit tensor, then the same DCN kernel reading it (used when dg*27 > 224).  mode "legacy": the round-1
     pipeline (fp16 offset record, dcn_fused.cuh), kept for A/B timing only - its fp16 offsets miss the 1e-3 bar at
     multi-pixel offsets."""
@@ -275,12 +276,23 @@ class DcnSite:
         self.dg = dg
         self.C = w.shape[1]
         self.main = pack_conv(w, b)
-        mode = mode or os.environ.get("EDVR_B200_DCN_SITE", "fused")
+        mode = mode or os.environ.get("EDVR_B200_DCN_SITE", "pair")
+        if mode == "pair" and not (w.shape[2] == 3 and self.main.wpair is not None and
+                                   L.lib().eb_dcn_pair_supported(self.C, dg, self.main.BN, self.main.n_tiles)):
+            mode = "fused"
         if mode == "fused" and (dg * 27 > 224 or w.shape[2] != 3):
             mode = "split"
         self.mode = mode
         self.n_off = dg * 27
-        if mode == "fused":
+        if mode == "pair":
+            nbytes = L.lib().eb_dcn_pair_offset_weight_bytes(self.C)
+            self.wo_pack = torch.empty(nbytes // 2, dtype=torch.float16, device=w.device)
+            self.bo_cols = torch.empty(224, dtype=torch.float32, device=w.device)
+            with _Rec("pack_weight", 1):
+                L.check(L.lib().eb_dcn_pair_pack_offset_weight(L.ptr(wo.contiguous()), L.ptr(None if bo is None else bo.contiguous()),
+                                                               self.C, dg, L.ptr(self.wo_pack), L.ptr(self.bo_cols),
+                                                               L.stream_ptr()), "eb_dcn_pair_pack_offset_weight")
+        elif mode == "fused":
             nbytes = L.lib().eb_dcn_site_offset_weight_bytes(self.C)
             self.wo_pack = torch.empty(nbytes // 2, dtype=torch.float16, device=w.device)
             self.bo_cols = torch.empty(224, dtype=torch.float32, device=w.device)
@@ -308,7 +320,7 @@ class DcnSite:
 
     def arena_record(self, arena, feat):
         """Scratch for the offsets shared by all sites of an executor (engine._Arena); None when nothing is materialised."""
-        if self.mode == "fused":
+        if self.mode in ("pair", "fused"):
             return None
         if self.mode == "split":
             return arena.f32("offraw", feat.N, self.n_off, feat.H, feat.W)
@@ -326,6 +338,13 @@ class DcnSite:
             return
         e = _epi(pc.b, act, out16, out_nchw=out_nchw, nchw_C=pc.cout)
         am = None if absmean is None else absmean.data_ptr()
+        if self.mode == "pair":
+            with _Rec("dcn_site", 1, flops + 2.0 * N * H * W * self.n_off * pc.cin * 9, f"{N}x{H}x{W} C{x.C} pair"):
+                L.check(L.lib().eb_dcn_site_pair(L.ptr(x.t), x.pix_stride, x.ch_off, N, H, W, x.C, self.dg,
+                                                 L.ptr(feat.t), feat.pix_stride, feat.ch_off, L.ptr(self.wo_pack),
+                                                 L.ptr(self.bo_cols), L.ptr(pc.wpair), pc.BN, ctypes.byref(e), am,
+                                                 L.stream_ptr()), "eb_dcn_site_pair")
+            return
         if self.mode == "split":
             raw = record if record is not None else self._raw(N, H, W, feat.t.device)
             conv2d(self.offset, [feat], act=ACT_NONE, out_nchw=raw, nchw_C=self.n_off)

@@ -157,6 +157,19 @@ int eb_dcn_site(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int
                 const void* feat, int f_pix_stride, int f_ch_off, const void* wo_pack, const float* bo_cols,
                 const void* wpack, int BN, int n_tiles_n, const eb_epilogue_t* epi, float* absmean, void* stream);
 
+/* ---- CTA-pair form of the fused DCN site (csrc/dcn_pair.cuh): same operation as eb_dcn_site with feat != NULL
+ * (DCNv2Pack.forward, arch_util.py:243-257), issued by clusters of two CTAs that split both weight matrices, with the
+ * conv_offset GEMM of the next half tile overlapping the gather of the current one.  Needs an even dg with (dg/2)*27 <= 112,
+ * C % 64 == 0, C/dg = 8 or a multiple of 16, one output-channel tile (Cout = BN <= 128): eb_dcn_pair_supported() == 1.
+ * wpair: the DCN weights packed by eb_pack_weight_pair (n_tiles_n = 1); wo_pack / bo_cols from eb_dcn_pair_pack_offset_weight. */
+int eb_dcn_pair_supported(int C, int dg, int BN, int n_tiles_n);
+size_t eb_dcn_pair_offset_weight_bytes(int C);
+int eb_dcn_pair_pack_offset_weight(const float* wo /* [dg*27][C][3][3] */, const float* bo /* [dg*27] or NULL */, int C,
+                                   int dg, void* wo_pack, float* bo_cols /* [224] */, void* stream);
+int eb_dcn_site_pair(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
+                     const void* feat, int f_pix_stride, int f_ch_off, const void* wo_pack, const float* bo_cols,
+                     const void* wpair, int BN, const eb_epilogue_t* epi, float* absmean, void* stream);
+
 /* ---- DCNv2 reference-layout operator (fp32 NCHW in / out) ------------------------------ */
 size_t eb_mdcn_forward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw);
 int eb_mdcn_forward(const float* x, const float* offset, const float* mask, const float* weight,

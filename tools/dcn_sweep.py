@@ -41,7 +41,7 @@ def parity(sigma, N=2, C=128, H=18, W=23, dg=8):
     site(ops.nchw_to_nhwc(x.cuda()), ops.nchw_to_nhwc(feat.cuda()), out)
     got = ops.nhwc_to_nchw(out).cpu()
     d = (got - ref).double()
-    return {"sigma": sigma, "offset_absmean": float(off.abs().mean()),
+    return {"sigma": sigma, "shape": [N, C, H, W, dg], "offset_absmean": float(off.abs().mean()),
             "max_rel": float(d.abs().max() / ref.abs().max()), "l2_rel": float(d.norm() / ref.double().norm())}
 
 
@@ -79,15 +79,16 @@ def main():
     ap.add_argument("--n", default="28,4")
     ap.add_argument("--sigmas", default="0.02,3,10")
     ap.add_argument("--json", default=os.path.join(ROOT, "gpurun_out", "dcn_sweep.json"))
-    ap.add_argument("--modes", default="fused,split,legacy", help="ops.DcnSite modes to compare")
+    ap.add_argument("--modes", default="pair,fused,legacy", help="ops.DcnSite modes to compare")
     a = ap.parse_args()
     res = {"parity": [], "timing": []}
     for mode in a.modes.split(","):
         os.environ["EDVR_B200_DCN_SITE"] = mode
         for s in [float(v) for v in a.sigmas.split(",")]:
-            r = dict(parity(s), mode=mode)
-            print("parity", r, flush=True)
-            res["parity"].append(r)
+            for shape in ((2, 128, 18, 23, 8), (1, 64, 16, 24, 8), (3, 64, 21, 9, 4)):
+                r = dict(parity(s, *shape), mode=mode)
+                print("parity", r, flush=True)
+                res["parity"].append(r)
     for n in [int(v) for v in a.n.split(",")]:
         for mode in a.modes.split(","):
             os.environ["EDVR_B200_DCN_SITE"] = mode

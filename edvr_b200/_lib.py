@@ -8,6 +8,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EDVR_B200_LIB", os.path.join(_HERE, "libedvr_b200.so"))   # override: A/B-test a build
+if os.environ.get("EDVR_B200_LIB"):      # development builds (e.g. the -DDP_PROF timing build of tools/dp_prof.py)
+    LIB_PATH = os.environ["EDVR_B200_LIB"]
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_DCN_PACK, ACT_SIGMOID = 0, 1, 2, 3, 4
 OUT_SAME, OUT_PIXSHUF2, OUT_STRIDE2 = 0, 1, 2
@@ -57,6 +59,7 @@ _SIGS = {
                             c_void_p, c_void_p, c_ll, c_ll, c_int,
                             c_void_p, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p, c_void_p]),
+    "eb_dcn_pair_prof_read": (c_int, [c_void_p]),
     "eb_dcn_pair_supported": (c_int, [c_int] * 4),
     "eb_dcn_pair_offset_weight_bytes": (c_size_t, [c_int]),
     "eb_dcn_pair_pack_offset_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),

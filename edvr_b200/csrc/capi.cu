@@ -784,7 +784,7 @@ int eb_dcn_pair_supported(int C, int dg, int BN, int n_tiles_n) {
     return 1;
 }
 
-size_t eb_dcn_pair_offset_weight_bytes(int C) { return static_cast<size_t>(4) * (C / 32) * 9 * DP_WO_STAGE; }
+size_t eb_dcn_pair_offset_weight_bytes(int C) { return static_cast<size_t>(4) * (C / 32) * 9 * DP_WO_TAP; }
 
 int eb_dcn_pair_pack_offset_weight(const float* wo, const float* bo, int C, int dg, void* wo_pack, float* bo_cols, void* stream) {
     if (!wo || !wo_pack || !bo_cols) return fail(EB_ERR_NULLPTR, "dcn_pair_pack: null pointer");
@@ -793,6 +793,22 @@ int eb_dcn_pair_pack_offset_weight(const float* wo, const float* bo, int C, int 
     pack_offset_weight_pair_kernel<<<grid_1d(groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         wo, bo, C, dg, static_cast<__half*>(wo_pack), bo_cols);
     return check_launch("pack_offset_weight_pair");
+}
+
+// Role timing counters of dcn_pair_kernel (library built with -DDP_PROF; otherwise reads zeros): copies the 32 counters to
+// `host` (synchronises the device) and clears them.
+static unsigned long long* dp_prof_buffer() {
+    static unsigned long long* buf = nullptr;
+    if (!buf && cudaMalloc(&buf, 32 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(buf, 0, 32 * sizeof(unsigned long long));
+    return buf;
+}
+int eb_dcn_pair_prof_read(unsigned long long* host) {
+    if (!host) return fail(EB_ERR_NULLPTR, "dcn_pair_prof_read: null pointer");
+    unsigned long long* buf = dp_prof_buffer();
+    if (!buf) return fail(EB_ERR_LAUNCH, "dcn_pair_prof_read: no buffer");
+    if (cudaMemcpy(host, buf, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(EB_ERR_LAUNCH, "dcn_pair_prof_read: copy");
+    cudaMemset(buf, 0, 32 * sizeof(unsigned long long));
+    return EB_OK;
 }
 
 int eb_dcn_site_pair(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
@@ -824,6 +840,13 @@ int eb_dcn_site_pair(const void* x, int x_pix_stride, int x_ch_off, int N, int H
     if (!nchw && (!P.epi.out16 || P.epi.out32 || P.epi.res32 || P.epi.res16)) return fail(EB_ERR_UNSUPPORTED, "dcn_site_pair: NHWC fp16 output only");
     PP.absmean = absmean;
     PP.f_ch_off = f_ch_off; PP.wo_pack = static_cast<const __half*>(wo_pack); PP.bo = bo_cols;
+    { const char* e = getenv("EDVR_B200_DP_DBG"); PP.dbg = e ? atoi(e) : 0; }      // profiling ablations, results are wrong when set
+    { const char* e = getenv("EDVR_B200_DP_HINT_CRIT"); PP.hint_crit = e ? atoi(e) : 0; }
+    { const char* e = getenv("EDVR_B200_DP_HINT_IDLE"); PP.hint_idle = e ? atoi(e) : 2000; }
+    { const char* e = getenv("EDVR_B200_DP_HINT_GATHER"); PP.hint_gather = e ? atoi(e) : 0; }
+#ifdef DP_PROF
+    PP.prof = dp_prof_buffer();
+#endif
     {
         const cuuint64_t ps = static_cast<cuuint64_t>(x_pix_stride);
         const cuuint64_t dims[4] = {ps, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
@@ -856,7 +879,7 @@ int eb_dcn_site_pair(const void* x, int x_pix_stride, int x_ch_off, int N, int H
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(EB_ERR_LAUNCH, "dcn_site_pair: weight tensor map failed (%d)", static_cast<int>(r));
-        const cuuint64_t dims_o[2] = {256, static_cast<cuuint64_t>(4) * (C / 32) * 9 * (DP_WO_STAGE / 512)};
+        const cuuint64_t dims_o[2] = {256, static_cast<cuuint64_t>(4) * (C / 32) * 3 * (DP_WO_STAGE / 512)};
         const cuuint32_t box_o[2] = {256, DP_WO_STAGE / 512};
         r = enc(&PP.tmap_wo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(wo_pack), dims_o, strides, box_o, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -77,6 +77,30 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_t<0>(bar, parity); }
 
+// Wait with a suspend-time hint (nanoseconds, run-time value; 0 = the plain loop above).  Without a hint try_wait gives up
+// after ~70 cycles and the loop around it re-issues ~8 instructions: nine waiting warps of the CTA-pair DCN kernel (issuers,
+// producers, forwarder, epilogue) spent a quarter of the SM's issue slots spinning while the 16 gather warps were issue
+// bound (profiles/r02_ncu_dcn_pair_v2: 60 % of all executed instructions were wait loops).  With a hint the thread sleeps in
+// the SYNCS unit until the phase completes or the time is up.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    if (hint_ns == 0) { mbar_wait_t<0>(bar, parity); return; }
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(hint_ns)
+            : "memory");
+        if (done) break;
+        if (spin == 64) t0 = clock64();
+        if (spin > 64 && (spin & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
 // Same, observing arrivals made by the other CTA of the cluster (acquire at cluster scope).
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);

@@ -169,6 +169,8 @@ int eb_dcn_pair_pack_offset_weight(const float* wo /* [dg*27][C][3][3] */, const
 int eb_dcn_site_pair(const void* x, int x_pix_stride, int x_ch_off, int N, int H, int W, int C, int dg,
                      const void* feat, int f_pix_stride, int f_ch_off, const void* wo_pack, const float* bo_cols,
                      const void* wpair, int BN, const eb_epilogue_t* epi, float* absmean, void* stream);
+/* development aid: per-role wait-time counters of the pair kernel (all zero unless the library was built with -DDP_PROF) */
+int eb_dcn_pair_prof_read(unsigned long long* host32);
 
 /* ---- DCNv2 reference-layout operator (fp32 NCHW in / out) ------------------------------ */
 size_t eb_mdcn_forward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw);

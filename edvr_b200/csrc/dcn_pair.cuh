@@ -18,9 +18,9 @@
 //      tensor cores refill half h for tile T+1 as soon as the gather of tile T has read it: phase A of the next tile
 //      overlaps phase B of this one with no extra tensor memory (2 x 128 accumulator + 2 x 112 offset columns = 480).
 //      Two issuer warps (one per phase) feed the tensor pipe independently.
-//   3. The sampling window is staged per 32-channel chunk ({32 ch, 24 x, 27 y} box, 64-byte TMA swizzle): half the bytes
-//      per buffer of the 64-channel window, which pays for the second staging ring AND for a wider margin (+-6 px in x,
-//      +-4 px in y served from shared memory instead of +-3).  A (chunk, tap) stage is gathered by 8 warps; the two
+//   3. The sampling window is staged per 32-channel chunk ({32 ch, 24 x, 31 y} box, 64-byte TMA swizzle): half the bytes
+//      per buffer of the 64-channel window, which pays for the second staging ring AND for a wider margin (-6 .. +7 px in x,
+//      +-6 px in y served from shared memory instead of +-3).  A (chunk, tap) stage is gathered by 8 warps; the two
 //      groups of 8 gather warps take alternate stages.
 // Thread mapping of the gather: lane = output pixel = TMEM lane; warp (q, kp) covers TMEM lane quarter q and the K-atom
 // pair kp (16 channels) of the 32-channel chunk; the (dh, dw, mask logit) triple of (pixel, group, tap) comes straight
@@ -48,13 +48,22 @@ namespace eb {
 #define DP_FLUSH(IDX_, VAR_) do { } while (0)
 #endif
 
-constexpr int DP_RY = 3;                                   // rows of offset served from shared memory above / below the 3x3 reach
+#ifndef DP_CFG_RY          // development overrides (nvcc -DDP_CFG_...): A/B builds of the ring depths and the window margin
+#define DP_CFG_RY 6
+#endif
+#ifndef DP_CFG_A_STAGES
+#define DP_CFG_A_STAGES 4
+#endif
+#ifndef DP_CFG_WO_STAGES
+#define DP_CFG_WO_STAGES 4
+#endif
+constexpr int DP_RY = DP_CFG_RY;                                   // rows of offset served from shared memory above / below the 3x3 reach
 constexpr int DP_XL = 6;                                   // columns to the left (to the right: DP_WW - 11 - DP_XL = 7)
 constexpr int DP_WW = 24;                                  // window columns; a multiple of 8 keeps the swizzle phase of row y+1
-constexpr int DP_WH = DC_TILE_H + 3 + 2 * DP_RY;           // 27 rows
+constexpr int DP_WH = DC_TILE_H + 3 + 2 * DP_RY;           // 31 rows
 constexpr int DP_WIN_TX = DP_WH * DP_WW * 64;              // bytes one window box delivers (32 channels per pixel)
 constexpr int DP_WIN_BYTES = ((DP_WIN_TX + 1023) / 1024) * 1024;
-constexpr int DP_A_STAGES = 6;                             // gathered operand: (32-channel chunk, tap) = 4 K-atom planes x 128 px; the
+constexpr int DP_A_STAGES = DP_CFG_A_STAGES;                             // gathered operand: (32-channel chunk, tap) = 4 K-atom planes x 128 px; the
                                                            // DCN weights of the stage travel in the same ring slot (one barrier pair)
 constexpr int DP_A_LBO = 128 * 16;
 constexpr int DP_A_STAGE = 4 * DP_A_LBO;                   // 8192
@@ -68,7 +77,7 @@ constexpr int DP_WO_TAP = 4 * DP_WO_ROWS * 16;             // 3584: (32-channel 
 constexpr int DP_WO_STAGE = 3 * DP_WO_TAP;                 // 10752: three taps per stage - one barrier round trip (~90 cycles for an
                                                            // already-complete try_wait) per 6 MMAs; per-tap stages left the A issuer
                                                            // wait-bound at ~150 cycles per 112 cycles of MMA work (r02_ncu_dcn_pair_v2)
-constexpr int DP_WO_STAGES = 4;
+constexpr int DP_WO_STAGES = DP_CFG_WO_STAGES;
 constexpr int DP_THREADS = 32 * 25;   // warps: 0 B-side producer, 1 B issuer, 2-5 epilogue, 6-21 gather, 22 forwarder, 23 A-side producer, 24 A issuer
 constexpr int DP_MISC_BYTES = 128 * 4 + 256 * 4 + 1024;    // DCN bias, conv_offset bias, barriers
 constexpr int DP_SMEM_BYTES = 2 * DP_WIN_BYTES + DP_A_STAGES * DP_A_STAGE + DP_W_STAGES * DP_W_STAGE + DP_F_STAGES * DP_F_STAGE +

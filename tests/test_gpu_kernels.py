@@ -538,13 +538,17 @@ def test_empty_batch_is_noop(ops):
 
 
 @pytest.mark.parametrize("sigma", [0.02, 3.0, 10.0])
-def test_dcn_site_fused_path_matches_oracle(ops, sigma):
+@pytest.mark.parametrize("mode,shape", [("pair", (2, 128, 18, 23, 8)),      # EDVR-L geometry, two channel chunks per offset half
+                                        ("pair", (1, 64, 16, 24, 8)),       # EDVR-M: 8 channels per group, odd tile count (dead tile)
+                                        ("pair", (3, 64, 21, 9, 4)),        # 4 groups, ragged tiles
+                                        ("fused", (2, 128, 18, 23, 8))])    # single-CTA form (odd dg / several output tiles)
+def test_dcn_site_fused_path_matches_oracle(ops, sigma, mode, shape):
     """Production DCN site (ops.DcnSite: conv_offset -> offsets + sigmoid(mask) -> deformable conv) at sampling offsets of
     ~N(0, sigma^2) pixels - near zero like a fresh model, and multi-pixel like a trained one (the reference warns at a mean
     of 50, arch_util.py:249-253).  The oracle gets the offsets the kernel computes (fp16-rounded conv_offset operands, exact
     accumulation), so the bound covers everything from the offset record on: 1e-3 (north_star)."""
     from oracle import dcn_oracle
-    N, C, H, W, dg = 2, 128, 18, 23, 8
+    N, C, H, W, dg = shape
     g = torch.Generator().manual_seed(2)
     x = torch.randn(N, C, H, W, generator=g)
     feat = torch.randn(N, C, H, W, generator=g)
@@ -556,7 +560,8 @@ def test_dcn_site_fused_path_matches_oracle(ops, sigma):
     raw = F.conv2d(feat.half().double(), wo.half().double(), bo.double(), padding=1).float()
     off, mask = raw[:, :dg * 18].contiguous(), torch.sigmoid(raw[:, dg * 18:]).contiguous()
     ref = dcn_oracle.forward(x.numpy(), off.numpy(), mask.numpy(), w.numpy(), b.numpy(), 1, 1, 1, 1, dg)
-    site = ops.DcnSite(wo.cuda(), bo.cuda(), w.cuda(), b.cuda(), dg)
+    site = ops.DcnSite(wo.cuda(), bo.cuda(), w.cuda(), b.cuda(), dg, mode=mode)
+    assert site.mode == mode
     acc = torch.zeros(1, device="cuda")
     out = ops.new_act(N, H, W, C)
     site(ops.nchw_to_nhwc(x.cuda()), ops.nchw_to_nhwc(feat.cuda()), out, absmean=acc)

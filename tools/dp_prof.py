@@ -22,6 +22,14 @@ if "--build" in sys.argv:
     r = subprocess.run(cmd, capture_output=True, text=True)
     print(r.stderr[-2000:] if r.returncode else "built " + PROF_LIB)
     sys.exit(r.returncode)
+if "--build-variant" in sys.argv:        # python tools/dp_prof.py --build-variant NAME -DDP_CFG_A_STAGES=4 ...
+    from edvr_b200 import build as b
+    i = sys.argv.index("--build-variant")
+    out = os.path.join(ROOT, "edvr_b200", f"libedvr_b200_{sys.argv[i + 1]}.so")
+    cmd = [b.NVCC] + b.FLAGS + sys.argv[i + 2:] + ["-o", out, os.path.join(b.CSRC, "capi.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    print(r.stderr[-2000:] if r.returncode else "built " + out)
+    sys.exit(r.returncode)
 
 os.environ["EDVR_B200_LIB"] = PROF_LIB
 os.environ["EDVR_B200_DCN_SITE"] = "pair"

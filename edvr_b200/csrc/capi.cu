@@ -895,10 +895,12 @@ int eb_dcn_site_pair(const void* x, int x_pix_stride, int x_ch_off, int N, int H
     cfg.blockDim = dim3(DP_THREADS);
     cfg.dynamicSmemBytes = DP_SMEM_BYTES;
     cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see pdl_wait() in dcn_pair.cuh
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = getenv("EDVR_B200_NO_PDL") ? 1 : 2;
     cudaError_t lerr = cudaSuccess;
     const bool two = P.cpg == 8;
 #define EB_LAUNCH_DP(EK_)                                                                          \
@@ -1235,9 +1237,12 @@ int eb_upsample2x(const void* src, int sps, int sco, void* dst, int dps, int dco
         return fail(EB_ERR_ALIGNMENT, "upsample2x: bad view");
     if (N < 0 || H < 1 || W < 1) return fail(EB_ERR_INVALID_SHAPE, "upsample2x: shape");
     if (N == 0) return EB_OK;
-    const long long items = static_cast<long long>(N) * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<grid_1d(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __half*>(src), sps, sco, static_cast<__half*>(dst), dps, dco, N, H, W, C, mul,
+    const long long per_img = static_cast<long long>(H) * W * (C / 8);
+    if (per_img > 0x7fffffffll || N > 65535) return fail(EB_ERR_INVALID_SHAPE, "upsample2x: image too large for 32-bit indexing");
+    const long long blocks = (per_img + 255) / 256;
+    const dim3 grid(static_cast<unsigned>(blocks < 65535 * 4 ? blocks : 65535 * 4), static_cast<unsigned>(N));
+    upsample2x_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(src), sps, sco, static_cast<__half*>(dst), dps, dco, H, W, C, mul,
         static_cast<const __half*>(add), aps, aco);
     return check_launch("upsample2x");
 }

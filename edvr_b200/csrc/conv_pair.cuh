@@ -259,19 +259,26 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                 const int tx = (t % tiles_x2) * 2 + static_cast<int>(rank), ty = (t / tiles_x2) % tiles_y;
                 const int img = t / (tiles_x2 * tiles_y);
                 const uint32_t ab = acc_it & 1u;
-                mbar_wait_warp(&acc_full[ab], (acc_it >> 1) & 1u);
-                tc_fence_after_sync();
                 const int y0 = ty * CV_TILE + 4 * q, x0 = tx * CV_TILE + 8 * sub;
                 const int y = y0 + (lane >> 3);
                 const int x = x0 + (lane & 7);
                 const bool valid = (y < P.H) && (x < P.W) && !(P.dbg & 1);
                 const bool box_ok = (y0 < P.H) && (x0 < P.W) && !(P.dbg & 1);          // warp-uniform
+                float4 rpre_a[8], rpre_b[8];
+                const bool pre_ok = !(P.dbg & 4) && ((EK == EK_F32 && P.epi.res32 != nullptr && P.epi.f32_blocked != 0) ||
+                                                     (EK == EK_PLAIN && P.epi.res16 != nullptr));
+                auto prefetch = [&](int c0, float4 (&r)[8]) {
+                    if (EK == EK_F32) epi_prefetch_res32_blocked(P.epi, img, y, x, c0, valid, r);
+                    else epi_prefetch_res16(P.epi, img, y, x, c0, valid, r);
+                };
+                if ((EK == EK_F32 || EK == EK_PLAIN) && pre_ok) prefetch(nt * P.BN, rpre_a);
+                mbar_wait_warp(&acc_full[ab], (acc_it >> 1) & 1u);
+                tc_fence_after_sync();
                 const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + ab * 256u + sub * 128u;
-#pragma unroll 1
-                for (int cc = 0; cc < ((P.dbg & 4) ? 0 : P.BN); cc += 32) {
+                auto do_chunk = [&](int cc, const float4* pre) {
                     float v[32];
                     tmem_ld32(t0 + cc, v);
-                    epi_store32<EK, TMA_OUT>(P.epi, has_bias ? bias_s - nt * P.BN : nullptr, v, img, y, x, nt * P.BN + cc, valid, abs_ptr);
+                    epi_store32<EK, TMA_OUT>(P.epi, has_bias ? bias_s - nt * P.BN : nullptr, v, img, y, x, nt * P.BN + cc, valid, abs_ptr, pre);
                     if (TMA_OUT && EK == EK_PIXSHUF) {
                         // PixelShuffle(2): conv channel 4k + 2i + j of pixel (y, x) is output channel k of pixel (2y+i, 2x+j)
                         // (edvr_arch.py:351,410-411).  Staging = the 8 x 16 output pixels of this warp, 8 channels (16 B) each,
@@ -317,6 +324,24 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const __grid_c
                             bulk_commit_group();
                         }
                     }
+                
+                };
+                const int bn_epi = (P.dbg & 4) ? 0 : P.BN;
+                if ((EK == EK_F32 || EK == EK_PLAIN) && pre_ok) {
+                    // residual stream (blocked fp32 of the trunk, fp16 elsewhere): chunk c+1's residual is in flight while chunk c
+                    // is processed (two static register buffers; the first one was requested before the accumulator wait)
+#pragma unroll 1
+                    for (int cc = 0; cc < bn_epi; cc += 64) {
+                        if (cc + 32 < bn_epi) prefetch(nt * P.BN + cc + 32, rpre_b);
+                        do_chunk(cc, rpre_a);
+                        if (cc + 32 < bn_epi) {
+                            if (cc + 64 < bn_epi) prefetch(nt * P.BN + cc + 64, rpre_a);
+                            do_chunk(cc + 32, rpre_b);
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int cc = 0; cc < bn_epi; cc += 32) do_chunk(cc, nullptr);
                 }
                 tc_fence_before_sync();
                 __syncwarp();

@@ -177,6 +177,10 @@ __global__ void __launch_bounds__(DP_THREADS, 1) dcn_pair_kernel(const __grid_co
     cluster_sync_all();                    // both CTAs' barriers and tensor memory exist before any remote traffic
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch (same contract as conv_pair.cuh): the next kernel of the stream may start its prologue on
+    // SMs this grid has left; everything above touched only constants, everything below waits for the predecessor.
+    pdl_trigger();
+    pdl_wait();
 
     // this CTA's share of a two-CTA stage: one arrival + its byte count on the EVEN CTA's barrier
     auto expect_on_leader = [&](uint64_t* bar, uint32_t bytes) {

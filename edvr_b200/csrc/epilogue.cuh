@@ -52,10 +52,40 @@ __host__ __device__ __forceinline__ long long blocked32_block(int img, int y, in
 // v: 32 consecutive accumulator channels [c0, c0+32) of output pixel (img, y, x).
 // Every lane of the warp must call this (shuffles inside); `valid` masks the memory traffic.
 // EXT16: the caller stores the fp16 NHWC copy itself (TMA store in conv_pair.cuh); v[] holds the final values on return.
+// Residual prefetch for the blocked fp32 stream (trunk blocks): the eight float4 slots epi_store32 would read for channels
+// [c0, c0+32) of pixel (img, y, x), issued early so that their DRAM latency overlaps the wait for the accumulator and the
+// previous chunk's stores (the trunk's conv2 launches were epilogue-latency bound: tensor pipe 39 % busy, DRAM 49 %).
+__device__ __forceinline__ void epi_prefetch_res32_blocked(const EpiParams& p, int img, int y, int x, int c0, bool valid,
+                                                           float4 (&r)[8]) {
+    if (!valid) return;
+    const float4* src = reinterpret_cast<const float4*>(
+        p.res32 + blocked32_block(img, y, x, (p.res_ch_off + c0) >> 5, p.H, p.W, p.res_pix_stride));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r[q] = __ldg(src + q * 32);
+}
+
+// Same for the fp16 residual of a ResidualBlockNoBN whose stream is fp16 (feature extraction, predeblur): the 64 bytes of
+// pixel (img, y, x), channels [c0, c0+32), land in r[0..3].
+__device__ __forceinline__ void epi_prefetch_res16(const EpiParams& p, int img, int y, int x, int c0, bool valid, float4 (&r)[8]) {
+    if (!valid) return;
+    const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+    const __half* src = p.res16 + pix * p.res_pix_stride + p.res_ch_off + c0;
+    uint4 u[4];
+    if (p.res16_wide) {
+        ldg_nc_v8(src, u[0], u[1]);
+        ldg_nc_v8(src + 16, u[2], u[3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[q] = ldg_nc_v4(src + q * 8);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = *reinterpret_cast<const float4*>(&u[q]);
+}
+
 template <int EK = EK_GENERIC, bool EXT16 = false>
 __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __restrict__ bias_s,
                                             float (&v)[32], int img, int y, int x, int c0,
-                                            bool valid, float* abs_sum = nullptr) {
+                                            bool valid, float* abs_sum = nullptr, const float4* res_pre = nullptr) {
     if (bias_s != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += bias_s[c0 + j];
@@ -87,7 +117,10 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
     if ((G || EK == EK_PLAIN) && p.res16 != nullptr) {
         const __half* r = p.res16 + pix * p.res_pix_stride + p.res_ch_off + c0;
         uint4 ru[4];
-        if (p.res16_wide) {     // lanes read different pixels: a 32-byte load halves the L1 wavefronts per byte
+        if (EK == EK_PLAIN && res_pre != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ru[q] = *reinterpret_cast<const uint4*>(&res_pre[q]);
+        } else if (p.res16_wide) {     // lanes read different pixels: a 32-byte load halves the L1 wavefronts per byte
             ldg_nc_v8(r, ru[0], ru[1]);
             ldg_nc_v8(r + 16, ru[2], ru[3]);
         } else {
@@ -105,7 +138,13 @@ __device__ __forceinline__ void epi_store32(const EpiParams& p, const float* __r
     // blocked fp32 stream: this thread's 32 channels are 8 float4 slots, 512 B apart, lanes 16 B apart
     const long long blk = ((G || EK == EK_F32) && p.f32_blocked)
         ? blocked32_block(img, y, x, (p.res_ch_off + c0) >> 5, p.H, p.W, p.res_pix_stride) : 0;
-    if ((G || EK == EK_F32) && p.res32 != nullptr) {
+    if (EK == EK_F32 && res_pre != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 f = res_pre[q];
+            v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+        }
+    } else if ((G || EK == EK_F32) && p.res32 != nullptr) {
         const float4* r = p.f32_blocked ? reinterpret_cast<const float4*>(p.res32 + blk)
                                         : reinterpret_cast<const float4*>(p.res32 + pix * p.res_pix_stride + p.res_ch_off + c0);
         const int rs = p.f32_blocked ? 32 : 1;          // float4 stride between consecutive 4-channel slots

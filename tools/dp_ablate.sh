@@ -1,10 +1,6 @@
 #!/bin/bash
-# dcn_pair: A/B of build variants (EDVR_B200_LIB) on one box
-for rep in 1 2; do
-for v in "" _cfgB _cfgE; do
-  for s in 0.02 3; do
-    echo -n "lib$v  "
-    EDVR_B200_LIB=$PWD/edvr_b200/libedvr_b200$v.so EDVR_B200_DCN_SITE=pair timeout 120 python tools/one_site.py 28 180 320 128 8 $s 3 2>&1 | tail -1 | cut -c1-120
-  done
-done
+# L2 set-aside for the trunk's fp32 residual stream: engine timing (cfg 3, B=4 and B=1) per set-aside size
+for mb in 0 32 48 64 80 96; do
+  echo -n "L2_PERSIST_MB=$mb  "
+  EDVR_B200_L2_PERSIST_MB=$mb timeout 200 python tools/time_engine.py --batches 4,1 --iters 20 2>&1 | tail -3 | tr '\n' ' ' | cut -c1-400; echo
 done

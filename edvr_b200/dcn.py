@@ -87,6 +87,21 @@ def mdcn_backward(x, offset, mask, weight, grad_out, with_bias, stride, padding,
 def _mdcn_backward_raw(x, offset, mask, weight, grad_out, with_bias, stride, padding, dilation, groups, dg):
     N, C, H, W = x.shape
     Cout, _, kh, kw = weight.shape
+    if groups > 1:          # composed from per-group calls (see ops.group_slices); shared deformable groups accumulate
+        gx, gw = torch.empty_like(x), torch.empty_like(weight)
+        goff, gmask = torch.zeros_like(offset), torch.zeros_like(mask)
+        gb = torch.zeros(Cout, dtype=torch.float32, device=x.device) if with_bias else None
+        for gi in range(groups):
+            cs, os_, fs, ms, dgg = ops.group_slices(C, Cout, kh * kw, groups, dg, gi)
+            r = _mdcn_backward_raw(x[:, cs].contiguous(), offset[:, fs].contiguous(), mask[:, ms].contiguous(),
+                                   weight[os_].contiguous(), grad_out[:, os_].contiguous(), with_bias, stride, padding,
+                                   dilation, 1, dgg)
+            gx[:, cs], gw[os_] = r[0], r[3]
+            goff[:, fs] += r[1]
+            gmask[:, ms] += r[2]
+            if with_bias:
+                gb[os_] = r[4]
+        return gx, goff, gmask, gw, gb
     gx = torch.empty_like(x)
     goff = torch.empty_like(offset)
     gmask = torch.empty_like(mask)

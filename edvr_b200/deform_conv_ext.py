@@ -53,6 +53,11 @@ def modulated_deform_conv_forward(input, weight, bias, ones, offset, mask, outpu
         raise RuntimeError(f"Input shape and kernel channels wont match: ({C} vs {weight.shape[1] * group}).")
     x, w, off, m = _f32(input), _f32(weight), _f32(offset), _f32(mask)
     b = _f32(bias) if with_bias else None
+    if group > 1:           # deform_conv_cuda.cpp:536-568: one GEMM per weight group; composed from per-group calls
+        from . import ops
+        with torch.cuda.device(input.device):
+            output.copy_(ops.mdcn_forward(x, off, m, w, b, stride_h, pad_h, dilation_h, group, deformable_group))
+        return
     out32 = output if (output.dtype == torch.float32 and output.is_contiguous()) else torch.empty(
         output.shape, dtype=torch.float32, device=output.device)
     need = L.lib().eb_mdcn_forward_workspace(N, C, H, W, Cout, kernel_h, kernel_w)
@@ -82,16 +87,22 @@ def modulated_deform_conv_backward(input, weight, bias, ones, offset, mask, colu
     go = (grad_output.float() * sc).contiguous()
     inv = 1.0 / sc
     new = lambda t: torch.empty(t.shape, dtype=torch.float32, device=t.device)
-    gx, goff, gm = new(grad_input), new(grad_offset), new(grad_mask)
-    gw = torch.zeros(grad_weight.shape, dtype=torch.float32, device=grad_weight.device)
-    gb = torch.zeros(grad_bias.shape, dtype=torch.float32, device=grad_bias.device) if with_bias else None
-    need = L.lib().eb_mdcn_backward_workspace(N, C, H, W, Cout, kernel_h, kernel_w, stride_h, pad_h, dilation_h)
-    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
-    with torch.cuda.device(input.device):
-        L.check(L.lib().eb_mdcn_backward(L.ptr(x), L.ptr(off), L.ptr(m), L.ptr(w), L.ptr(go), L.ptr(gx), L.ptr(goff),
-                                         L.ptr(gm), L.ptr(gw), L.ptr(gb), N, C, H, W, Cout, kernel_h, kernel_w,
-                                         stride_h, pad_h, dilation_h, group, deformable_group, L.ptr(ws), ws.numel(),
-                                         L.stream_ptr()), "eb_mdcn_backward")
+    if group > 1:           # deform_conv_cuda.cpp:617-671 per weight group; composed from per-group calls
+        from .dcn import _mdcn_backward_raw
+        with torch.cuda.device(input.device):
+            gx, goff, gm, gw, gb = _mdcn_backward_raw(x, off, m, w, go, bool(with_bias), stride_h, pad_h, dilation_h, group,
+                                                      deformable_group)
+    else:
+        gx, goff, gm = new(grad_input), new(grad_offset), new(grad_mask)
+        gw = torch.zeros(grad_weight.shape, dtype=torch.float32, device=grad_weight.device)
+        gb = torch.zeros(grad_bias.shape, dtype=torch.float32, device=grad_bias.device) if with_bias else None
+        need = L.lib().eb_mdcn_backward_workspace(N, C, H, W, Cout, kernel_h, kernel_w, stride_h, pad_h, dilation_h)
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
+        with torch.cuda.device(input.device):
+            L.check(L.lib().eb_mdcn_backward(L.ptr(x), L.ptr(off), L.ptr(m), L.ptr(w), L.ptr(go), L.ptr(gx), L.ptr(goff),
+                                             L.ptr(gm), L.ptr(gw), L.ptr(gb), N, C, H, W, Cout, kernel_h, kernel_w,
+                                             stride_h, pad_h, dilation_h, group, deformable_group, L.ptr(ws), ws.numel(),
+                                             L.stream_ptr()), "eb_mdcn_backward")
     grad_input.copy_(gx * inv)                  # overwritten, like deform_conv_cuda.cpp:617-657
     grad_offset.copy_(goff * inv)
     grad_mask.copy_(gm * inv)
@@ -175,6 +186,17 @@ def deform_conv_forward(input, weight, offset, output, columns, ones, kW, kH, dW
     shape = (N, Cout, Ho, Wo) if input.dim() == 4 else (Cout, Ho, Wo)
     if tuple(output.shape) != shape:
         output.resize_(shape)
+    if group > 1:           # deform_conv_cuda.cpp:213-226: one GEMM per weight group; composed from per-group calls
+        from .ops import group_slices
+        parts = []
+        for gi in range(group):
+            cs, os_, fs, _ms, dgg = group_slices(C, Cout, kH * kW, group, deformable_group, gi)
+            part = torch.empty(N, Cout // group, Ho, Wo, dtype=torch.float32, device=input.device)
+            deform_conv_forward(x[:, cs].contiguous(), w[os_].contiguous(), off[:, fs].contiguous(), part, columns, ones, kW, kH,
+                                dW, dH, padW, padH, dilationW, dilationH, 1, dgg, im2col_step)
+            parts.append(part)
+        output.copy_(torch.cat(parts, 1).reshape(shape))
+        return 1
     out32, copy_back = _out_buf(output)
     need = L.lib().eb_mdcn_forward_workspace(N, C, H, W, Cout, kH, kW)
     ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
@@ -199,6 +221,22 @@ def deform_conv_backward_input(input, offset, gradOutput, gradInput, gradOffset,
         raise RuntimeError("im2col step must divide batchsize")
     Cout = weight.shape[0]
     x, w, off = _f32(input4), _f32(weight), _f32(offset4)
+    if group > 1:           # composed from per-group calls; deformable groups shared between weight groups accumulate
+        from .ops import group_slices
+        gx4 = torch.empty(input4.shape, dtype=torch.float32, device=input.device)
+        goff4 = torch.zeros(offset4.shape, dtype=torch.float32, device=input.device)
+        go4f = go4.float()
+        for gi in range(group):
+            cs, os_, fs, _ms, dgg = group_slices(C, Cout, kH * kW, group, deformable_group, gi)
+            xg, og = x[:, cs].contiguous(), off[:, fs].contiguous()
+            gxg, gog = torch.empty_like(xg), torch.empty_like(og)
+            deform_conv_backward_input(xg, og, go4f[:, os_].contiguous(), gxg, gog, w[os_].contiguous(), columns, kW, kH, dW, dH,
+                                       padW, padH, dilationW, dilationH, 1, dgg, im2col_step)
+            gx4[:, cs] = gxg
+            goff4[:, fs] += gog
+        gradInput.copy_(gx4.reshape(gradInput.shape))
+        gradOffset.copy_(goff4.reshape(gradOffset.shape))
+        return 1
     sc = _pow2_scale(go4)
     go = (go4.float() * sc).contiguous()
     gx = torch.empty(gradInput.shape, dtype=torch.float32, device=gradInput.device)
@@ -227,6 +265,17 @@ def deform_conv_backward_parameters(input, offset, gradOutput, gradWeight, colum
         raise RuntimeError("im2col step must divide batchsize")
     Cout = gradWeight.shape[0]
     x, off = _f32(input4), _f32(offset4)
+    if group > 1:           # deform_conv_cuda.cpp:455-470 per weight group; composed from per-group calls
+        from .ops import group_slices
+        go4f = go4.float()
+        for gi in range(group):
+            cs, os_, fs, _ms, dgg = group_slices(C, Cout, kH * kW, group, deformable_group, gi)
+            gwg = torch.zeros(gradWeight[os_].shape, dtype=torch.float32, device=gradWeight.device)
+            deform_conv_backward_parameters(x[:, cs].contiguous(), off[:, fs].contiguous(), go4f[:, os_].contiguous(), gwg,
+                                            columns, ones, kW, kH, dW, dH, padW, padH, dilationW, dilationH, 1, dgg, scale,
+                                            im2col_step)
+            gradWeight[os_] += gwg.to(gradWeight.dtype)
+        return 1
     sc = _pow2_scale(go4)
     go = (go4.float() * sc).contiguous()
     gw = torch.zeros(gradWeight.shape, dtype=torch.float32, device=gradWeight.device)

@@ -442,10 +442,36 @@ def tsa_modulate(feat, attn, attn_add, out16=None, out32=None):
                                         attn.C, 1 if blocked else 0, L.stream_ptr()), "eb_tsa_modulate")
 
 
+def group_slices(C, Cout, K, groups, dg, gi):
+    """Weight group gi of a grouped (deformable) convolution as a groups == 1 problem: (input channels, output channels,
+    offset channels, mask channels, deformable groups of the slice).  The reference runs one im2col over all channels and
+    one GEMM per weight group (deform_conv_cuda.cpp:536-568); its column rows of group gi belong to the deformable groups
+    below, which are whole groups when dg % groups == 0 and one shared group when groups % dg == 0."""
+    Cg, Og = C // groups, Cout // groups
+    if dg % groups == 0:
+        dgg = dg // groups
+        d0 = gi * dgg
+    elif groups % dg == 0:
+        dgg, d0 = 1, gi // (groups // dg)
+    else:
+        raise RuntimeError(f"edvr_b200: groups={groups} with deformable_groups={dg} (one must divide the other)")
+    return (slice(gi * Cg, (gi + 1) * Cg), slice(gi * Og, (gi + 1) * Og), slice(d0 * 2 * K, (d0 + dgg) * 2 * K),
+            slice(d0 * K, (d0 + dgg) * K), dgg)
+
+
 def mdcn_forward(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, workspace=None):
-    """Reference-layout operator (fp32 NCHW) through eb_mdcn_forward."""
+    """Reference-layout operator (fp32 NCHW) through eb_mdcn_forward.  Weight groups > 1 (deform_conv_cuda.cpp:536-568) are
+    composed from per-group calls on channel slices - EDVR itself always uses groups == 1."""
     N, C, H, W = x.shape
     Cout, _, kh, kw = weight.shape
+    if groups > 1:
+        outs = []
+        for gi in range(groups):
+            cs, os_, fs, ms, dgg = group_slices(C, Cout, kh * kw, groups, dg, gi)
+            outs.append(mdcn_forward(x[:, cs].contiguous(), offset[:, fs].contiguous(), mask[:, ms].contiguous(),
+                                     weight[os_].contiguous(), None if bias is None else bias[os_].contiguous(),
+                                     stride, padding, dilation, 1, dgg))
+        return torch.cat(outs, 1)
     Ho = (H + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1
     Wo = (W + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1
     out = torch.empty(N, Cout, Ho, Wo, dtype=torch.float32, device=x.device)

@@ -415,6 +415,43 @@ def test_autograd_function_matches_oracle(ops):
         modulated_deform_conv(x, off, mask, w, b, 1, 1, 1, 1, 8)
 
 
+@pytest.mark.parametrize("groups,dg", [(2, 2), (2, 4), (2, 1)])
+def test_weight_groups_match_oracle(ops, groups, dg):
+    """Weight groups > 1 (deform_conv_cuda.cpp:536-568: one GEMM per weight group over the rows of the shared im2col matrix):
+    DCNv2 forward + all five gradients through the autograd Function, and DCNv1 forward + gradients, against the C oracle
+    (itself checked against torchvision's grouped deform_conv2d in tests/test_oracle.py).  dg a multiple of groups, and
+    several weight groups sharing one deformable group (their offset / mask gradients add)."""
+    from oracle import dcn_oracle
+    from edvr_b200.dcn import deform_conv, modulated_deform_conv
+    N, C, H, W, Cout = 2, 128, 11, 13, 64
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(N, C, H, W, generator=g)
+    off = torch.randn(N, dg * 18, H, W, generator=g) * 2
+    mask = torch.sigmoid(torch.randn(N, dg * 9, H, W, generator=g))
+    w = (torch.rand(Cout, C // groups, 3, 3, generator=g) * 2 - 1) / (9 * C // groups) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    go = torch.randn(N, Cout, H, W, generator=g)
+    ts = [t.cuda().requires_grad_(True) for t in (x, off, mask, w, b)]
+    y = modulated_deform_conv(*ts, 1, 1, 1, groups, dg)
+    ref = dcn_oracle.forward(x.numpy(), off.numpy(), mask.numpy(), w.numpy(), b.numpy(), 1, 1, 1, groups, dg)
+    e = rel_err(y.detach().cpu(), ref)
+    assert e[0] < TOL and e[1] < TOL, e
+    y.backward(go.cuda())
+    grads = dcn_oracle.backward(x.numpy(), off.numpy(), mask.numpy(), w.numpy(), go.numpy(), True, 1, 1, 1, groups, dg)
+    for nm, t, r in zip(("gx", "goff", "gmask", "gw", "gb"), ts, grads):
+        e = rel_err(t.grad.cpu(), r)
+        assert e[0] < TOL and e[1] < TOL, (nm, e)
+    t1 = [t.cuda().requires_grad_(True) for t in (x, off, w)]
+    y1 = deform_conv(*t1, 1, 1, 1, groups, dg)
+    e = rel_err(y1.detach().cpu(), dcn_oracle.forward_v1(x.numpy(), off.numpy(), w.numpy(), (1, 1), (1, 1), (1, 1), groups, dg))
+    assert e[0] < TOL and e[1] < TOL, e
+    y1.backward(go.cuda())
+    grads1 = dcn_oracle.backward_v1(x.numpy(), off.numpy(), w.numpy(), go.numpy(), (1, 1), (1, 1), (1, 1), groups, dg)
+    for nm, t, r in zip(("gx", "goff", "gw"), t1, grads1):
+        e = rel_err(t.grad.cpu(), r)
+        assert e[0] < TOL and e[1] < TOL, ("v1 " + nm, e)
+
+
 # ---- DCNv1 (SURVEY §8 row a13): deform_conv_forward / backward_input / backward_parameters -------------------------
 V1_GPU_CASES = {  # N, C, H, W, Cout, dg, (kh, kw), stride, padding, dilation, offset scale
     "iso_dg8": (2, 64, 12, 14, 64, 8, (3, 3), (1, 1), (1, 1), (1, 1), 2.0),

@@ -437,7 +437,8 @@ def profile_step(eng, x):
         n_img = int(dcn_l1[0][2].split("x")[0])
         C = CFG3["num_feat"]
         alg = n_img * LR_H * LR_W * C * 2 * 3 + (C * C * 9 + 216 * C * 9) * 2
-        dcn = {"kernel": "dcn_site_kernel (L1 launches: conv_offset + offsets in TMEM + gather + DCN GEMM)", "launch_ms": ms,
+        kern = "dcn_pair_kernel" if " pair" in dcn_l1[0][2] else "dcn_site_kernel"
+        dcn = {"kernel": f"{kern} (L1 launches: conv_offset + offsets in TMEM + gather + DCN GEMM)", "launch_ms": ms,
                "images": n_img, "tflops": dcn_l1[0][1] / (ms * 1e9), "algorithmic_bytes": alg, "gbs": alg / (ms * 1e6),
                "survey_fp32_operator_bytes": n_img * 109.34e6, "share_of_step": agg["dcn_site"][0] / total}
     return {"shares": shares, "dcn": dcn,

@@ -465,44 +465,27 @@ __global__ void __launch_bounds__(DP_THREADS, 1) dcn_pair_kernel(const __grid_co
                 }
                 return out;
             };
-            // one 16-byte K atom (hi = 0 / 1 of the warp's pair) of one sample, any mix of in-window and far lanes
-            auto sample8_any = [&](const Geo& gq, uint32_t hi, int ch) -> uint4 {
-                uint4 u0, u1, u2, u3;
-                if (!gq.slow) {
-                    const uint32_t x16 = hi << 4;
-                    u0 = lds_v4(gq.a0 ^ x16);
-                    u1 = lds_v4(gq.a1 ^ x16);
-                    u2 = lds_v4((gq.a0 ^ x16) + DP_WW * 64);
-                    u3 = lds_v4((gq.a1 ^ x16) + DP_WW * 64);
-                } else {
-                    const int hl = gq.hw >> 16, wl = static_cast<int>(static_cast<short>(gq.hw & 0xffff));
-                    const bool t = hl >= 0, b = hl + 1 <= H - 1, l = wl >= 0, r = wl + 1 <= W - 1;
-                    const __half* base = ximg + hl * ixrow + wl * ixps + ch;
-                    u0 = ldg_nc_v4((t && l) ? base : zbuf);
-                    u1 = ldg_nc_v4((t && r) ? base + ixps : zbuf);
-                    u2 = ldg_nc_v4((b && l) ? base + ixrow : zbuf);
-                    u3 = ldg_nc_v4((b && r) ? base + ixrow + ixps : zbuf);
-                }
-                return blend(gq, u0, u1, u2, u3);
-            };
-            // both atoms of one sample when some lane of the warp left the window (the far lanes fetch a corner's 32 contiguous
-            // bytes with one load when the view allows it)
-            auto sample16_any = [&](const Geo& gq, int ch, uint4& v0, uint4& v1) {
-                if (!gq.slow || !wide) {
-                    v0 = sample8_any(gq, 0u, ch);
-                    v1 = sample8_any(gq, 1u, ch + 8);
-                    return;
-                }
+            // Far samples (offset beyond the staged window): the lane replaces the four corners it read from shared memory by
+            // global loads (zero buffer for corners outside the image - the reference's border rule).  Only the far lanes take
+            // the branch; the shared-memory reads and the blend stay warp-uniform.
+            auto far_corners = [&](const Geo& gq, int ch, uint4& u0, uint4& u1, uint4& u2, uint4& u3, uint4& t0, uint4& t1, uint4& t2,
+                                   uint4& t3, bool both) {
                 const int hl = gq.hw >> 16, wl = static_cast<int>(static_cast<short>(gq.hw & 0xffff));
                 const bool t = hl >= 0, b = hl + 1 <= H - 1, l = wl >= 0, r = wl + 1 <= W - 1;
                 const __half* base = ximg + hl * ixrow + wl * ixps + ch;
-                uint4 a0, a1, b0, b1, c0, c1, d0, d1;
-                ldg_nc_v8((t && l) ? base : zbuf, a0, a1);
-                ldg_nc_v8((t && r) ? base + ixps : zbuf, b0, b1);
-                ldg_nc_v8((b && l) ? base + ixrow : zbuf, c0, c1);
-                ldg_nc_v8((b && r) ? base + ixrow + ixps : zbuf, d0, d1);
-                v0 = blend(gq, a0, b0, c0, d0);
-                v1 = blend(gq, a1, b1, c1, d1);
+                const __half* p0 = (t && l) ? base : zbuf;
+                const __half* p1 = (t && r) ? base + ixps : zbuf;
+                const __half* p2 = (b && l) ? base + ixrow : zbuf;
+                const __half* p3 = (b && r) ? base + ixrow + ixps : zbuf;
+                if (both && wide) {          // the K-atom pair of a corner is 32 contiguous, aligned bytes
+                    ldg_nc_v8(p0, u0, t0); ldg_nc_v8(p1, u1, t1); ldg_nc_v8(p2, u2, t2); ldg_nc_v8(p3, u3, t3);
+                } else {
+                    u0 = ldg_nc_v4(p0); u1 = ldg_nc_v4(p1); u2 = ldg_nc_v4(p2); u3 = ldg_nc_v4(p3);
+                    if (both) {
+                        t0 = ldg_nc_v4(p0 == zbuf ? zbuf : p0 + 8); t1 = ldg_nc_v4(p1 == zbuf ? zbuf : p1 + 8);
+                        t2 = ldg_nc_v4(p2 == zbuf ? zbuf : p2 + 8); t3 = ldg_nc_v4(p3 == zbuf ? zbuf : p3 + 8);
+                    }
+                }
             };
 
             // The warp's stages of this tile, chunk by chunk: st = 9 * chunk + tap with st % 2 == wg, i.e. inside a chunk the taps
@@ -538,11 +521,12 @@ __global__ void __launch_bounds__(DP_THREADS, 1) dcn_pair_kernel(const __grid_co
                     const bool any_slow = __any_sync(0xffffffffu, q0.slow || (TWO && q1.slow));
                     uint4 v0, v1;
                     Geo n0 = q0, n1 = q1;
-                    if (!any_slow) {
-                        // every lane samples inside the window: eight conflict-free LDS.128, no divergence
+                    {
+                        // eight LDS.128 per lane (window pixel 0 for the lanes whose sample is far or invalid: harmless), conflict
+                        // free; far lanes then swap in their global corners
                         const uint32_t b0 = q0.a0, b1 = q0.a1, c0 = (TWO ? q1.a0 : q0.a0) ^ 16u, c1 = (TWO ? q1.a1 : q0.a1) ^ 16u;
-                        const uint4 u0 = lds_v4(b0), u1 = lds_v4(b1), u2 = lds_v4(b0 + DP_WW * 64), u3 = lds_v4(b1 + DP_WW * 64);
-                        const uint4 t0 = lds_v4(c0), t1 = lds_v4(c1), t2 = lds_v4(c0 + DP_WW * 64), t3 = lds_v4(c1 + DP_WW * 64);
+                        uint4 u0 = lds_v4(b0), u1 = lds_v4(b1), u2 = lds_v4(b0 + DP_WW * 64), u3 = lds_v4(b1 + DP_WW * 64);
+                        uint4 t0 = lds_v4(c0), t1 = lds_v4(c1), t2 = lds_v4(c0 + DP_WW * 64), t3 = lds_v4(c1 + DP_WW * 64);
                         if (more) {          // geometry of the warp's next stage while the corners are in flight
                             fetch_wait(pv0, pv1);
                             r0 = fetch_finish(col0 + 3 * (tap + 2), pv0);
@@ -551,19 +535,17 @@ __global__ void __launch_bounds__(DP_THREADS, 1) dcn_pair_kernel(const __grid_co
                             n0 = geometry(r0, tap + 2, win);
                             if (TWO) n1 = geometry(r1, tap + 2, win);
                         }
+                        if (any_slow) {
+                            if (TWO) {
+                                uint4 d0, d1, d2, d3;
+                                if (q0.slow) far_corners(q0, ch0, u0, u1, u2, u3, d0, d1, d2, d3, false);
+                                if (q1.slow) far_corners(q1, ch0 + 8, t0, t1, t2, t3, d0, d1, d2, d3, false);
+                            } else if (q0.slow) {
+                                far_corners(q0, ch0, u0, u1, u2, u3, t0, t1, t2, t3, true);
+                            }
+                        }
                         v0 = blend(q0, u0, u1, u2, u3);
                         v1 = blend(TWO ? q1 : q0, t0, t1, t2, t3);
-                    } else {
-                        if (TWO) { v0 = sample8_any(q0, 0u, ch0); v1 = sample8_any(q1, 1u, ch0 + 8); }
-                        else sample16_any(q0, ch0, v0, v1);
-                        if (more) {
-                            fetch_wait(pv0, pv1);
-                            r0 = fetch_finish(col0 + 3 * (tap + 2), pv0);
-                            if (TWO) r1 = fetch_finish(col0 + 27 + 3 * (tap + 2), pv1);
-                            if (tap + 4 < 9) { fetch_issue(col0 + 3 * (tap + 4), pv0); if (TWO) fetch_issue(col0 + 27 + 3 * (tap + 4), pv1); }
-                            n0 = geometry(r0, tap + 2, win);
-                            if (TWO) n1 = geometry(r1, tap + 2, win);
-                        }
                     }
                     if (more && count_abs) abs_sum += fabsf(r0.dh) + fabsf(r0.dw) + (TWO ? fabsf(r1.dh) + fabsf(r1.dw) : 0.f);
                     DP_TIMED(pt_empty, mbar_wait_hint(&empty[as], pa ^ 1u, hg));

@@ -272,13 +272,8 @@ class DcnSite:
     pipeline (fp16 offset record, dcn_fused.cuh), kept for A/B timing only - its fp16 offsets miss the 1e-3 bar at
     multi-pixel offsets."""
 
-    PAIR_MIN_TILES = 1024       # 16x8-pixel tiles below which mode "pair" hands the call to the single-CTA kernel
-
     def __init__(self, wo, bo, w, b, dg, mode=None):
         self.dg = dg
-        self.small = None
-        self.small_ok = mode is None and "EDVR_B200_DCN_SITE" not in os.environ and dg * 27 <= 224 and w.shape[2] == 3
-        self._src = (wo, bo, w, b) if self.small_ok else None
         self.C = w.shape[1]
         self.main = pack_conv(w, b)
         mode = mode or os.environ.get("EDVR_B200_DCN_SITE", "pair")
@@ -343,12 +338,6 @@ class DcnSite:
             return
         e = _epi(pc.b, act, out16, out_nchw=out_nchw, nchw_C=pc.cout)
         am = None if absmean is None else absmean.data_ptr()
-        if self.mode == "pair" and N * ((H + 15) // 16) * ((W + 7) // 8) < self.PAIR_MIN_TILES and self.small_ok:
-            # few tiles: the single-CTA kernel wins (one tile per SM instead of per CTA pair, shorter prologue; 65 vs 74 us for 16
-            # EDVR-M frames of 64x64)
-            if self.small is None:
-                self.small = DcnSite(*self._src, self.dg, mode="fused")
-            return self.small(x, feat, out16, act, absmean, record, out_nchw)
         if self.mode == "pair":
             with _Rec("dcn_site", 1, flops + 2.0 * N * H * W * self.n_off * pc.cin * 9, f"{N}x{H}x{W} C{x.C} pair"):
                 L.check(L.lib().eb_dcn_site_pair(L.ptr(x.t), x.pix_stride, x.ch_off, N, H, W, x.C, self.dg,

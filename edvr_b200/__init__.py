@@ -3,6 +3,7 @@
     from edvr_b200 import EDVR, PCDAlignment, TSAFusion, ResidualBlockNoBN, PredeblurModule     # drop-in module types
     from edvr_b200 import DCNv2Pack, ModulatedDeformConvPack, modulated_deform_conv, deform_conv # dcn operator API
     from edvr_b200 import EDVREngine                                                           # fused inference executor
+    from edvr_b200 import read_img_seq, tensor2img                                               # frame staging on the device
 """
 _EXPORTS = {
     "EDVR": "edvr", "PCDAlignment": "edvr", "TSAFusion": "edvr", "ResidualBlockNoBN": "edvr", "PredeblurModule": "edvr",
@@ -10,6 +11,7 @@ _EXPORTS = {
     "DCNv2Pack": "dcn", "ModulatedDeformConv": "dcn", "ModulatedDeformConvPack": "dcn", "modulated_deform_conv": "dcn",
     "DeformConv": "dcn", "DeformConvPack": "dcn", "deform_conv": "dcn",
     "EDVREngine": "engine",
+    "read_img_seq": "img", "tensor2img": "img", "frames_to_tensor": "img", "tensor_to_bytes": "img",
 }
 __all__ = sorted(_EXPORTS)
 

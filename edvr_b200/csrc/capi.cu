@@ -1247,6 +1247,28 @@ int eb_upsample2x(const void* src, int sps, int sco, void* dst, int dps, int dco
     return check_launch("upsample2x");
 }
 
+// ---- frame staging either side of the network (read_img_seq / tensor2img arithmetic, bit-exact; elementwise.cuh)
+int eb_frames_u8_to_f32(const void* hwc_u8, float* chw_f32, int N, int H, int W, int bgr2rgb, void* stream) {
+    if (!hwc_u8 || !chw_f32) return fail(EB_ERR_NULLPTR, "frames_u8_to_f32: null pointer");
+    if (N < 0 || H < 1 || W < 1 || static_cast<long long>(H) * W > 0x7fffffffll) return fail(EB_ERR_INVALID_SHAPE, "frames_u8_to_f32: N=%d H=%d W=%d", N, H, W);
+    if (N == 0) return EB_OK;
+    const long long total = static_cast<long long>(N) * H * W;
+    frames_u8_to_f32_kernel<<<grid_1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(hwc_u8), chw_f32, H * W, total, bgr2rgb ? 1 : 0);
+    return check_launch("frames_u8_to_f32");
+}
+
+int eb_tensor2img_u8(const float* chw_f32, void* hwc_u8, int N, int C, int H, int W, int rgb2bgr, float lo, float hi, void* stream) {
+    if (!chw_f32 || !hwc_u8) return fail(EB_ERR_NULLPTR, "tensor2img_u8: null pointer");
+    if (N < 0 || (C != 1 && C != 3) || H < 1 || W < 1 || static_cast<long long>(H) * W > 0x7fffffffll || !(hi > lo))
+        return fail(EB_ERR_INVALID_SHAPE, "tensor2img_u8: N=%d C=%d H=%d W=%d range [%g, %g]", N, C, H, W, lo, hi);
+    if (N == 0) return EB_OK;
+    const long long total = static_cast<long long>(N) * H * W;
+    tensor2img_u8_kernel<<<grid_1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        chw_f32, static_cast<uint8_t*>(hwc_u8), C, H * W, total, rgb2bgr ? 1 : 0, lo, hi);
+    return check_launch("tensor2img_u8");
+}
+
 int eb_pool_max_avg(const void* src, int sps, int sco, void* dst, int dps, int dco, int N, int H, int W, int C,
                     void* stream) {
     if (!view_ok(src, sps, sco, C) || !view_ok(dst, dps, dco, 2 * C)) return fail(EB_ERR_ALIGNMENT, "pool: bad view");

@@ -382,6 +382,45 @@ __global__ void add_base_kernel(const float* __restrict__ base, long long base_i
     }
 }
 
+// ------------------------------------------------------------------ frame staging either side of the network
+// Decoded frames -> network input: what read_img_seq does after cv2.imread (basicsr/data/data_util.py:28-32, img2tensor
+// basicsr/utils/img_util.py:22-27): uint8 [N][H][W][3] BGR -> fp32 [N][3][H][W] RGB (bgr2rgb) = u / 255, a correctly rounded
+// fp32 division (the library is built with --use_fast_math: __fdiv_rn keeps the IEEE quotient).  Bit-exact.
+__global__ void frames_u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int HW, long long total,
+                                        int bgr2rgb) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long n = i / HW;
+        const int p = static_cast<int>(i - n * HW);
+        const uint8_t* s = src + i * 3;
+        float* d = dst + n * 3 * HW + p;
+        const float c0 = __fdiv_rn(static_cast<float>(s[0]), 255.0f), c1 = __fdiv_rn(static_cast<float>(s[1]), 255.0f),
+                    c2 = __fdiv_rn(static_cast<float>(s[2]), 255.0f);
+        d[0] = bgr2rgb ? c2 : c0;
+        d[HW] = c1;
+        d[2 * static_cast<long long>(HW)] = bgr2rgb ? c0 : c2;
+    }
+}
+// Network output -> image bytes: tensor2img with out_type uint8 (basicsr/utils/img_util.py:62-97): clamp to [lo, hi],
+// (x - lo) / (hi - lo), CHW -> HWC (RGB -> BGR for 3 channels), round half to even of x * 255 in fp32, uint8.  Bit-exact.
+__global__ void tensor2img_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int C, int HW, long long total,
+                                     int rgb2bgr, float lo, float hi) {
+    const float span = __fsub_rn(hi, lo);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long n = i / HW;
+        const int p = static_cast<int>(i - n * HW);
+        const float* s = src + n * C * HW + p;
+        uint8_t* d = dst + i * C;
+        for (int c = 0; c < C; ++c) {
+            const float x = s[static_cast<long long>(c) * HW];
+            const float v = fminf(fmaxf(x, lo), hi);
+            const float q = rintf(__fmul_rn(__fdiv_rn(__fsub_rn(v, lo), span), 255.0f));
+            d[(rgb2bgr && C == 3) ? 2 - c : c] = static_cast<uint8_t>(static_cast<int>(q));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ bilinear x2 (align_corners=False)
 // out[2k] = .25 in[k-1] + .75 in[k]; out[2k+1] = .75 in[k] + .25 in[k+1]; edges replicate (nn.Upsample(scale_factor=2,
 // mode='bilinear', align_corners=False): edvr_arch.py:68,112-115,157).

@@ -225,6 +225,12 @@ int eb_add_base(const float* base, long long base_img_stride, int scale, float* 
 int eb_upsample2x(const void* src, int src_pix_stride, int src_ch_off, void* dst, int dst_pix_stride,
                   int dst_ch_off, int N, int H, int W, int C, float mul, const void* add,
                   int add_pix_stride, int add_ch_off, void* stream);
+/* ---- frame staging either side of the network: the arithmetic of read_img_seq after cv2.imread
+ * (basicsr/data/data_util.py:28-32 + img2tensor, utils/img_util.py:22-27) and of tensor2img with out_type uint8
+ * (utils/img_util.py:62-97), bit-exact.  uint8 images are [N][H][W][C] (OpenCV order, BGR), tensors fp32 [N][C][H][W]. */
+int eb_frames_u8_to_f32(const void* hwc_u8, float* chw_f32, int N, int H, int W, int bgr2rgb, void* stream);
+int eb_tensor2img_u8(const float* chw_f32, void* hwc_u8, int N, int C /* 1 or 3 */, int H, int W, int rgb2bgr,
+                     float lo, float hi, void* stream);
 /* MaxPool2d(3,2,1) -> dst[.., 0:C) and AvgPool2d(3,2,1, count_include_pad) -> dst[.., C:2C) */
 int eb_pool_max_avg(const void* src, int src_pix_stride, int src_ch_off, void* dst,
                     int dst_pix_stride, int dst_ch_off, int N, int H, int W, int C, void* stream);

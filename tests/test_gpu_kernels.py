@@ -766,3 +766,61 @@ def test_edvr_full_size_shape_determinism_and_batch_consistency():
     y0 = eng.forward(x[:1].contiguous())
     assert torch.equal(y0[0], y[0])
     assert float(eng.offset_absmeans().max()) < 50
+
+
+# ---- frame staging either side of the network: edvr_b200/img.py, bit-exact ------------------------------
+def test_frame_staging_matches_reference_golden_bit_exact(ops):
+    """eb_frames_u8_to_f32 / eb_tensor2img_u8 against the fixture recorded from the unmodified reference helpers
+    (tests/golden/img_ref_import.npz, oracle/make_golden_img.py) and against oracle/img_ref.py: byte / fp32-bit equality,
+    incl. values outside [0, 1], products on k + 0.5 (round half to even), gray images, min_max = (-1, 1), RGB kept."""
+    from edvr_b200 import frames_to_tensor, tensor2img
+    from oracle import img_ref
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "img_ref_import.npz"))
+    x = frames_to_tensor(torch.from_numpy(z["frames"]).cuda())
+    assert np.array_equal(x.cpu().numpy().view(np.uint32), z["x"].view(np.uint32))
+    out = torch.from_numpy(z["out"]).cuda()
+    assert np.array_equal(tensor2img([out]), z["y"])
+    assert np.array_equal(tensor2img(out, rgb2bgr=False), z["y_rgb"])
+    g = tensor2img(out[:, :1])
+    assert g.shape == z["gray"].shape and np.array_equal(g, z["gray"])
+    assert np.array_equal(tensor2img(out * 2 - 1, min_max=(-1, 1)), z["y_pm1"])
+    assert np.array_equal(tensor2img(out[0, 0]), img_ref.tensor2img(z["out"][0, 0]))
+    both = tensor2img([out, out[:, :1]])
+    assert isinstance(both, list) and np.array_equal(both[0], z["y"]) and np.array_equal(both[1], z["gray"])
+    f = tensor2img(out, out_type=np.float32)
+    assert f.dtype == np.float32 and f.shape == (12, 18, 3) and float(f.min()) >= 0.0 and float(f.max()) <= 1.0
+    with pytest.raises(NotImplementedError):
+        tensor2img(out.cpu())
+    with pytest.raises(NotImplementedError):
+        tensor2img(torch.zeros(2, 3, 4, 4, device="cuda"))
+    with pytest.raises(TypeError):
+        tensor2img("not a tensor")
+
+
+def test_frame_staging_full_size_round_trip_and_files(ops, tmp_path):
+    """Size-independent properties at the BASELINE frame sizes: every byte survives frames -> [0, 1] floats -> bytes
+    (7 LR frames 180x320 and one HR frame 720x1280, ragged sizes too), the kernels agree with the oracle on them, and
+    read_img_seq on PNG files equals the oracle applied to the decoded frames."""
+    import cv2
+    from edvr_b200 import frames_to_tensor, read_img_seq, tensor2img
+    from oracle import img_ref
+    rng = np.random.default_rng(1)
+    for shape in ((7, 180, 320, 3), (1, 720, 1280, 3), (2, 37, 53, 3)):
+        frames = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        x = frames_to_tensor(torch.from_numpy(frames).cuda())
+        assert np.array_equal(x.cpu().numpy().view(np.uint32), img_ref.frames_to_tensor(frames).view(np.uint32))
+        for i in range(shape[0]):
+            assert np.array_equal(tensor2img(x[i]), frames[i])
+    hr = torch.randn(1, 3, 720, 1280, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2)) * 0.4 + 0.5
+    assert np.array_equal(tensor2img(hr), img_ref.tensor2img(hr.cpu().numpy()))
+    frames = rng.integers(0, 256, size=(3, 21, 34, 3), dtype=np.uint8)
+    paths = []
+    for i, f in enumerate(frames):
+        paths.append(str(tmp_path / f"{i:08d}.png"))
+        assert cv2.imwrite(paths[-1], f)
+    want = img_ref.frames_to_tensor(frames)
+    for arg in (paths, str(tmp_path)):
+        got = read_img_seq(arg)
+        assert got.is_cuda and np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    got = read_img_seq(paths, require_mod_crop=True, scale=4)
+    assert np.array_equal(got.cpu().numpy(), want[:, :, :20, :32])

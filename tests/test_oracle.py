@@ -183,3 +183,36 @@ def test_edvr_port_matches_reference_import_live():
         y = net(x)
     assert torch.equal(y, edvr_ref.edvr_forward(sd, x))
     assert set(sd) == set(net.state_dict())
+
+
+# ---- frame staging either side of the network: oracle/img_ref.py ---------------------------------------
+GOLDEN_IMG = os.path.join(os.path.dirname(__file__), "golden", "img_ref_import.npz")
+
+
+def test_img_oracle_matches_reference_import_golden_bit_exact():
+    """oracle/img_ref.py against tests/golden/img_ref_import.npz, recorded from the UNMODIFIED basicsr.utils.img_util /
+    data_util arithmetic (oracle/make_golden_img.py): byte and fp32-bit equality."""
+    from oracle import img_ref
+    z = np.load(GOLDEN_IMG)
+    x = img_ref.frames_to_tensor(z["frames"])
+    assert x.dtype == np.float32 and np.array_equal(x.view(np.uint32), z["x"].view(np.uint32))
+    assert np.array_equal(img_ref.tensor2img(z["out"]), z["y"])
+    assert np.array_equal(img_ref.tensor2img(z["out"], rgb2bgr=False), z["y_rgb"])
+    assert np.array_equal(img_ref.tensor2img(z["out"][:, :1]), z["gray"]) and z["gray"].ndim == 2
+    assert np.array_equal(img_ref.tensor2img(z["out"] * 2 - 1, min_max=(-1, 1)), z["y_pm1"])
+    # every byte survives the round trip frames -> [0, 1] floats -> bytes
+    ramp = np.arange(256, dtype=np.uint8).reshape(1, 16, 16, 1).repeat(3, axis=3)
+    assert np.array_equal(img_ref.tensor2img(img_ref.frames_to_tensor(ramp)[0]), ramp[0])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/basicsr"), reason="reference tree not mounted")
+def test_img_oracle_matches_live_reference_import():
+    from oracle import img_ref, make_golden_img
+    img2tensor, tensor2img = make_golden_img.reference_functions()
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, size=(2, 9, 11, 3), dtype=np.uint8)
+    ref = torch.stack(img2tensor([f.astype(np.float32) / 255. for f in frames], bgr2rgb=True, float32=True), 0).numpy()
+    assert np.array_equal(img_ref.frames_to_tensor(frames).view(np.uint32), ref.view(np.uint32))
+    out = rng.normal(0.5, 0.6, size=(1, 3, 13, 7)).astype(np.float32)
+    assert np.array_equal(img_ref.tensor2img(out), tensor2img(torch.from_numpy(out)))
+    assert np.array_equal(img_ref.tensor2img(out[0, 0]), tensor2img(torch.from_numpy(out[0, 0])))

@@ -68,6 +68,8 @@ _SIGS = {
                                  c_void_p, c_int, ctypes.POINTER(Epilogue), c_void_p, c_void_p]),
     "eb_mdcn_forward_workspace": (c_size_t, [c_int] * 7),
     "eb_mdcn_forward": (c_int, [c_void_p] * 6 + [c_int] * 12 + [c_void_p, c_size_t, c_void_p]),
+    "eb_mdcn_forward_f16_workspace": (c_size_t, [c_int] * 8),
+    "eb_mdcn_forward_f16": (c_int, [c_void_p] * 6 + [c_int] * 12 + [c_void_p, c_size_t, c_void_p]),
     "eb_mdcn_backward_workspace": (c_size_t, [c_int] * 10),
     "eb_mdcn_backward": (c_int, [c_void_p] * 10 + [c_int] * 12 + [c_void_p, c_size_t, c_void_p]),
     "eb_selftest_mma_rate": (c_int, [c_int] * 10 + [c_void_p, c_void_p, c_void_p]),

@@ -940,9 +940,10 @@ struct Geo2 { int sh, sw, ph, pw, dh, dw; };
 // Shared implementation of the reference-layout forward: mask == NULL and bias == NULL give DCNv1.
 int dcn_forward_impl(const char* who, const float* x, const float* offset, const float* mask, const float* weight,
                      const float* bias, float* out, int N, int C, int H, int W, int Cout, int kh, int kw, Geo2 g,
-                     int groups, int dg, void* workspace, size_t workspace_bytes, void* stream, bool need_mask) {
+                     int groups, int dg, void* workspace, size_t workspace_bytes, void* stream, bool need_mask,
+                     const __half* x_half = nullptr) {      // x_half: the input as an fp16 NCHW tensor instead of x
     if (N == 0 && C > 0 && H > 0 && W > 0 && Cout > 0) return EB_OK;   // empty batch: nothing to do, pointers may be NULL
-    if (!x || !offset || (need_mask && !mask) || !weight || !out) return fail(EB_ERR_NULLPTR, "%s: null pointer", who);
+    if ((!x && !x_half) || !offset || (need_mask && !mask) || !weight || !out) return fail(EB_ERR_NULLPTR, "%s: null pointer", who);
     if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || g.sh < 1 || g.sw < 1 || g.ph < 0 || g.pw < 0 ||
         g.dh < 1 || g.dw < 1 || groups < 1 || dg < 1 || C % dg || C % groups || Cout % groups)
         return fail(EB_ERR_INVALID_SHAPE, "%s: invalid shape", who);
@@ -966,7 +967,8 @@ int dcn_forward_impl(const char* who, const float* x, const float* offset, const
     float* bpack = reinterpret_cast<float*>(ws);
     {
         dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
-        nchw_f32_to_nhwc_f16_kernel<<<grid, block, 0, st>>>(x, x16, C, H * W, C, 0);
+        if (x_half) nchw_f16_to_nhwc_f16_kernel<<<grid, block, 0, st>>>(x_half, x16, C, H * W);
+        else nchw_f32_to_nhwc_f16_kernel<<<grid, block, 0, st>>>(x, x16, C, H * W, C, 0);
         if (int rc = check_launch("nchw_to_nhwc")) return rc;
     }
     if (int rc = eb_pack_weight(weight, Cout, C, kh * kw, nullptr, BN, nt, 0, wpack, stream)) return rc;
@@ -993,6 +995,59 @@ int eb_mdcn_forward(const float* x, const float* offset, const float* mask, cons
                     size_t workspace_bytes, void* stream) {
     return dcn_forward_impl("mdcn_forward", x, offset, mask, weight, bias, out, N, C, H, W, Cout, kh, kw,
                             Geo2{stride, stride, pad, pad, dil, dil}, groups, dg, workspace, workspace_bytes, stream, true);
+}
+
+/* Half-precision operator entry: what the reference's AT_DISPATCH_FLOATING_TYPES_AND_HALF instantiation answers for
+ * at::Half tensors (deform_conv_cuda_kernel.cu:781-800, deform_conv_cuda.cpp:490-569).  All tensors fp16 in the reference
+ * layouts; the arithmetic is the library's (fp16 tensor-core operands - the input is used as given, no re-rounding -, fp32
+ * offsets / masks / accumulation), the result is rounded to fp16 once. */
+size_t eb_mdcn_forward_f16_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int dg) {
+    // fp32 copies of offset, mask, weight, bias and the fp32 result; sized for outputs of up to 2 x H x W pixels
+    return eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw) +
+           up256(static_cast<size_t>(N) * dg * 3 * kh * kw * H * W * 4) * 2 +          // offset + mask (Ho*Wo <= H*W for pad <= k/2)
+           up256(static_cast<size_t>(Cout) * C * kh * kw * 4) + up256(static_cast<size_t>(Cout) * 4) +
+           up256(static_cast<size_t>(N) * Cout * H * W * 4) * 2;
+}
+
+int eb_mdcn_forward_f16(const void* x, const void* offset, const void* mask, const void* weight, const void* bias, void* out,
+                        int N, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil, int groups, int dg,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (N == 0 && C > 0 && H > 0 && W > 0 && Cout > 0) return EB_OK;
+    if (!x || !offset || !mask || !weight || !out) return fail(EB_ERR_NULLPTR, "mdcn_forward_f16: null pointer");
+    if (N < 0 || C < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || stride < 1 || pad < 0 || dil < 1 || dg < 1)
+        return fail(EB_ERR_INVALID_SHAPE, "mdcn_forward_f16: invalid shape");
+    const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1, Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
+    if (Ho < 1 || Wo < 1) return fail(EB_ERR_INVALID_SHAPE, "mdcn_forward_f16: empty output");
+    if (static_cast<long long>(Ho) * Wo > 2ll * H * W) return fail(EB_ERR_UNSUPPORTED, "mdcn_forward_f16: padding beyond the kernel reach");
+    const size_t need = eb_mdcn_forward_f16_workspace(N, C, H, W, Cout, kh, kw, dg);
+    if (!workspace || workspace_bytes < need) return fail(EB_ERR_WORKSPACE, "mdcn_forward_f16: workspace %zu < %zu", workspace_bytes, need);
+    if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "mdcn_forward_f16: workspace must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    const size_t inner = eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw);
+    uint8_t* cur = ws + inner;
+    auto take = [&](size_t elems) { float* p = reinterpret_cast<float*>(cur); cur += up256(elems * 4); return p; };
+    const long long n_off = static_cast<long long>(N) * dg * 2 * kh * kw * Ho * Wo, n_mask = n_off / 2;
+    const long long n_w = static_cast<long long>(Cout) * (C / (groups > 0 ? groups : 1)) * kh * kw, n_out = static_cast<long long>(N) * Cout * Ho * Wo;
+    float* off32 = take(static_cast<size_t>(N) * dg * 3 * kh * kw * H * W);
+    float* mask32 = take(static_cast<size_t>(N) * dg * 3 * kh * kw * H * W);
+    float* w32 = take(static_cast<size_t>(Cout) * C * kh * kw);
+    float* b32 = take(Cout);
+    float* out32 = take(static_cast<size_t>(N) * Cout * H * W * 2);
+    auto to_f32 = [&](const void* src, float* dst, long long n) {
+        half_to_float_kernel<<<grid_1d(n, 256), 256, 0, st>>>(static_cast<const __half*>(src), dst, n);
+    };
+    to_f32(offset, off32, n_off);
+    to_f32(mask, mask32, n_mask);
+    to_f32(weight, w32, n_w);
+    if (bias) to_f32(bias, b32, Cout);
+    if (int rc = check_launch("half_to_float")) return rc;
+    if (int rc = dcn_forward_impl("mdcn_forward_f16", nullptr, off32, mask32, w32, bias ? b32 : nullptr, out32, N, C, H, W, Cout, kh, kw,
+                                  Geo2{stride, stride, pad, pad, dil, dil}, groups, dg, ws, inner, stream, true,
+                                  static_cast<const __half*>(x)))
+        return rc;
+    float_to_half_kernel<<<grid_1d(n_out, 256), 256, 0, st>>>(out32, static_cast<__half*>(out), n_out);
+    return check_launch("float_to_half");
 }
 
 /* DCNv1: deform_conv_forward of the reference extension (deform_conv_ext.cpp:51-67, deform_conv_cuda.cpp:152-237) */

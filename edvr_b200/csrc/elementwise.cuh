@@ -38,6 +38,30 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ src, __hal
                 __float2half_rn(tile[threadIdx.x][i]);
     }
 }
+// half-precision operator entry (eb_mdcn_forward_f16): the same transpose from an fp16 NCHW tensor, and flat converters
+__global__ void nchw_f16_to_nhwc_f16_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int C, int HW) {
+    __shared__ __half tile[32][34];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? src[(static_cast<size_t>(n) * C + c) * HW + p] : __float2half(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C) dst[(static_cast<size_t>(n) * HW + p) * C + c] = tile[threadIdx.x][i];
+    }
+}
+__global__ void half_to_float_kernel(const __half* __restrict__ src, float* __restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dst[i] = __half2float(src[i]);
+}
+__global__ void float_to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dst[i] = __float2half_rn(src[i]);
+}
 __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst,
                                             int C, int HW, int src_pix_stride, int src_ch_off) {
     __shared__ float tile[32][33];

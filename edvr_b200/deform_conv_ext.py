@@ -51,6 +51,17 @@ def modulated_deform_conv_forward(input, weight, bias, ones, offset, mask, outpu
     Cout = weight.shape[0]
     if C != weight.shape[1] * group:
         raise RuntimeError(f"Input shape and kernel channels wont match: ({C} vs {weight.shape[1] * group}).")
+    halves = [input, weight, offset, mask, output] + ([bias] if with_bias else [])
+    if group == 1 and all(t.dtype == torch.float16 and t.is_contiguous() for t in halves):
+        # at::Half tensors (the reference dispatches on them: deform_conv_cuda_kernel.cu:781): the fp16 entry point, no casts
+        need = L.lib().eb_mdcn_forward_f16_workspace(N, C, H, W, Cout, kernel_h, kernel_w, deformable_group)
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=input.device)
+        with torch.cuda.device(input.device):
+            L.check(L.lib().eb_mdcn_forward_f16(L.ptr(input), L.ptr(offset), L.ptr(mask), L.ptr(weight),
+                                                L.ptr(bias if with_bias else None), L.ptr(output), N, C, H, W, Cout, kernel_h,
+                                                kernel_w, stride_h, pad_h, dilation_h, group, deformable_group, L.ptr(ws),
+                                                ws.numel(), L.stream_ptr()), "eb_mdcn_forward_f16")
+        return
     x, w, off, m = _f32(input), _f32(weight), _f32(offset), _f32(mask)
     b = _f32(bias) if with_bias else None
     if group > 1:           # deform_conv_cuda.cpp:536-568: one GEMM per weight group; composed from per-group calls

@@ -178,6 +178,13 @@ int eb_mdcn_forward(const float* x, const float* offset, const float* mask, cons
                     const float* bias /* NULL = no bias */, float* out, int N, int C, int H, int W,
                     int Cout, int kh, int kw, int stride, int pad, int dil, int groups, int dg,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* Half-precision entry (the reference dispatches its kernels on at::Half too: deform_conv_cuda_kernel.cu:781): every tensor
+ * fp16 in the reference layouts.  fp16 tensor-core operands (the input as given), fp32 offsets / masks / accumulation, one
+ * rounding of the result to fp16.  fp64 tensors have no entry point: callers convert (the B1 shim does). */
+size_t eb_mdcn_forward_f16_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int dg);
+int eb_mdcn_forward_f16(const void* x, const void* offset, const void* mask, const void* weight, const void* bias /* or NULL */,
+                        void* out, int N, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
+                        int groups, int dg, void* workspace, size_t workspace_bytes, void* stream);
 size_t eb_mdcn_backward_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int stride,
                                   int pad, int dil);
 int eb_mdcn_backward(const float* x, const float* offset, const float* mask, const float* weight,

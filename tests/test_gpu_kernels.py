@@ -452,6 +452,39 @@ def test_weight_groups_match_oracle(ops, groups, dg):
         assert e[0] < TOL and e[1] < TOL, ("v1 " + nm, e)
 
 
+@pytest.mark.parametrize("shape,geo", [((2, 64, 12, 14, 64, 8), (1, 1, 1)), ((1, 128, 15, 11, 96, 4), (2, 1, 1)),
+                                       ((1, 64, 13, 13, 32, 1), (1, 2, 2))])
+def test_half_precision_operator_entry(ops, shape, geo):
+    """at::Half tensors at the B1 boundary (the reference instantiates its kernels for them: deform_conv_cuda_kernel.cu:781)
+    go through eb_mdcn_forward_f16 without casts.  Checked against the C oracle fed the same fp16-rounded tensors: the
+    kernel's 1e-3 plus one rounding of the result to fp16 (2^-11 relative) - bar 1.5e-3 of max |out|; fp64 tensors take the
+    conversion path of the shim."""
+    from oracle import dcn_oracle
+    from edvr_b200 import deform_conv_ext as ext
+    N, C, H, W, Cout, dg = shape
+    stride, pad, dil = geo
+    Ho, Wo = dcn_oracle.out_hw(H, W, 3, 3, stride, pad, dil)
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(N, C, H, W, generator=g).half()
+    off = (torch.randn(N, dg * 18, Ho, Wo, generator=g) * 2).half()
+    mask = torch.sigmoid(torch.randn(N, dg * 9, Ho, Wo, generator=g)).half()
+    w = ((torch.rand(Cout, C, 3, 3, generator=g) * 2 - 1) / (9 * C) ** 0.5).half()
+    b = (torch.randn(Cout, generator=g) * 0.1).half()
+    ref = dcn_oracle.forward(x.float().numpy(), off.float().numpy(), mask.float().numpy(), w.float().numpy(),
+                             b.float().numpy(), stride, pad, dil, 1, dg)
+    out = torch.full((N, Cout, Ho, Wo), float("nan"), dtype=torch.float16, device="cuda")
+    launches = ops.LAUNCHES[0]
+    ext.modulated_deform_conv_forward(x.cuda(), w.cuda(), b.cuda(), None, off.cuda(), mask.cuda(), out, None, 3, 3, stride,
+                                      stride, pad, pad, dil, dil, 1, dg, True)
+    assert out.dtype == torch.float16 and not torch.isnan(out).any()
+    e = rel_err(out.float().cpu(), ref)
+    assert e[0] < 1.5e-3 and e[1] < 1.5e-3, e
+    out64 = torch.empty(N, Cout, Ho, Wo, dtype=torch.float64, device="cuda")
+    ext.modulated_deform_conv_forward(x.double().cuda(), w.double().cuda(), b.double().cuda(), None, off.double().cuda(),
+                                      mask.double().cuda(), out64, None, 3, 3, stride, stride, pad, pad, dil, dil, 1, dg, True)
+    assert rel_err(out64.float().cpu(), ref)[0] < TOL
+
+
 # ---- DCNv1 (SURVEY §8 row a13): deform_conv_forward / backward_input / backward_parameters -------------------------
 V1_GPU_CASES = {  # N, C, H, W, Cout, dg, (kh, kw), stride, padding, dilation, offset scale
     "iso_dg8": (2, 64, 12, 14, 64, 8, (3, 3), (1, 1), (1, 1), (1, 1), 2.0),

@@ -183,3 +183,45 @@ def test_official_key_map_matches_reference_conversion_script(monkeypatch):
         assert set(saved) == set(keys)
         for k in keys:
             assert official_key(k) == saved[k], (k, official_key(k), saved[k])
+
+
+def test_group_slices_compose_a_grouped_dcn_from_single_group_calls():
+    """Host logic of the weight-group composition (edvr_b200.ops.group_slices, used by the B1 / B2 boundary for groups > 1;
+    deform_conv_cuda.cpp:536-568): running the ORACLE once per slice with groups = 1 and concatenating must equal the oracle's
+    own grouped forward, for deformable groups that are a multiple of the weight groups and for shared deformable groups."""
+    import numpy as np
+    import torch
+    from edvr_b200.ops import group_slices
+    from oracle import dcn_oracle
+    g = torch.Generator().manual_seed(4)
+    N, C, H, W, Cout = 1, 16, 6, 7, 8
+    for groups, dg in ((2, 2), (2, 4), (4, 2), (2, 1)):
+        x = torch.randn(N, C, H, W, generator=g).numpy()
+        off = (torch.randn(N, dg * 18, H, W, generator=g) * 2).numpy()
+        mask = torch.rand(N, dg * 9, H, W, generator=g).numpy()
+        w = torch.randn(Cout, C // groups, 3, 3, generator=g).numpy()
+        b = torch.randn(Cout, generator=g).numpy()
+        want = dcn_oracle.forward(x, off, mask, w, b, 1, 1, 1, groups, dg)
+        parts = []
+        for gi in range(groups):
+            cs, os_, fs, ms, dgg = group_slices(C, Cout, 9, groups, dg, gi)
+            parts.append(dcn_oracle.forward(np.ascontiguousarray(x[:, cs]), np.ascontiguousarray(off[:, fs]),
+                                            np.ascontiguousarray(mask[:, ms]), np.ascontiguousarray(w[os_]),
+                                            np.ascontiguousarray(b[os_]), 1, 1, 1, 1, dgg))
+        got = np.concatenate(parts, 1)
+        assert np.abs(got - want).max() < 1e-5 * np.abs(want).max(), (groups, dg)
+    with pytest.raises(RuntimeError, match="one must divide the other"):
+        group_slices(24, 24, 9, 2, 3, 0)
+
+
+def test_frame_staging_has_no_cpu_fallback():
+    import torch
+    from edvr_b200 import frames_to_tensor, tensor2img, tensor_to_bytes
+    with pytest.raises(NotImplementedError):
+        tensor2img(torch.zeros(3, 4, 4))
+    with pytest.raises(NotImplementedError):
+        frames_to_tensor(torch.zeros(1, 4, 4, 3, dtype=torch.uint8))
+    with pytest.raises(NotImplementedError):
+        tensor_to_bytes(torch.zeros(1, 3, 4, 4))
+    with pytest.raises(TypeError):
+        tensor2img(3.0)

@@ -1002,11 +1002,11 @@ int eb_mdcn_forward(const float* x, const float* offset, const float* mask, cons
  * layouts; the arithmetic is the library's (fp16 tensor-core operands - the input is used as given, no re-rounding -, fp32
  * offsets / masks / accumulation), the result is rounded to fp16 once. */
 size_t eb_mdcn_forward_f16_workspace(int N, int C, int H, int W, int Cout, int kh, int kw, int dg) {
-    // fp32 copies of offset, mask, weight, bias and the fp32 result; sized for outputs of up to 2 x H x W pixels
-    return eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw) +
-           up256(static_cast<size_t>(N) * dg * 3 * kh * kw * H * W * 4) * 2 +          // offset + mask (Ho*Wo <= H*W for pad <= k/2)
-           up256(static_cast<size_t>(Cout) * C * kh * kw * 4) + up256(static_cast<size_t>(Cout) * 4) +
-           up256(static_cast<size_t>(N) * Cout * H * W * 4) * 2;
+    // fp32 copies of offset, mask, weight, bias and the fp32 result, sized for outputs of at most H x W pixels (checked by
+    // eb_mdcn_forward_f16: the usual "same" or strided geometries)
+    const size_t hw = static_cast<size_t>(H) * W, k = static_cast<size_t>(kh) * kw;
+    return eb_mdcn_forward_workspace(N, C, H, W, Cout, kh, kw) + up256(N * dg * 2 * k * hw * 4) + up256(N * dg * k * hw * 4) +
+           up256(static_cast<size_t>(Cout) * C * k * 4) + up256(static_cast<size_t>(Cout) * 4) + up256(N * Cout * hw * 4);
 }
 
 int eb_mdcn_forward_f16(const void* x, const void* offset, const void* mask, const void* weight, const void* bias, void* out,
@@ -1018,7 +1018,8 @@ int eb_mdcn_forward_f16(const void* x, const void* offset, const void* mask, con
         return fail(EB_ERR_INVALID_SHAPE, "mdcn_forward_f16: invalid shape");
     const int Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1, Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
     if (Ho < 1 || Wo < 1) return fail(EB_ERR_INVALID_SHAPE, "mdcn_forward_f16: empty output");
-    if (static_cast<long long>(Ho) * Wo > 2ll * H * W) return fail(EB_ERR_UNSUPPORTED, "mdcn_forward_f16: padding beyond the kernel reach");
+    if (static_cast<long long>(Ho) * Wo > static_cast<long long>(H) * W)
+        return fail(EB_ERR_UNSUPPORTED, "mdcn_forward_f16: output larger than the input (padding beyond the kernel reach)");
     const size_t need = eb_mdcn_forward_f16_workspace(N, C, H, W, Cout, kh, kw, dg);
     if (!workspace || workspace_bytes < need) return fail(EB_ERR_WORKSPACE, "mdcn_forward_f16: workspace %zu < %zu", workspace_bytes, need);
     if (!al16(workspace)) return fail(EB_ERR_ALIGNMENT, "mdcn_forward_f16: workspace must be 16-byte aligned");
@@ -1029,11 +1030,11 @@ int eb_mdcn_forward_f16(const void* x, const void* offset, const void* mask, con
     auto take = [&](size_t elems) { float* p = reinterpret_cast<float*>(cur); cur += up256(elems * 4); return p; };
     const long long n_off = static_cast<long long>(N) * dg * 2 * kh * kw * Ho * Wo, n_mask = n_off / 2;
     const long long n_w = static_cast<long long>(Cout) * (C / (groups > 0 ? groups : 1)) * kh * kw, n_out = static_cast<long long>(N) * Cout * Ho * Wo;
-    float* off32 = take(static_cast<size_t>(N) * dg * 3 * kh * kw * H * W);
-    float* mask32 = take(static_cast<size_t>(N) * dg * 3 * kh * kw * H * W);
+    float* off32 = take(static_cast<size_t>(N) * dg * 2 * kh * kw * H * W);
+    float* mask32 = take(static_cast<size_t>(N) * dg * kh * kw * H * W);
     float* w32 = take(static_cast<size_t>(Cout) * C * kh * kw);
     float* b32 = take(Cout);
-    float* out32 = take(static_cast<size_t>(N) * Cout * H * W * 2);
+    float* out32 = take(static_cast<size_t>(N) * Cout * H * W);
     auto to_f32 = [&](const void* src, float* dst, long long n) {
         half_to_float_kernel<<<grid_1d(n, 256), 256, 0, st>>>(static_cast<const __half*>(src), dst, n);
     };

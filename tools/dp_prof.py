@@ -1,10 +1,11 @@
-"""Where does the CTA-pair DCN site kernel (dcn_pair.cuh) wait?  Builds a -DDP_PROF copy of the library into
-gpurun_out/libedvr_b200_prof.so (run `python tools/dp_prof.py --build` on the CPU box first; the .so travels with gpurun... no:
-gpurun_out is not pushed, so the build goes to edvr_b200/libedvr_b200_prof.so), then on the GPU runs one launch per
-EDVR_B200_DP_DBG setting and prints, per role, the mean cycles per tile spent in each wait.
+"""Where does the CTA-pair DCN site kernel (dcn_pair.cuh) wait?  `--build` compiles a -DDP_PROF copy of the library into
+edvr_b200/libedvr_b200_prof.so (in-tree, so that it travels to the GPU box; git-ignored like every .so); the run loads it
+through EDVR_B200_LIB, launches the site once per EDVR_B200_DP_DBG setting and prints, per role, the mean cycles per tile
+spent inside each kind of wait (profiles/r02_dcn_pair_role_timing.txt).
 
-    python tools/dp_prof.py --build            # CPU box
-    python tools/dp_prof.py [N] [sigma] [dbg,dbg,...]   # GPU box
+    python tools/dp_prof.py --build                               # where nvcc is
+    python tools/dp_prof.py --build-variant NAME -DDP_CFG_...     # A/B builds of the ring depths / window margin
+    python tools/dp_prof.py [N] [sigma] [dbg,dbg,...]             # on the GPU box
 """
 import ctypes
 import os
